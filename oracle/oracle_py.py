@@ -1,0 +1,132 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for the checker libraries.
+
+* ``run_ref``    : oracle/_ref/libref_<system>_<algo>_<prec>.so -- the reference's own kernel source
+                   compiled for the host (built by oracle/Makefile from /root/reference).
+* ``run_oracle`` : oracle/liboracle_perthread.so -- our CPU restatement of the same algorithm.
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import this
+module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class _Options(C.Structure):
+    _fields_ = [("InitialTimeStep", C.c_double), ("MaximumTimeStep", C.c_double), ("MinimumTimeStep", C.c_double),
+                ("TimeStepGrowLimit", C.c_double), ("TimeStepShrinkLimit", C.c_double),
+                ("DenseOutputMinimumTimeStep", C.c_double), ("DenseOutputSaveFrequency", C.c_int),
+                ("NumberOfActiveThreads", C.c_int), ("Phases", C.c_int), ("HostThreads", C.c_int)]
+
+
+class _Buffers(C.Structure):
+    _fields_ = [("NT", C.c_int)] + [(n, C.c_void_p) for n in (
+        "TimeDomain", "ActualState", "ActualTime", "ControlParameters", "SharedParameters",
+        "IntegerSharedParameters", "Accessories", "IntegerAccessories", "RelativeTolerance",
+        "AbsoluteTolerance", "EventTolerance", "EventDirection", "DenseOutputIndex",
+        "DenseOutputTimeInstances", "DenseOutputStates", "steps_attempted", "steps_accepted")]
+
+
+class _Shape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("SD", "NCP", "NSP", "NISP", "NE", "NA", "NIA", "NDO", "Algorithm", "Precision")]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None or a.size == 0:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def _pack(wl, buffers, phases, host_threads):
+    """Build the C structs for a run that mutates ``buffers`` in place."""
+    shape, NT = wl.shape, buffers.NT
+    o = wl.options.resolved(shape, NT)
+    att = np.zeros(NT, np.int64)
+    acc = np.zeros(NT, np.int64)
+    keep = [o.RelativeTolerance, o.AbsoluteTolerance, o.EventTolerance, o.EventDirection, att, acc]
+    cb = _Buffers(NT, _ptr(buffers.TimeDomain), _ptr(buffers.ActualState), _ptr(buffers.ActualTime),
+                  _ptr(buffers.ControlParameters), _ptr(buffers.SharedParameters),
+                  _ptr(buffers.IntegerSharedParameters), _ptr(buffers.Accessories),
+                  _ptr(buffers.IntegerAccessories), _ptr(o.RelativeTolerance), _ptr(o.AbsoluteTolerance),
+                  _ptr(o.EventTolerance), _ptr(o.EventDirection), _ptr(buffers.DenseIndex),
+                  _ptr(buffers.DenseTime), _ptr(buffers.DenseState), _ptr(att), _ptr(acc))
+    co = _Options(o.InitialTimeStep, o.MaximumTimeStep, o.MinimumTimeStep, o.TimeStepGrowLimit,
+                  o.TimeStepShrinkLimit, o.DenseOutputMinimumTimeStep, o.DenseOutputSaveFrequency,
+                  o.ActiveNumberOfThreads, phases, host_threads)
+    return cb, co, att, acc, keep
+
+
+def _prec_tag(dtype) -> str:
+    return "f64" if np.dtype(dtype) == np.float64 else "f32"
+
+
+def ref_library_path(wl, fast: bool = False) -> str:
+    from_algo = {0: "rk4", 1: "rkck45"}[wl.shape.Algorithm]
+    name = f"libref_{wl.name}_{from_algo}_{_prec_tag(wl.shape.dtype)}{'_fast' if fast else ''}.so"
+    return os.path.join(HERE, "_ref", name)
+
+
+def ref_available(wl, fast: bool = False) -> bool:
+    return os.path.exists(ref_library_path(wl, fast))
+
+
+def _check_shape(s: _Shape, wl):
+    sh = wl.shape
+    got = (s.SD, s.NCP, s.NSP, s.NISP, s.NE, s.NA, s.NIA, s.NDO, s.Algorithm, s.Precision)
+    want = (sh.SD, sh.NCP, sh.NSP, sh.NISP, sh.NE, sh.NA, sh.NIA, sh.NDO, sh.Algorithm, np.dtype(sh.dtype).itemsize)
+    if got != want:
+        raise ValueError(f"checker library shape {got} does not match workload shape {want}")
+
+
+def run_ref(wl, buffers=None, phases: Optional[int] = None, host_threads: int = 1, fast: bool = False
+            ) -> Tuple[object, np.ndarray, np.ndarray]:
+    """Run the host-compiled REFERENCE kernel; returns (buffers_after, attempted, accepted)."""
+    lib = C.CDLL(ref_library_path(wl, fast))
+    s = _Shape()
+    lib.ref_perthread_shape(C.byref(s))
+    _check_shape(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    cb, co, att, acc, _keep = _pack(wl, out, wl.phases if phases is None else phases, host_threads)
+    lib.ref_perthread_run.restype = C.c_int
+    rc = lib.ref_perthread_run(C.byref(cb), C.byref(co))
+    if rc != 0:
+        raise RuntimeError(f"ref_perthread_run failed: {rc}")
+    return out, att, acc
+
+
+_ORACLE = {}
+
+
+def oracle_library_path(fast: bool = False) -> str:
+    return os.path.join(HERE, "liboracle_perthread_fast.so" if fast else "liboracle_perthread.so")
+
+
+def run_oracle(wl, buffers=None, phases: Optional[int] = None, host_threads: int = 1, fast: bool = False
+               ) -> Tuple[object, np.ndarray, np.ndarray]:
+    """Run our CPU restatement; returns (buffers_after, attempted, accepted)."""
+    path = oracle_library_path(fast)
+    lib = _ORACLE.get(path)
+    if lib is None:
+        lib = _ORACLE[path] = C.CDLL(path)
+        lib.oracle_perthread_run.restype = C.c_int
+        lib.oracle_perthread_shape.restype = C.c_int
+    sh = wl.shape
+    prec = np.dtype(sh.dtype).itemsize
+    s = _Shape()
+    rc = lib.oracle_perthread_shape(wl.name.encode(), sh.Algorithm, prec, sh.NDO, C.byref(s))
+    if rc != 0:
+        raise KeyError(f"oracle has no system {wl.name!r} for algorithm {sh.Algorithm} precision {prec}")
+    _check_shape(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    cb, co, att, acc, _keep = _pack(wl, out, wl.phases if phases is None else phases, host_threads)
+    rc = lib.oracle_perthread_run(wl.name.encode(), sh.Algorithm, prec, sh.NDO, C.byref(cb), C.byref(co))
+    if rc != 0:
+        raise RuntimeError(f"oracle_perthread_run failed: {rc}")
+    return out, att, acc
