@@ -66,7 +66,7 @@ typedef struct oracle_perthread_shape
 //   void ref_perthread_shape(oracle_perthread_shape*);
 //   int  ref_perthread_run(const oracle_perthread_buffers*, const oracle_perthread_options*);
 // Exported by liboracle_perthread.so:
-//   int  oracle_perthread_shape(const char* system, int algorithm, int precision, int ndo, oracle_perthread_shape*);
+//   int  oracle_perthread_query_shape(const char* system, int algorithm, int precision, int ndo, oracle_perthread_shape*);
 //   int  oracle_perthread_run(const char* system, int algorithm, int precision, int ndo,
 //                             const oracle_perthread_buffers*, const oracle_perthread_options*);
 

@@ -108,19 +108,25 @@ def oracle_library_path(fast: bool = False) -> str:
     return os.path.join(HERE, "liboracle_perthread_fast.so" if fast else "liboracle_perthread.so")
 
 
-def run_oracle(wl, buffers=None, phases: Optional[int] = None, host_threads: int = 1, fast: bool = False
-               ) -> Tuple[object, np.ndarray, np.ndarray]:
-    """Run our CPU restatement; returns (buffers_after, attempted, accepted)."""
+def run_oracle(wl, buffers=None, phases: Optional[int] = None, host_threads: int = 1, fast: bool = False,
+               double_literals: bool = False) -> Tuple[object, np.ndarray, np.ndarray]:
+    """Run our CPU restatement; returns (buffers_after, attempted, accepted).
+
+    ``double_literals`` only matters for float32 runs: True evaluates the system definitions'
+    floating literals in double exactly as the reference's FP32 instantiation does (bit-comparable
+    with oracle/_ref); False is the true-FP32 arithmetic of the CUDA built-in systems."""
     path = oracle_library_path(fast)
     lib = _ORACLE.get(path)
     if lib is None:
         lib = _ORACLE[path] = C.CDLL(path)
         lib.oracle_perthread_run.restype = C.c_int
-        lib.oracle_perthread_shape.restype = C.c_int
+        lib.oracle_perthread_query_shape.restype = C.c_int
     sh = wl.shape
     prec = np.dtype(sh.dtype).itemsize
+    if prec == 4 and double_literals:
+        prec = -4
     s = _Shape()
-    rc = lib.oracle_perthread_shape(wl.name.encode(), sh.Algorithm, prec, sh.NDO, C.byref(s))
+    rc = lib.oracle_perthread_query_shape(wl.name.encode(), sh.Algorithm, prec, sh.NDO, C.byref(s))
     if rc != 0:
         raise KeyError(f"oracle has no system {wl.name!r} for algorithm {sh.Algorithm} precision {prec}")
     _check_shape(s, wl)

@@ -80,7 +80,11 @@ static void run_range(const oracle_perthread_buffers* b, const oracle_perthread_
 
 	std::vector<P> td(2), x(SD), t(1), cp(NCP > 0 ? NCP : 1), acc(NA > 0 ? NA : 1);
 	std::vector<int> acci(NIA > 0 ? NIA : 1), didx(1);
-	std::vector<P> dt(NDO > 0 ? NDO : 1), ds(NDO > 0 ? NDO * SD : 1);
+	// The reference stores the first point of every phase without checking the dense index
+	// (Solver.cuh:179-193), i.e. it writes one slot past NDO per phase once the buffer is full;
+	// give the private buffers that much slack so the harness stays memory-safe.
+	const int slack = o->Phases + 1;
+	std::vector<P> dt(NDO > 0 ? NDO + slack : 1), ds(NDO > 0 ? (NDO + slack) * SD : 1);
 
 	Struct_ThreadConfiguration tc;  tc.GridSize = 1;  tc.BlockSize = 1;  tc.NumberOfActiveThreads = 1;
 	Struct_SharedMemoryUsage   sm;  sm.PreferSharedMemory = 0;  sm.IsAdaptive = (REF_ALGO == RK4 ? 0 : 1);
