@@ -1,0 +1,534 @@
+// perthread_kernel.cuh -- thread-per-system ensemble integrator for sm_100a (B200).
+//
+// One lane integrates one ODE instance through one integration phase (the reference's
+// SingleSystem_PerThread kernel, SourceCodes/SingleSystem_PerThread_Solver.cuh:11-437, with its
+// steppers ..._ExplicitRungeKutta_Steppers.cuh:7-290, error controllers
+// ..._ErrorControllers.cuh:6-86, event step control ..._EventHandling.cuh:6-45 and dense output
+// ..._DenseOutput.cuh:6-58).  Same algorithm and decision semantics, different machine mapping:
+//
+//  * state, stage vectors, control parameters, accessories and event values live in registers
+//    (all loops over SD/NE/... are fully unrolled; callbacks are inlined through `Sys`);
+//  * solver options and tolerances travel in the by-value kernel argument (constant bank), so
+//    they cost neither registers nor loads; shared parameters are staged in shared memory;
+//  * the RKCK45 controller needs no FP64 division and no pow(): the limiting component is found
+//    by cross-multiplication and (tol/err)^(1/5 | 1/4) by division-free Newton steps from a
+//    single-precision seed (error ~1 ulp; exotic operand ranges take the exact slow path);
+//  * LaneRefill: persistent warps; a lane that finishes its instance stores it and takes the
+//    next instance id from a device-side queue, so a warp never idles behind its slowest lane
+//    (the "tailing effect" the reference's README describes).  Per-instance arithmetic does not
+//    depend on the lane an instance runs on, so results are identical in both mappings.
+//
+// The kernel is instantiated in the translation unit that defines the callbacks; the host side
+// reaches it through a plain function pointer (mpgos_perthread_launcher, mpgos_b200.h).
+#ifndef MPGOS_B200_PERTHREAD_KERNEL_CUH
+#define MPGOS_B200_PERTHREAD_KERNEL_CUH
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include "../mpgos_b200.h"
+
+namespace mpgos_b200 {
+
+constexpr int kMaxThreadsPerBlock = 256;
+constexpr int kAlgRK4 = 0, kAlgRKCK45 = 1;
+
+template <int N> struct AtLeastOne { static constexpr int value = (N > 0 ? N : 1); };
+
+// By-value kernel argument (constant bank).  Role of the reference's Struct_GlobalVariables +
+// Struct_SolverOptions + Struct_ThreadConfiguration (Interface.cuh:72-115).
+template <class P, int SD, int NE>
+struct PerThreadArgs
+{
+	P*   TimeDomain;  P* ActualState;  P* ActualTime;  P* ControlParameters;
+	P*   SharedParameters;  int* IntegerSharedParameters;
+	P*   Accessories;  int* IntegerAccessories;
+	int* DenseOutputIndex;  P* DenseOutputTimeInstances;  P* DenseOutputStates;
+	unsigned long long* StepsAttempted;
+	unsigned long long* StepsAccepted;
+	unsigned int*       WorkQueue;
+	int  Stride;             // instances held by the buffers (SoA stride)
+	int  Active;             // instances [0, Active) are integrated
+	int  InstanceOffset;     // global id of local instance 0
+	int  GlobalInstances;    // NT as the callbacks see it
+	int  DenseCapacity;      // NDO
+	int  DenseOutputSaveFrequency;
+	int  DeviceMessages;
+	P    InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit;
+	P    DenseOutputMinimumTimeStep;
+	P    RelativeTolerance[SD];
+	P    AbsoluteTolerance[SD];
+	P    EventTolerance[AtLeastOne<NE>::value];
+	int  EventDirection[AtLeastOne<NE>::value];
+};
+
+// ---------------------------------------------------------------------------------------------
+// numeric helpers
+
+template <class P> struct Num;
+
+template <> struct Num<double>
+{
+	static __device__ __forceinline__ bool finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+	static __device__ __forceinline__ int  exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
+	static constexpr int kBias = 1023, kHalfRange = 100, kNewton = 2;
+	static __device__ __forceinline__ float  narrow(double x) { return __double2float_rn(x); }
+};
+
+template <> struct Num<float>
+{
+	static __device__ __forceinline__ bool finite(float x) { return (__float_as_int(x) & 0x7f800000) != 0x7f800000; }
+	static __device__ __forceinline__ int  exponent(float x) { return (__float_as_int(x) >> 23) & 0xff; }
+	static constexpr int kBias = 127, kHalfRange = 60, kNewton = 1;
+	static __device__ __forceinline__ float  narrow(float x) { return x; }
+};
+
+// True when tol and err are positive normal numbers whose magnitudes, cross products and ratio
+// stay well inside the single-precision range (so the seed below is valid) and whose ratio is
+// below the reference's initial value 1e30 of the running minimum (ErrorControllers.cuh:38).
+template <class P>
+__device__ __forceinline__ bool ratio_in_fast_range(P tol, P err)
+{
+	const int et = Num<P>::exponent(tol), ee = Num<P>::exponent(err);
+	const bool sign_ok = (tol > P(0)) && (err > P(0));
+	return sign_ok && ((unsigned)(et - (Num<P>::kBias - Num<P>::kHalfRange)) < (unsigned)(Num<P>::kHalfRange + 30))
+	               && ((unsigned)(ee - (Num<P>::kBias - Num<P>::kHalfRange)) < (unsigned)(Num<P>::kHalfRange + 30))
+	               && (et - ee < 98);
+}
+
+// y = (tol/err)^(1/5) if accept, (tol/err)^(1/4) otherwise, without FP64 division or pow.
+// With a = err/tol, y = a^(-1/n) is the fixed point of the division-free Newton map
+//     y <- y + y (1 - a y^n)/n  =  y + y (tol - err y^n) / (n tol).
+// The residual tol - err y^n is one FMA in working precision; the factor 1/(n tol) only scales a
+// correction of relative size <= 1e-5, so a single-precision reciprocal is exact enough.  The
+// seed comes from the SFU (lg2/ex2) with relative error <~ 4e-6; two steps in FP64 (one in FP32)
+// leave ~1 ulp.
+template <class P>
+__device__ __forceinline__ P ratio_root_fast(P tol, P err, bool accept)
+{
+	const float tf  = Num<P>::narrow(tol);
+	const float ef  = Num<P>::narrow(err);
+	const float inv = accept ? 0.2f : 0.25f;
+	P y = (P)exp2f((__log2f(tf) - __log2f(ef)) * inv);
+	const P rn = (P)(__frcp_rn(tf) * inv);
+	#pragma unroll
+	for (int it = 0; it < Num<P>::kNewton; it++)
+	{
+		const P y2 = y * y;
+		const P y4 = y2 * y2;
+		const P yn = accept ? y4 * y : y4;
+		const P res = fma(-err, yn, tol);
+		y = fma(y * res, rn, y);
+	}
+	return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One instance's registers.
+
+template <class P, int SD, int NCP, int NE, int NA, int NIA>
+struct LaneState
+{
+	P   td[2];
+	P   x[SD];
+	P   t;
+	P   cpar[AtLeastOne<NCP>::value];
+	P   acc[AtLeastOne<NA>::value];
+	int acci[AtLeastOne<NIA>::value];
+	P   ev[AtLeastOne<NE>::value];       // event values at the actual state
+	P   dt_new;
+	P   dense_next_time;
+	int dense_index;
+	int dense_skipped;
+	unsigned attempted, accepted;
+};
+
+// ---------------------------------------------------------------------------------------------
+// The kernel.  Sys supplies the six callbacks as static device functions with the reference's
+// argument lists (see include/SingleSystem_PerThread_Interface.cuh for the adapter that binds the
+// user's PerThread_* functions).
+
+template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL>
+__global__ void __launch_bounds__(kMaxThreadsPerBlock)
+perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
+{
+	// shared parameters: staged once per block (Solver.cuh:66-88); unlike the reference we
+	// synchronise before the first use.
+	__shared__ P   s_par[AtLeastOne<NSP>::value];
+	__shared__ int s_pari[AtLeastOne<NISP>::value];
+	if (NSP > 0 || NISP > 0)
+	{
+		for (int i = threadIdx.x; i < NSP; i += blockDim.x)  s_par[i]  = a.SharedParameters[i];
+		for (int i = threadIdx.x; i < NISP; i += blockDim.x) s_pari[i] = a.IntegerSharedParameters[i];
+		__syncthreads();
+	}
+
+	const int NTG    = a.GlobalInstances;
+	const int stride = a.Stride;
+	const unsigned grid_threads = gridDim.x * blockDim.x;
+
+	LaneState<P, SD, NCP, NE, NA, NIA> s;
+	int  inst  = blockIdx.x * blockDim.x + threadIdx.x;
+	bool alive = false;
+	bool first = true;
+
+	for (;;)
+	{
+		if (!alive)
+		{
+			// ---- take an instance ------------------------------------------------------------
+			if (!first)
+			{
+				if (!REFILL) break;
+				inst = (int)(grid_threads + atomicAdd(a.WorkQueue, 1u));
+			}
+			first = false;
+			if (inst >= a.Active) break;
+
+			// ---- load (coalesced on the first fill), Solver.cuh:117-142 ----------------------
+			#pragma unroll
+			for (int i = 0; i < 2; i++)   s.td[i]   = a.TimeDomain[inst + i * stride];
+			#pragma unroll
+			for (int i = 0; i < SD; i++)  s.x[i]    = a.ActualState[inst + i * stride];
+			#pragma unroll
+			for (int i = 0; i < NCP; i++) s.cpar[i] = a.ControlParameters[inst + i * stride];
+			#pragma unroll
+			for (int i = 0; i < NA; i++)  s.acc[i]  = a.Accessories[inst + i * stride];
+			#pragma unroll
+			for (int i = 0; i < NIA; i++) s.acci[i] = a.IntegerAccessories[inst + i * stride];
+			s.t = a.ActualTime[inst];
+			s.dense_index = DENSE ? a.DenseOutputIndex[inst] : 0;
+			s.dense_skipped = 0;
+			s.dense_next_time = P(0);
+			s.dt_new = a.InitialTimeStep;
+			s.attempted = 0;  s.accepted = 0;
+			alive = true;
+
+			P dt0 = a.InitialTimeStep;
+			const int gid = inst + a.InstanceOffset;
+			Sys::Initialization(gid, NTG, s.dense_index, s.t, dt0, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+			if (NE > 0)
+				Sys::EventFunction(gid, NTG, s.ev, s.t, dt0, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+			if (DENSE)   // first point of the phase, stored without looking at the index (Solver.cuh:179-193)
+			{
+				if (s.dense_index < a.DenseCapacity)
+				{
+					a.DenseOutputTimeInstances[inst + (size_t)s.dense_index * stride] = s.t;
+					#pragma unroll
+					for (int i = 0; i < SD; i++)
+						a.DenseOutputStates[inst + (size_t)i * stride + (size_t)s.dense_index * stride * SD] = s.x[i];
+				}
+				s.dense_index++;
+				s.dense_skipped = 0;
+				s.dense_next_time = fmin(s.t + a.DenseOutputMinimumTimeStep, s.td[1]);
+			}
+		}
+
+		// ======================== one attempted step (Solver.cuh:197-394) =====================
+		const int gid = inst + a.InstanceOffset;
+		bool update = true, finite = true, terminate = false, end_reached = false;
+		P dt = s.dt_new;
+		{
+			const P remaining = s.td[1] - s.t;
+			if (dt > remaining) { dt = remaining; end_reached = true; }
+		}
+		s.attempted++;
+
+		P xn[SD];
+		if (ALG == kAlgRK4)
+		{
+			// Steppers.cuh:7-117 -- xn accumulates k1 + 2 k2 + 2 k3 (+ k4)
+			P X[SD], k[SD], T;
+			const P half = P(0.5) * dt;
+			const P sixth = P(1.0 / 6.0) * dt;
+			Sys::OdeFunction(gid, NTG, xn, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+			T = s.t + half;
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + xn[i] * half;
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) { xn[i] = xn[i] + P(2.0) * k[i]; X[i] = s.x[i] + k[i] * half; }
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			T = s.t + dt;
+			#pragma unroll
+			for (int i = 0; i < SD; i++) { xn[i] = xn[i] + P(2.0) * k[i]; X[i] = s.x[i] + k[i] * dt; }
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++)
+			{
+				xn[i] = s.x[i] + sixth * (xn[i] + k[i]);
+				finite = finite && Num<P>::finite(xn[i]);
+			}
+			// ErrorControllers.cuh:6-20: never rejects; a non-finite state ends the phase, committed
+			if (!finite)
+			{
+				if (a.DeviceMessages) printf("Error: State is not a finite number. Try to use smaller step size. (thread id: %d)\n", gid);
+				terminate = true;
+			}
+			s.dt_new = a.InitialTimeStep;
+		}
+		else
+		{
+			// Steppers.cuh:122-290 -- Cash-Karp 4(5)
+			P X[SD], T, k1[SD], k2[SD], k3[SD], k4[SD], k5[SD], k6[SD], err[SD];
+			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			T = s.t + dt * P(1.0 / 5.0);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(1.0 / 5.0) * k1[i]);
+			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			T = s.t + dt * P(3.0 / 10.0);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(3.0 / 40.0) * k1[i] + P(9.0 / 40.0) * k2[i]);
+			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			T = s.t + dt * P(3.0 / 5.0);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(3.0 / 10.0) * k1[i] + P(-9.0 / 10.0) * k2[i] + P(6.0 / 5.0) * k3[i]);
+			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			T = s.t + dt;
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(-11.0 / 54.0) * k1[i] + P(5.0 / 2.0) * k2[i] + P(-70.0 / 27.0) * k3[i] + P(35.0 / 27.0) * k4[i]);
+			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			T = s.t + dt * P(7.0 / 8.0);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(1631.0 / 55296.0) * k1[i] + P(175.0 / 512.0) * k2[i] + P(575.0 / 13824.0) * k3[i] + P(44275.0 / 110592.0) * k4[i] + P(253.0 / 4096.0) * k5[i]);
+			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			#pragma unroll
+			for (int i = 0; i < SD; i++)
+			{
+				xn[i] = s.x[i] + dt * (P(37.0 / 378.0) * k1[i] + P(250.0 / 621.0) * k3[i] + P(125.0 / 594.0) * k4[i] + P(512.0 / 1771.0) * k6[i]);
+				const P e = P(37.0 / 378.0 - 2825.0 / 27648.0) * k1[i] + P(250.0 / 621.0 - 18575.0 / 48384.0) * k3[i]
+				          + P(125.0 / 594.0 - 13525.0 / 55296.0) * k4[i] + P(0.0 - 277.0 / 14336.0) * k5[i] + P(512.0 / 1771.0 - 1.0 / 4.0) * k6[i];
+				err[i] = dt * fabs(e) + P(1e-18);
+				finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
+			}
+
+			// ErrorControllers.cuh:24-86 -- accept test, limiting component, new step size
+			P tol[SD];
+			#pragma unroll
+			for (int i = 0; i < SD; i++)
+			{
+				tol[i] = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(s.x[i])), a.AbsoluteTolerance[i]);
+				update = update && (err[i] < tol[i]);
+			}
+			// component with the smallest tol/err: tol_a/err_a < tol_b/err_b  <=>  tol_a err_b < tol_b err_a
+			P tsel = tol[0], esel = err[0];
+			bool fast = ratio_in_fast_range(tol[0], err[0]);
+			#pragma unroll
+			for (int i = 1; i < SD; i++)
+			{
+				fast = fast && ratio_in_fast_range(tol[i], err[i]);
+				const bool less = tol[i] * esel < tsel * err[i];
+				tsel = less ? tol[i] : tsel;
+				esel = less ? err[i] : esel;
+			}
+			P mult;
+			if (finite && fast)
+				mult = P(0.9) * ratio_root_fast<P>(tsel, esel, update);
+			else
+			{
+				P rel = P(1e30);
+				#pragma unroll
+				for (int i = 0; i < SD; i++) rel = fmin(rel, tol[i] / err[i]);
+				mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+				if (!Num<P>::finite(mult)) finite = false;
+			}
+
+			const bool at_minimum = dt < a.MinimumTimeStep * P(1.01);
+			if (!finite)
+			{
+				mult = a.TimeStepShrinkLimit;
+				update = false;
+				if (at_minimum)
+				{
+					if (a.DeviceMessages) printf("Error: State is not a finite number even with the minimal step size. Try to use less stringent tolerances. (thread id: %d)\n", gid);
+					terminate = true;
+				}
+			}
+			else if (at_minimum)
+			{
+				if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
+				update = true;
+			}
+			mult = fmin(mult, a.TimeStepGrowLimit);
+			mult = fmax(mult, a.TimeStepShrinkLimit);
+			P dt_new = dt * mult;
+			dt_new = fmin(dt_new, a.MaximumTimeStep);
+			dt_new = fmax(dt_new, a.MinimumTimeStep);
+			s.dt_new = dt_new;
+		}
+
+		// ---- events: step-size control (EventHandling.cuh:6-45) ------------------------------
+		P evn[AtLeastOne<NE>::value];
+		if (NE > 0)
+		{
+			Sys::EventFunction(gid, NTG, evn, s.t + dt, dt, s.td, xn, s.cpar, s_par, s_pari, s.acc, s.acci);
+			if (update && !terminate)
+			{
+				P dt_event = dt;
+				bool corrected = false;
+				#pragma unroll
+				for (int i = 0; i < NE; i++)
+				{
+					const P et = a.EventTolerance[i];
+					if (((s.ev[i] > et) && (evn[i] < -et) && (a.EventDirection[i] <= 0)) ||
+					    ((s.ev[i] < -et) && (evn[i] > et) && (a.EventDirection[i] >= 0)))
+					{
+						dt_event = fmin(dt_event, -s.ev[i] / (evn[i] - s.ev[i]) * dt);
+						corrected = true;
+					}
+				}
+				if (corrected)
+				{
+					if (dt_event < a.MinimumTimeStep)
+					{
+						if (a.DeviceMessages) printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (thread id: %d)\n", gid);
+					}
+					else { s.dt_new = dt_event; update = false; }
+				}
+			}
+		}
+
+		// ---- accepted step (Solver.cuh:302-392) ------------------------------------------------
+		if (update)
+		{
+			int user_terminate = 0;
+			s.accepted++;
+			s.t += dt;
+			#pragma unroll
+			for (int i = 0; i < SD; i++) s.x[i] = xn[i];
+
+			Sys::ActionAfterSuccessfulTimeStep(gid, NTG, user_terminate, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+
+			if (NE > 0)
+			{
+				#pragma unroll
+				for (int i = 0; i < NE; i++)
+				{
+					const P et = a.EventTolerance[i];
+					if (((s.ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) ||
+					    ((s.ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
+						Sys::ActionAfterEventDetection(gid, NTG, i, user_terminate, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+				}
+				Sys::EventFunction(gid, NTG, s.ev, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+			}
+
+			if (DENSE)   // DenseOutput.cuh:41-58 then :6-37
+			{
+				const bool room = s.dense_index < a.DenseCapacity;
+				bool store = room && (s.dense_next_time < s.t) && (s.dense_skipped >= (a.DenseOutputSaveFrequency - 1));
+				if (room && (end_reached || user_terminate == 1)) store = true;
+				if (store)
+				{
+					a.DenseOutputTimeInstances[inst + (size_t)s.dense_index * stride] = s.t;
+					#pragma unroll
+					for (int i = 0; i < SD; i++)
+						a.DenseOutputStates[inst + (size_t)i * stride + (size_t)s.dense_index * stride * SD] = s.x[i];
+					s.dense_index++;
+					s.dense_skipped = 0;
+					s.dense_next_time = fmin(s.t + a.DenseOutputMinimumTimeStep, s.td[1]);
+				}
+				else s.dense_skipped++;
+			}
+
+			if (end_reached || user_terminate == 1) terminate = true;
+		}
+
+		// ---- end of the phase for this instance (Solver.cuh:398-435) ---------------------------
+		if (terminate)
+		{
+			Sys::Finalization(gid, NTG, s.dense_index, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < 2; i++)   a.TimeDomain[inst + i * stride] = s.td[i];
+			#pragma unroll
+			for (int i = 0; i < SD; i++)  a.ActualState[inst + i * stride] = s.x[i];
+			#pragma unroll
+			for (int i = 0; i < NCP; i++) a.ControlParameters[inst + i * stride] = s.cpar[i];
+			#pragma unroll
+			for (int i = 0; i < NA; i++)  a.Accessories[inst + i * stride] = s.acc[i];
+			#pragma unroll
+			for (int i = 0; i < NIA; i++) a.IntegerAccessories[inst + i * stride] = s.acci[i];
+			a.ActualTime[inst] = s.t;
+			if (DENSE) a.DenseOutputIndex[inst] = s.dense_index;
+			a.StepsAttempted[inst] += s.attempted;
+			a.StepsAccepted[inst]  += s.accepted;
+			alive = false;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launcher generated next to the kernel.
+
+template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG>
+struct PerThreadLauncher
+{
+	template <bool REFILL>
+	static cudaError_t enqueue(const mpgos_perthread_launch* L, const PerThreadArgs<P, SD, NE>& args, cudaStream_t stream)
+	{
+		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL>;
+		int block = L->ThreadsPerBlock;
+		if (block < 32) block = 32;
+		if (block > kMaxThreadsPerBlock) block = kMaxThreadsPerBlock;
+		block = (block / 32) * 32;
+		const int active = args.Active;
+		if (active <= 0) return cudaSuccess;
+		int grid = (active + block - 1) / block;
+		if (REFILL)
+		{
+			// persistent grid: as many blocks as are resident at once, a multiple of the SM count
+			int per_sm = 0;
+			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+			if (e != cudaSuccess) return e;
+			if (per_sm < 1) per_sm = 1;
+			const int resident = per_sm * (L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148);
+			if (grid > resident) grid = resident;
+			e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
+			if (e != cudaSuccess) return e;
+		}
+		kernel<<<grid, block, 0, stream>>>(args);
+		return cudaGetLastError();
+	}
+
+	static int launch(const mpgos_perthread_launch* L, void* stream_v)
+	{
+		cudaStream_t stream = (cudaStream_t)stream_v;
+		const mpgos_perthread_desc& d = L->desc;
+		if (d.SD != SD || d.NCP != NCP || d.NSP != NSP || d.NISP != NISP || d.NE != NE || d.NA != NA || d.NIA != NIA ||
+		    d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
+			return (int)cudaErrorInvalidValue;
+
+		PerThreadArgs<P, SD, NE> a;
+		a.TimeDomain = (P*)L->d_TimeDomain;  a.ActualState = (P*)L->d_ActualState;  a.ActualTime = (P*)L->d_ActualTime;
+		a.ControlParameters = (P*)L->d_ControlParameters;  a.SharedParameters = (P*)L->d_SharedParameters;
+		a.IntegerSharedParameters = L->d_IntegerSharedParameters;  a.Accessories = (P*)L->d_Accessories;
+		a.IntegerAccessories = L->d_IntegerAccessories;  a.DenseOutputIndex = L->d_DenseOutputIndex;
+		a.DenseOutputTimeInstances = (P*)L->d_DenseOutputTimeInstances;  a.DenseOutputStates = (P*)L->d_DenseOutputStates;
+		a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
+		a.Stride = d.NT;
+		a.Active = L->ActiveNumberOfThreads < d.NT ? L->ActiveNumberOfThreads : d.NT;
+		a.InstanceOffset = d.InstanceOffset;
+		a.GlobalInstances = d.GlobalInstances > 0 ? d.GlobalInstances : d.NT;
+		a.DenseCapacity = d.NDO;
+		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;
+		a.DeviceMessages = L->DeviceMessages;
+		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;
+		a.MinimumTimeStep = (P)L->MinimumTimeStep;  a.TimeStepGrowLimit = (P)L->TimeStepGrowLimit;
+		a.TimeStepShrinkLimit = (P)L->TimeStepShrinkLimit;  a.DenseOutputMinimumTimeStep = (P)L->DenseOutputMinimumTimeStep;
+		for (int i = 0; i < SD; i++) { a.RelativeTolerance[i] = (P)L->RelativeTolerance[i];  a.AbsoluteTolerance[i] = (P)L->AbsoluteTolerance[i]; }
+		for (int i = 0; i < AtLeastOne<NE>::value; i++)
+		{
+			a.EventTolerance[i] = (i < NE) ? (P)L->EventTolerance[i] : P(0);
+			a.EventDirection[i] = (i < NE) ? L->EventDirection[i] : 0;
+		}
+		return (int)(L->LaneRefill ? enqueue<true>(L, a, stream) : enqueue<false>(L, a, stream));
+	}
+};
+
+} // namespace mpgos_b200
+#endif

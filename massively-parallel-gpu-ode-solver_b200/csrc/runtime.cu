@@ -1,0 +1,533 @@
+// runtime.cu -- implementation of the C-ABI in include/mpgos_b200.h.
+//
+// Plays the role of the host half of the reference's ProblemSolver object
+// (SourceCodes/SingleSystem_PerThread_Interface.cuh:309-1312): device selection, one stream and
+// one event per solver object, pinned host mirrors, device buffers in the same structure-of-arrays
+// layout, option bookkeeping, asynchronous copies, launch, synchronisation.  The integration
+// kernel itself is not here: Solve() receives a launcher generated next to the user's callbacks
+// (include/mpgos_b200/perthread_kernel.cuh) or one of the built-in systems (builtin_*.cu).
+//
+// There is no CPU path: every entry point that needs the device fails with MPGOS_ERR_CUDA when
+// CUDA is unavailable.
+#include "../../include/mpgos_b200.h"
+#include "builtin_registry.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CUDA_TRY(call)                                                                                   \
+	do {                                                                                                 \
+		cudaError_t e_ = (call);                                                                         \
+		if (e_ != cudaSuccess)                                                                           \
+			return fail(MPGOS_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+// One host mirror + device buffer pair.
+struct Mirror
+{
+	void*  host = nullptr;
+	void*  dev = nullptr;
+	size_t elements = 0;
+	size_t bytes = 0;
+};
+
+// sum of two u64 arrays, one block-level reduction per 1024 elements, finished with atomics
+__global__ void reduce_step_counters(const unsigned long long* __restrict__ attempted, const unsigned long long* __restrict__ accepted,
+                                     int n, unsigned long long* __restrict__ out)
+{
+	unsigned long long a = 0, b = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { a += attempted[i]; b += accepted[i]; }
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+	if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], a); atomicAdd(&out[1], b); }
+}
+
+// independent FMA chains held in registers; 16 chains x 2 flops x iters per thread
+template <class P>
+__global__ void fma_peak_kernel(P* out, int iters, P a, P b)
+{
+	P x[16];
+	#pragma unroll
+	for (int i = 0; i < 16; i++) x[i] = (P)(threadIdx.x + i);
+	for (int it = 0; it < iters; it++)
+	{
+		#pragma unroll
+		for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+	}
+	P s = 0;
+	#pragma unroll
+	for (int i = 0; i < 16; i++) s += x[i];
+	if (s == (P)123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <class P>
+int probe_fma_peak(double* tflops)
+{
+	P* d = nullptr;
+	CUDA_TRY(cudaMalloc(&d, sizeof(P)));
+	cudaDeviceProp prop;  int dev = 0;
+	CUDA_TRY(cudaGetDevice(&dev));
+	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));  CUDA_TRY(cudaEventCreate(&e1));
+	double best = 0;
+	for (int rep = 0; rep < 6; rep++)
+	{
+		CUDA_TRY(cudaEventRecord(e0));
+		fma_peak_kernel<P><<<blocks, threads>>>(d, iters, (P)0.999999, (P)1e-7);
+		CUDA_TRY(cudaEventRecord(e1));
+		CUDA_TRY(cudaEventSynchronize(e1));
+		float ms = 0;
+		CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+		const double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);  cudaEventDestroy(e1);  cudaFree(d);
+	*tflops = best;
+	return MPGOS_OK;
+}
+
+} // namespace
+
+struct mpgos_perthread_solver
+{
+	mpgos_perthread_desc desc;
+	int          sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t  event = nullptr;
+	cudaEvent_t  t0 = nullptr, t1 = nullptr;
+	Mirror       var[13];   // indexed by mpgos_variable (All and DenseOutput unused)
+	unsigned long long* d_attempted = nullptr;
+	unsigned long long* d_accepted = nullptr;
+	unsigned long long* d_totals = nullptr;   // [2]
+	unsigned int*       d_queue = nullptr;
+	// options (Interface.cuh:475-496 defaults)
+	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12;
+	double TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1, DenseOutputMinimumTimeStep = 0.0;
+	int    DenseOutputSaveFrequency = 1;
+	int    ThreadsPerBlock = 128;
+	int    ActiveNumberOfThreads = 0;
+	int    PreferSharedMemory = 1;
+	int    LaneRefill = 1;
+	int    DeviceMessages = 0;
+	std::vector<double> rtol, atol, evtol;
+	std::vector<int>    evdir;
+};
+
+extern "C" {
+
+const char* mpgos_last_error(void) { return g_error; }
+int mpgos_abi_version(void) { return MPGOS_B200_ABI_VERSION; }
+
+int mpgos_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+static int alloc_mirror(Mirror& m, size_t elements, size_t elem_size)
+{
+	m.elements = elements;
+	m.bytes = elements * elem_size;
+	if (m.bytes == 0) return MPGOS_OK;
+	CUDA_TRY(cudaMallocHost(&m.host, m.bytes));
+	std::memset(m.host, 0, m.bytes);
+	CUDA_TRY(cudaMalloc(&m.dev, m.bytes));
+	CUDA_TRY(cudaMemset(m.dev, 0, m.bytes));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_solver** out)
+{
+	if (!desc || !out) return fail(MPGOS_ERR_ARGUMENT, "null argument");
+	*out = nullptr;
+	const mpgos_perthread_desc& d = *desc;
+	if (d.NT <= 0 || d.SD <= 0 || d.NCP < 0 || d.NSP < 0 || d.NISP < 0 || d.NE < 0 || d.NA < 0 || d.NIA < 0 || d.NDO < 0)
+		return fail(MPGOS_ERR_ARGUMENT, "invalid sizes in descriptor");
+	if (d.Algorithm != MPGOS_RK4 && d.Algorithm != MPGOS_RKCK45) return fail(MPGOS_ERR_ARGUMENT, "unknown algorithm %d", d.Algorithm);
+	if (d.PrecisionBytes != 8 && d.PrecisionBytes != 4) return fail(MPGOS_ERR_ARGUMENT, "precision must be 8 or 4 bytes");
+
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	if (d.Device < 0 || d.Device >= ndev) return fail(MPGOS_ERR_ARGUMENT, "device %d not present (%d devices)", d.Device, ndev);
+	CUDA_TRY(cudaSetDevice(d.Device));
+
+	// memory check before allocating anything (Interface.cuh:368-396)
+	const size_t P = (size_t)d.PrecisionBytes, NT = (size_t)d.NT;
+	const size_t need = P * NT * (2 + d.SD + 1 + d.NCP + d.NA + (size_t)d.NDO * (1 + d.SD)) + P * d.NSP
+	                  + 4 * (d.NISP + NT * d.NIA + NT) + 16 * NT + 64;
+	size_t free_b = 0, total_b = 0;
+	CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+	if (need >= free_b) return fail(MPGOS_ERR_MEMORY, "solver needs %zu bytes of device memory, %zu free", need, free_b);
+
+	mpgos_perthread_solver* s = new (std::nothrow) mpgos_perthread_solver();
+	if (!s) return fail(MPGOS_ERR_MEMORY, "host allocation failed");
+	s->desc = d;
+	s->ActiveNumberOfThreads = d.NT;
+	s->rtol.assign(d.SD, 1e-8);  s->atol.assign(d.SD, 1e-8);
+	s->evtol.assign(d.NE > 0 ? d.NE : 1, 1e-6);  s->evdir.assign(d.NE > 0 ? d.NE : 1, 0);
+
+	int rc = MPGOS_OK;
+	auto A = [&](int v, size_t elements, size_t elem) { if (rc == MPGOS_OK) rc = alloc_mirror(s->var[v], elements, elem); };
+	A(MPGOS_VAR_TimeDomain, 2 * NT, P);
+	A(MPGOS_VAR_ActualState, d.SD * NT, P);
+	A(MPGOS_VAR_ActualTime, NT, P);
+	A(MPGOS_VAR_ControlParameters, d.NCP * NT, P);
+	A(MPGOS_VAR_SharedParameters, d.NSP, P);
+	A(MPGOS_VAR_IntegerSharedParameters, d.NISP, 4);
+	A(MPGOS_VAR_Accessories, d.NA * NT, P);
+	A(MPGOS_VAR_IntegerAccessories, d.NIA * NT, 4);
+	A(MPGOS_VAR_DenseIndex, NT, 4);
+	A(MPGOS_VAR_DenseTime, (size_t)d.NDO * NT, P);
+	A(MPGOS_VAR_DenseState, (size_t)d.NDO * d.SD * NT, P);
+	cudaDeviceProp prop;
+	if (rc == MPGOS_OK && cudaGetDeviceProperties(&prop, d.Device) != cudaSuccess) rc = fail(MPGOS_ERR_CUDA, "cudaGetDeviceProperties failed");
+	if (rc == MPGOS_OK)
+	{
+		s->sm_count = prop.multiProcessorCount;
+		auto ok = [&](cudaError_t e, const char* what) { if (rc == MPGOS_OK && e != cudaSuccess) rc = fail(MPGOS_ERR_CUDA, "%s -> %s", what, cudaGetErrorString(e)); };
+		ok(cudaStreamCreate(&s->stream), "cudaStreamCreate");
+		ok(cudaEventCreateWithFlags(&s->event, cudaEventDisableTiming), "cudaEventCreate");
+		ok(cudaEventCreate(&s->t0), "cudaEventCreate");
+		ok(cudaEventCreate(&s->t1), "cudaEventCreate");
+		ok(cudaMalloc(&s->d_attempted, 8 * NT), "cudaMalloc");
+		ok(cudaMalloc(&s->d_accepted, 8 * NT), "cudaMalloc");
+		ok(cudaMalloc(&s->d_totals, 16), "cudaMalloc");
+		ok(cudaMalloc(&s->d_queue, 4), "cudaMalloc");
+		if (rc == MPGOS_OK)
+		{
+			ok(cudaMemset(s->d_attempted, 0, 8 * NT), "cudaMemset");
+			ok(cudaMemset(s->d_accepted, 0, 8 * NT), "cudaMemset");
+			ok(cudaMemset(s->d_queue, 0, 4), "cudaMemset");
+		}
+	}
+	if (rc != MPGOS_OK) { char keep[512]; std::memcpy(keep, g_error, sizeof(keep)); mpgos_perthread_destroy(s); std::memcpy(g_error, keep, sizeof(keep)); return rc; }
+	*out = s;
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_destroy(mpgos_perthread_solver* s)
+{
+	if (!s) return MPGOS_OK;
+	cudaSetDevice(s->desc.Device);
+	if (s->stream) cudaStreamSynchronize(s->stream);
+	for (Mirror& m : s->var) { if (m.host) cudaFreeHost(m.host); if (m.dev) cudaFree(m.dev); }
+	if (s->d_attempted) cudaFree(s->d_attempted);
+	if (s->d_accepted) cudaFree(s->d_accepted);
+	if (s->d_totals) cudaFree(s->d_totals);
+	if (s->d_queue) cudaFree(s->d_queue);
+	if (s->t0) cudaEventDestroy(s->t0);
+	if (s->t1) cudaEventDestroy(s->t1);
+	if (s->event) cudaEventDestroy(s->event);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+	return MPGOS_OK;
+}
+
+static bool is_buffer_variable(int v)
+{
+	return (v >= MPGOS_VAR_TimeDomain && v <= MPGOS_VAR_IntegerAccessories) || (v >= MPGOS_VAR_DenseIndex && v <= MPGOS_VAR_DenseState);
+}
+
+void* mpgos_perthread_host_ptr(mpgos_perthread_solver* s, int variable, size_t* elements)
+{
+	if (!s || !is_buffer_variable(variable)) { fail(MPGOS_ERR_ARGUMENT, "host_ptr: bad variable %d", variable); return nullptr; }
+	if (elements) *elements = s->var[variable].elements;
+	return s->var[variable].host;
+}
+
+void* mpgos_perthread_device_ptr(mpgos_perthread_solver* s, int variable, size_t* elements)
+{
+	if (!s || !is_buffer_variable(variable)) { fail(MPGOS_ERR_ARGUMENT, "device_ptr: bad variable %d", variable); return nullptr; }
+	if (elements) *elements = s->var[variable].elements;
+	return s->var[variable].dev;
+}
+
+int mpgos_perthread_set_option(mpgos_perthread_solver* s, int option, double value)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	switch (option)
+	{
+		case MPGOS_OPT_ThreadsPerBlock:            s->ThreadsPerBlock = (int)value; break;
+		case MPGOS_OPT_InitialTimeStep:            s->InitialTimeStep = value; break;
+		case MPGOS_OPT_ActiveNumberOfThreads:      s->ActiveNumberOfThreads = (int)value; break;
+		case MPGOS_OPT_MaximumTimeStep:            s->MaximumTimeStep = value; break;
+		case MPGOS_OPT_MinimumTimeStep:            s->MinimumTimeStep = value; break;
+		case MPGOS_OPT_TimeStepGrowLimit:          s->TimeStepGrowLimit = value; break;
+		case MPGOS_OPT_TimeStepShrinkLimit:        s->TimeStepShrinkLimit = value; break;
+		case MPGOS_OPT_DenseOutputMinimumTimeStep: s->DenseOutputMinimumTimeStep = value; break;
+		case MPGOS_OPT_DenseOutputSaveFrequency:   s->DenseOutputSaveFrequency = (int)value; break;
+		case MPGOS_OPT_PreferSharedMemory:         s->PreferSharedMemory = (int)value; break;
+		case MPGOS_OPT_LaneRefill:                 s->LaneRefill = (int)value != 0; break;
+		case MPGOS_OPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
+		default: return fail(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
+	}
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_set_option_indexed(mpgos_perthread_solver* s, int option, int index, double value)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	const int SD = s->desc.SD, NE = s->desc.NE;
+	switch (option)
+	{
+		case MPGOS_OPT_RelativeTolerance:
+			if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "RelativeTolerance index %d outside 0-%d", index, SD - 1);
+			s->rtol[index] = value; break;
+		case MPGOS_OPT_AbsoluteTolerance:
+			if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "AbsoluteTolerance index %d outside 0-%d", index, SD - 1);
+			s->atol[index] = value; break;
+		case MPGOS_OPT_EventTolerance:
+			if (index < 0 || index >= NE) return fail(MPGOS_ERR_BOUNDS, "EventTolerance index %d outside 0-%d", index, NE - 1);
+			s->evtol[index] = value; break;
+		case MPGOS_OPT_EventDirection:
+			if (index < 0 || index >= NE) return fail(MPGOS_ERR_BOUNDS, "EventDirection index %d outside 0-%d", index, NE - 1);
+			s->evdir[index] = (int)value; break;
+		default: return fail(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 1 input argument or is not applicable", option);
+	}
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_get_option(mpgos_perthread_solver* s, int option, int index, double* value)
+{
+	if (!s || !value) return fail(MPGOS_ERR_ARGUMENT, "null argument");
+	const int SD = s->desc.SD, NE = s->desc.NE;
+	switch (option)
+	{
+		case MPGOS_OPT_ThreadsPerBlock:            *value = s->ThreadsPerBlock; break;
+		case MPGOS_OPT_InitialTimeStep:            *value = s->InitialTimeStep; break;
+		case MPGOS_OPT_ActiveNumberOfThreads:      *value = s->ActiveNumberOfThreads; break;
+		case MPGOS_OPT_MaximumTimeStep:            *value = s->MaximumTimeStep; break;
+		case MPGOS_OPT_MinimumTimeStep:            *value = s->MinimumTimeStep; break;
+		case MPGOS_OPT_TimeStepGrowLimit:          *value = s->TimeStepGrowLimit; break;
+		case MPGOS_OPT_TimeStepShrinkLimit:        *value = s->TimeStepShrinkLimit; break;
+		case MPGOS_OPT_DenseOutputMinimumTimeStep: *value = s->DenseOutputMinimumTimeStep; break;
+		case MPGOS_OPT_DenseOutputSaveFrequency:   *value = s->DenseOutputSaveFrequency; break;
+		case MPGOS_OPT_PreferSharedMemory:         *value = s->PreferSharedMemory; break;
+		case MPGOS_OPT_LaneRefill:                 *value = s->LaneRefill; break;
+		case MPGOS_OPT_DeviceMessages:             *value = s->DeviceMessages; break;
+		case MPGOS_OPT_RelativeTolerance: if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->rtol[index]; break;
+		case MPGOS_OPT_AbsoluteTolerance: if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->atol[index]; break;
+		case MPGOS_OPT_EventTolerance:    if (index < 0 || index >= NE) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->evtol[index]; break;
+		case MPGOS_OPT_EventDirection:    if (index < 0 || index >= NE) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->evdir[index]; break;
+		default: return fail(MPGOS_ERR_ARGUMENT, "unknown option %d", option);
+	}
+	return MPGOS_OK;
+}
+
+static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	// groups exactly as the reference: All = every mirror (Interface.cuh:878-890),
+	// DenseOutput = index + time + state (Interface.cuh:924-928)
+	int list[11];  int n = 0;
+	if (variable == MPGOS_VAR_All)
+	{
+		for (int v = MPGOS_VAR_TimeDomain; v <= MPGOS_VAR_IntegerAccessories; v++) list[n++] = v;
+		list[n++] = MPGOS_VAR_DenseIndex;  list[n++] = MPGOS_VAR_DenseTime;  list[n++] = MPGOS_VAR_DenseState;
+	}
+	else if (variable == MPGOS_VAR_DenseOutput) { list[n++] = MPGOS_VAR_DenseIndex;  list[n++] = MPGOS_VAR_DenseTime;  list[n++] = MPGOS_VAR_DenseState; }
+	else if (is_buffer_variable(variable)) list[n++] = variable;
+	else return fail(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
+	for (int i = 0; i < n; i++)
+	{
+		Mirror& m = s->var[list[i]];
+		if (m.bytes == 0) continue;
+		if (to_device) CUDA_TRY(cudaMemcpyAsync(m.dev, m.host, m.bytes, cudaMemcpyHostToDevice, s->stream));
+		else           CUDA_TRY(cudaMemcpyAsync(m.host, m.dev, m.bytes, cudaMemcpyDeviceToHost, s->stream));
+	}
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_sync_h2d(mpgos_perthread_solver* s, int variable) { return copy_variable(s, variable, true); }
+int mpgos_perthread_sync_d2h(mpgos_perthread_solver* s, int variable) { return copy_variable(s, variable, false); }
+
+static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
+{
+	L.desc = s->desc;
+	L.d_TimeDomain = s->var[MPGOS_VAR_TimeDomain].dev;  L.d_ActualState = s->var[MPGOS_VAR_ActualState].dev;
+	L.d_ActualTime = s->var[MPGOS_VAR_ActualTime].dev;  L.d_ControlParameters = s->var[MPGOS_VAR_ControlParameters].dev;
+	L.d_SharedParameters = s->var[MPGOS_VAR_SharedParameters].dev;
+	L.d_IntegerSharedParameters = (int*)s->var[MPGOS_VAR_IntegerSharedParameters].dev;
+	L.d_Accessories = s->var[MPGOS_VAR_Accessories].dev;  L.d_IntegerAccessories = (int*)s->var[MPGOS_VAR_IntegerAccessories].dev;
+	L.d_DenseOutputIndex = (int*)s->var[MPGOS_VAR_DenseIndex].dev;
+	L.d_DenseOutputTimeInstances = s->var[MPGOS_VAR_DenseTime].dev;  L.d_DenseOutputStates = s->var[MPGOS_VAR_DenseState].dev;
+	L.d_StepsAttempted = s->d_attempted;  L.d_StepsAccepted = s->d_accepted;  L.d_WorkQueue = s->d_queue;
+	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();
+	L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
+	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
+	L.TimeStepGrowLimit = s->TimeStepGrowLimit;  L.TimeStepShrinkLimit = s->TimeStepShrinkLimit;
+	L.DenseOutputMinimumTimeStep = s->DenseOutputMinimumTimeStep;  L.DenseOutputSaveFrequency = s->DenseOutputSaveFrequency;
+	L.ThreadsPerBlock = s->ThreadsPerBlock;  L.ActiveNumberOfThreads = s->ActiveNumberOfThreads;
+	L.PreferSharedMemory = s->PreferSharedMemory;  L.LaneRefill = s->LaneRefill;  L.DeviceMessages = s->DeviceMessages;
+	L.MultiProcessorCount = s->sm_count;
+}
+
+int mpgos_perthread_solve(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher)
+{
+	if (!s || !launcher) return fail(MPGOS_ERR_ARGUMENT, "Solve: null solver or launcher");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	mpgos_perthread_launch L;
+	fill_launch(s, L);
+	const int e = launcher(&L, (void*)s->stream);
+	if (e != 0) return fail(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_solve_timed(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher, int phases, float* elapsed_ms)
+{
+	if (!s || !launcher || !elapsed_ms || phases < 0) return fail(MPGOS_ERR_ARGUMENT, "solve_timed: bad argument");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	mpgos_perthread_launch L;
+	fill_launch(s, L);
+	CUDA_TRY(cudaEventRecord(s->t0, s->stream));
+	for (int p = 0; p < phases; p++)
+	{
+		const int e = launcher(&L, (void*)s->stream);
+		if (e != 0) return fail(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+	}
+	CUDA_TRY(cudaEventRecord(s->t1, s->stream));
+	CUDA_TRY(cudaEventSynchronize(s->t1));
+	CUDA_TRY(cudaEventElapsedTime(elapsed_ms, s->t0, s->t1));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_insert_sync_point(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaEventRecord(s->event, s->stream));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_sync_solver(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaEventSynchronize(s->event));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_sync_device(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_read_step_counters(mpgos_perthread_solver* s, unsigned long long* attempted, unsigned long long* accepted)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	const size_t bytes = 8 * (size_t)s->desc.NT;
+	if (attempted) CUDA_TRY(cudaMemcpyAsync(attempted, s->d_attempted, bytes, cudaMemcpyDeviceToHost, s->stream));
+	if (accepted)  CUDA_TRY(cudaMemcpyAsync(accepted, s->d_accepted, bytes, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_reset_step_counters(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	const size_t bytes = 8 * (size_t)s->desc.NT;
+	CUDA_TRY(cudaMemsetAsync(s->d_attempted, 0, bytes, s->stream));
+	CUDA_TRY(cudaMemsetAsync(s->d_accepted, 0, bytes, s->stream));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_total_steps(mpgos_perthread_solver* s, unsigned long long* attempted, unsigned long long* accepted)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 16, s->stream));
+	reduce_step_counters<<<148 * 4, 256, 0, s->stream>>>(s->d_attempted, s->d_accepted, s->desc.NT, s->d_totals);
+	CUDA_TRY(cudaGetLastError());
+	unsigned long long h[2] = {0, 0};
+	CUDA_TRY(cudaMemcpyAsync(h, s->d_totals, 16, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	if (attempted) *attempted = h[0];
+	if (accepted)  *accepted = h[1];
+	return MPGOS_OK;
+}
+
+void* mpgos_perthread_stream(mpgos_perthread_solver* s) { return s ? (void*)s->stream : nullptr; }
+int   mpgos_perthread_device(mpgos_perthread_solver* s) { return s ? s->desc.Device : -1; }
+
+int mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops)
+{
+	if (!tflops || (precision_bytes != 8 && precision_bytes != 4)) return fail(MPGOS_ERR_ARGUMENT, "probe_fma_peak: bad argument");
+	CUDA_TRY(cudaSetDevice(device));
+	return precision_bytes == 8 ? probe_fma_peak<double>(tflops) : probe_fma_peak<float>(tflops);
+}
+
+// ---- built-in systems -------------------------------------------------------------------------
+
+static void collect(std::vector<mpgos_b200::BuiltinEntry>& all)
+{
+	int n = 0;
+	const mpgos_b200::BuiltinEntry* e;
+	e = mpgos_b200::builtin_entries_lorenz(&n);        all.insert(all.end(), e, e + n);
+	e = mpgos_b200::builtin_entries_duffing(&n);       all.insert(all.end(), e, e + n);
+	e = mpgos_b200::builtin_entries_impact(&n);        all.insert(all.end(), e, e + n);
+	e = mpgos_b200::builtin_entries_kellermiksis(&n);  all.insert(all.end(), e, e + n);
+}
+
+static const std::vector<mpgos_b200::BuiltinEntry>& entries()
+{
+	static std::vector<mpgos_b200::BuiltinEntry> all;
+	static bool done = false;
+	if (!done) { collect(all); done = true; }
+	return all;
+}
+
+static const char* const kBuiltinNames[] = { "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense" };
+
+int mpgos_perthread_builtin_count(void) { return (int)(sizeof(kBuiltinNames) / sizeof(kBuiltinNames[0])); }
+const char* mpgos_perthread_builtin_name(int i) { return (i >= 0 && i < mpgos_perthread_builtin_count()) ? kBuiltinNames[i] : nullptr; }
+
+int mpgos_perthread_builtin_desc(const char* system, mpgos_perthread_desc* desc)
+{
+	if (!system || !desc) return fail(MPGOS_ERR_ARGUMENT, "null argument");
+	for (const mpgos_b200::BuiltinEntry& e : entries())
+		if (!std::strcmp(e.name, system))
+		{
+			desc->SD = e.SD; desc->NCP = e.NCP; desc->NSP = e.NSP; desc->NISP = e.NISP;
+			desc->NE = e.NE; desc->NA = e.NA; desc->NIA = e.NIA;
+			return MPGOS_OK;
+		}
+	return fail(MPGOS_ERR_UNKNOWN_SYSTEM, "no built-in system named '%s'", system);
+}
+
+mpgos_perthread_launcher mpgos_perthread_builtin_launcher(const char* system, int algorithm, int precision_bytes, int dense_output)
+{
+	if (!system) return nullptr;
+	for (const mpgos_b200::BuiltinEntry& e : entries())
+		if (!std::strcmp(e.name, system) && e.Algorithm == algorithm && e.PrecisionBytes == precision_bytes && e.Dense == (dense_output != 0))
+			return e.launcher;
+	fail(MPGOS_ERR_UNKNOWN_SYSTEM, "no built-in launcher for system '%s' algorithm %d precision %d dense %d", system, algorithm, precision_bytes, dense_output);
+	return nullptr;
+}
+
+} // extern "C"

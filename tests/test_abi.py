@@ -1,0 +1,96 @@
+"""The C-ABI library: it loads, exports every symbol include/mpgos_b200.h declares, knows the
+built-in systems, validates arguments, and fails loudly (no fallback) without a CUDA device.
+No compute calls here -- those are the -m gpu tests."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "mpgos_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpgos_[a-z0-9_]+)\s*\(", text)) - {"mpgos_perthread_launcher"})
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    declared = header_functions()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mpgos_b200.h but not exported"
+    assert sorted(pkg.ABI_SYMBOLS) == declared
+    assert lib.mpgos_abi_version() == 1
+
+
+def test_builtin_systems_and_shapes(pkg):
+    lib = pkg.load_library()
+    names = [lib.mpgos_perthread_builtin_name(i).decode() for i in range(lib.mpgos_perthread_builtin_count())]
+    assert names == ["lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense"]
+    from importlib import import_module
+    solver = import_module(pkg.__name__ + ".solver")
+    expect = {"lorenz": (3, 1, 0, 0, 0, 0, 0), "poincare": (2, 1, 1, 0, 0, 0, 0), "duffing": (2, 1, 1, 0, 2, 3, 1),
+              "impact": (3, 1, 4, 0, 2, 3, 2), "kellermiksis": (2, 13, 0, 0, 0, 1, 0), "kellermiksis_dense": (2, 13, 0, 0, 0, 1, 0)}
+    for n, shape in expect.items():
+        d = solver._Desc()
+        assert lib.mpgos_perthread_builtin_desc(n.encode(), C.byref(d)) == 0
+        assert (d.SD, d.NCP, d.NSP, d.NISP, d.NE, d.NA, d.NIA) == shape
+    d = solver._Desc()
+    assert lib.mpgos_perthread_builtin_desc(b"nonesuch", C.byref(d)) == -5
+    assert b"nonesuch" in lib.mpgos_last_error()
+    # launchers exist for the BASELINE configurations, not for unknown combinations
+    assert lib.mpgos_perthread_builtin_launcher(b"lorenz", 1, 8, 0)
+    assert lib.mpgos_perthread_builtin_launcher(b"lorenz", 1, 4, 0)
+    assert lib.mpgos_perthread_builtin_launcher(b"duffing", 0, 8, 1)
+    assert lib.mpgos_perthread_builtin_launcher(b"impact", 1, 8, 0)
+    assert lib.mpgos_perthread_builtin_launcher(b"kellermiksis_dense", 1, 8, 1)
+    assert not lib.mpgos_perthread_builtin_launcher(b"lorenz", 7, 8, 0)
+
+
+def test_create_rejects_bad_descriptors(pkg):
+    lib = pkg.load_library()
+    from importlib import import_module
+    solver = import_module(pkg.__name__ + ".solver")
+    h = C.c_void_p()
+    d = solver._Desc(NT=0, SD=3, PrecisionBytes=8, Algorithm=1)
+    assert lib.mpgos_perthread_create(C.byref(d), C.byref(h)) == -1 and not h.value
+    d = solver._Desc(NT=8, SD=3, PrecisionBytes=2, Algorithm=1)
+    assert lib.mpgos_perthread_create(C.byref(d), C.byref(h)) == -1
+    d = solver._Desc(NT=8, SD=3, PrecisionBytes=8, Algorithm=5)
+    assert lib.mpgos_perthread_create(C.byref(d), C.byref(h)) == -1
+    assert lib.mpgos_perthread_create(None, C.byref(h)) == -1
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device, creating a solver must raise -- never silently compute elsewhere."""
+    lib = pkg.load_library()
+    if lib.mpgos_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.MpgosError):
+        pkg.ProblemSolver("lorenz", 64)
+    with pytest.raises(pkg.MpgosError):
+        pkg.run_workload(pkg.workloads.lorenz(NT=64))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package or include/ may reference it."""
+    pkgdir = os.path.join(ROOT, "massively-parallel-gpu-ode-solver_b200")
+    for base in (pkgdir, os.path.join(ROOT, "include")):
+        for dp, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    text = open(os.path.join(dp, f)).read()
+                    assert "oracle_py" not in text and "liboracle" not in text and "libref_" not in text, os.path.join(dp, f)
+
+
+def test_workload_generators(workloads):
+    wl = workloads.lorenz(NT=1 << 10)
+    assert wl.buffers.ControlParameters[0, 0] == 0.0 and wl.buffers.ControlParameters[0, -1] == 21.0
+    km = workloads.keller_miksis_t5(NT=128)
+    assert km.shape.NCP == 13 and km.buffers.ControlParameters.shape == (13, 128) and np.isfinite(km.buffers.ControlParameters).all()
+    sub = km.buffers.take([0, 5, 127])
+    assert sub.NT == 3 and np.array_equal(sub.ControlParameters[:, 1], km.buffers.ControlParameters[:, 5])
