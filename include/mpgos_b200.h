@@ -146,6 +146,12 @@ int   mpgos_perthread_get_option(mpgos_perthread_solver* s, int option, int inde
 int   mpgos_perthread_sync_h2d(mpgos_perthread_solver* s, int variable);
 int   mpgos_perthread_sync_d2h(mpgos_perthread_solver* s, int variable);
 
+/* Same copies between the device buffer of ONE variable and a caller-owned host array of the same
+ * layout and length (pinned or pageable), bypassing the solver's own mirror; asynchronous on the
+ * solver's stream when the host array is pinned. */
+int   mpgos_perthread_upload(mpgos_perthread_solver* s, int variable, const void* host_src, size_t bytes);
+int   mpgos_perthread_download(mpgos_perthread_solver* s, int variable, void* host_dst, size_t bytes);
+
 /* Solve(), ST/Interface.cuh:1280-1285: one integration phase, asynchronous */
 int   mpgos_perthread_solve(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher);
 
@@ -161,6 +167,14 @@ int   mpgos_perthread_read_step_counters(mpgos_perthread_solver* s, unsigned lon
 int   mpgos_perthread_reset_step_counters(mpgos_perthread_solver* s);
 /* Sum over instances, reduced on the device; synchronises the solver's stream. */
 int   mpgos_perthread_total_steps(mpgos_perthread_solver* s, unsigned long long* attempted, unsigned long long* accepted);
+
+/* Device-resident checkpoint of every per-instance buffer (time domain, state, time, control
+ * parameters, accessories, dense index; the reference's implicit checkpoint is a round trip
+ * through the host mirrors).  save copies device -> device-side snapshot,
+ * restore copies it back; both asynchronous on the solver's stream.  Lets a sweep be re-run from
+ * the same initial condition without touching the host. */
+int   mpgos_perthread_save_state(mpgos_perthread_solver* s);
+int   mpgos_perthread_restore_state(mpgos_perthread_solver* s);
 
 /* Raw handles for callers that bracket Solve() with their own CUDA events. */
 void* mpgos_perthread_stream(mpgos_perthread_solver* s);     /* cudaStream_t */

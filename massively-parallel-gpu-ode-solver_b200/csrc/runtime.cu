@@ -119,6 +119,7 @@ struct mpgos_perthread_solver
 	unsigned long long* d_accepted = nullptr;
 	unsigned long long* d_totals = nullptr;   // [2]
 	unsigned int*       d_queue = nullptr;
+	void*               snapshot[13] = {};        // device-side checkpoint, allocated on first save
 	// options (Interface.cuh:475-496 defaults)
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12;
 	double TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1, DenseOutputMinimumTimeStep = 0.0;
@@ -231,6 +232,7 @@ int mpgos_perthread_destroy(mpgos_perthread_solver* s)
 	cudaSetDevice(s->desc.Device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (Mirror& m : s->var) { if (m.host) cudaFreeHost(m.host); if (m.dev) cudaFree(m.dev); }
+	for (void* p : s->snapshot) if (p) cudaFree(p);
 	if (s->d_attempted) cudaFree(s->d_attempted);
 	if (s->d_accepted) cudaFree(s->d_accepted);
 	if (s->d_totals) cudaFree(s->d_totals);
@@ -362,6 +364,28 @@ static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device
 int mpgos_perthread_sync_h2d(mpgos_perthread_solver* s, int variable) { return copy_variable(s, variable, true); }
 int mpgos_perthread_sync_d2h(mpgos_perthread_solver* s, int variable) { return copy_variable(s, variable, false); }
 
+int mpgos_perthread_upload(mpgos_perthread_solver* s, int variable, const void* host_src, size_t bytes)
+{
+	if (!s || !is_buffer_variable(variable) || (!host_src && bytes)) return fail(MPGOS_ERR_ARGUMENT, "upload: bad argument");
+	Mirror& m = s->var[variable];
+	if (bytes != m.bytes) return fail(MPGOS_ERR_BOUNDS, "upload: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
+	if (bytes == 0) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_download(mpgos_perthread_solver* s, int variable, void* host_dst, size_t bytes)
+{
+	if (!s || !is_buffer_variable(variable) || (!host_dst && bytes)) return fail(MPGOS_ERR_ARGUMENT, "download: bad argument");
+	Mirror& m = s->var[variable];
+	if (bytes != m.bytes) return fail(MPGOS_ERR_BOUNDS, "download: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
+	if (bytes == 0) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaMemcpyAsync(host_dst, m.dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+	return MPGOS_OK;
+}
+
 static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
 {
 	L.desc = s->desc;
@@ -469,6 +493,37 @@ int mpgos_perthread_total_steps(mpgos_perthread_solver* s, unsigned long long* a
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	if (attempted) *attempted = h[0];
 	if (accepted)  *accepted = h[1];
+	return MPGOS_OK;
+}
+
+static const int kStateVariables[] = { MPGOS_VAR_TimeDomain, MPGOS_VAR_ActualState, MPGOS_VAR_ActualTime, MPGOS_VAR_ControlParameters,
+                                       MPGOS_VAR_Accessories, MPGOS_VAR_IntegerAccessories, MPGOS_VAR_DenseIndex };
+
+int mpgos_perthread_save_state(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	for (int v : kStateVariables)
+	{
+		Mirror& m = s->var[v];
+		if (m.bytes == 0) continue;
+		if (!s->snapshot[v]) CUDA_TRY(cudaMalloc(&s->snapshot[v], m.bytes));
+		CUDA_TRY(cudaMemcpyAsync(s->snapshot[v], m.dev, m.bytes, cudaMemcpyDeviceToDevice, s->stream));
+	}
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_restore_state(mpgos_perthread_solver* s)
+{
+	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	for (int v : kStateVariables)
+	{
+		Mirror& m = s->var[v];
+		if (m.bytes == 0) continue;
+		if (!s->snapshot[v]) return fail(MPGOS_ERR_ARGUMENT, "restore_state: no snapshot saved");
+		CUDA_TRY(cudaMemcpyAsync(m.dev, s->snapshot[v], m.bytes, cudaMemcpyDeviceToDevice, s->stream));
+	}
 	return MPGOS_OK;
 }
 

@@ -78,7 +78,8 @@ ABI_SYMBOLS = (
     "mpgos_perthread_read_step_counters", "mpgos_perthread_reset_step_counters", "mpgos_perthread_total_steps",
     "mpgos_perthread_stream", "mpgos_perthread_device", "mpgos_perthread_device_ptr", "mpgos_perthread_solve_timed",
     "mpgos_perthread_builtin_count", "mpgos_perthread_builtin_name", "mpgos_perthread_builtin_desc",
-    "mpgos_perthread_builtin_launcher", "mpgos_probe_fma_peak",
+    "mpgos_perthread_builtin_launcher", "mpgos_probe_fma_peak", "mpgos_perthread_save_state", "mpgos_perthread_restore_state",
+    "mpgos_perthread_upload", "mpgos_perthread_download",
 )
 
 
@@ -87,8 +88,9 @@ class _Desc(C.Structure):
                                         "PrecisionBytes", "Device", "InstanceOffset", "GlobalInstances")]
 
 
-def library_path() -> str:
-    return os.path.join(HERE, "libmpgos_b200.so")
+def library_path(strict: bool = False) -> str:
+    """The product library, or (strict) the same sources built with -fmad=false for the parity tests."""
+    return os.path.join(HERE, "libmpgos_b200_strict.so" if strict else "libmpgos_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -101,15 +103,14 @@ def build_library(verbose: bool = False) -> str:
     return library_path()
 
 
-_LIB = None
+_LIBS = {}
 
 
-def load_library():
+def load_library(strict: bool = False):
     """Load the CUDA library; raises if it has not been built (there is no other implementation)."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = library_path()
+    if strict in _LIBS:
+        return _LIBS[strict]
+    path = library_path(strict)
     if not os.path.exists(path):
         raise MpgosError(f"{path} is missing: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(path)
@@ -127,7 +128,7 @@ def load_library():
     lib.mpgos_perthread_sync_d2h.argtypes = [C.c_void_p, C.c_int]
     lib.mpgos_perthread_solve.argtypes = [C.c_void_p, C.c_void_p]
     lib.mpgos_perthread_solve_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
-    for f in ("insert_sync_point", "sync_solver", "sync_device", "reset_step_counters"):
+    for f in ("insert_sync_point", "sync_solver", "sync_device", "reset_step_counters", "save_state", "restore_state"):
         getattr(lib, "mpgos_perthread_" + f).argtypes = [C.c_void_p]
     lib.mpgos_perthread_read_step_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mpgos_perthread_total_steps.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -138,8 +139,10 @@ def load_library():
     lib.mpgos_perthread_builtin_desc.argtypes = [C.c_char_p, C.POINTER(_Desc)]
     lib.mpgos_perthread_builtin_launcher.restype = C.c_void_p
     lib.mpgos_perthread_builtin_launcher.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    lib.mpgos_perthread_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    lib.mpgos_perthread_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.mpgos_probe_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
-    _LIB = lib
+    _LIBS[strict] = lib
     return lib
 
 
@@ -162,8 +165,8 @@ class ProblemSolver:
     arguments, everything else keeps the reference's names."""
 
     def __init__(self, system: str, NT: int, NDO: int = 0, Algorithm: int = Algorithms.RKCK45, Precision=np.float64,
-                 Device: int = 0, InstanceOffset: int = 0, GlobalInstances: int = 0):
-        self._lib = lib = load_library()
+                 Device: int = 0, InstanceOffset: int = 0, GlobalInstances: int = 0, strict: bool = False):
+        self._lib = lib = load_library(strict)
         self._h = None
         self.system = system
         self.dtype = np.dtype(Precision)
@@ -338,6 +341,25 @@ class ProblemSolver:
         _check(self._lib, self._lib.mpgos_perthread_total_steps(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def Upload(self, variable: int, host_ptr: int, nbytes: int):
+        """Asynchronous H2D copy of one variable from a caller-owned host array (address, bytes)."""
+        _check(self._lib, self._lib.mpgos_perthread_upload(self._h, int(variable), host_ptr, nbytes))
+
+    def Download(self, variable: int, host_ptr: int, nbytes: int):
+        _check(self._lib, self._lib.mpgos_perthread_download(self._h, int(variable), host_ptr, nbytes))
+
+    def SaveState(self):
+        """Device-resident checkpoint of all per-instance buffers (asynchronous)."""
+        _check(self._lib, self._lib.mpgos_perthread_save_state(self._h))
+
+    def RestoreState(self):
+        _check(self._lib, self._lib.mpgos_perthread_restore_state(self._h))
+
+    @property
+    def stream(self) -> int:
+        """The solver's cudaStream_t as an integer (for torch.cuda.ExternalStream)."""
+        return int(self._lib.mpgos_perthread_stream(self._h) or 0)
+
     def SolveTimed(self, phases: int = 1) -> float:
         """Enqueue ``phases`` Solve() calls bracketed by CUDA events on the solver's stream; returns milliseconds."""
         ms = C.c_float()
@@ -389,12 +411,12 @@ def read_back(ps: ProblemSolver, wl):
 
 
 def run_workload(wl, buffers=None, phases: Optional[int] = None, lane_refill: Optional[bool] = None, device: int = 0,
-                 threads_per_block: Optional[int] = None):
+                 threads_per_block: Optional[int] = None, strict: bool = False):
     """Integrate a workload on the GPU through the public API; returns (buffers_after, attempted, accepted)
     with the same meaning as the checker's ``run_oracle`` / ``run_ref``."""
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
-    with ProblemSolver(wl.name, b.NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=device) as ps:
+    with ProblemSolver(wl.name, b.NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=device, strict=strict) as ps:
         apply_workload(ps, wl, b)
         if lane_refill is not None:
             ps.SolverOption(Options.LaneRefill, int(lane_refill))

@@ -28,17 +28,61 @@ def rel_err(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
 
 
-@pytest.mark.parametrize("name", ["lorenz_rk4_f64", "poincare_rk4_f64"])
 @pytest.mark.parametrize("refill", [0, 1])
-def test_rk4_fixed_step_endpoints_1e12(name, refill, cases, pkg, oracle):
-    wl, phases = cases[name]
+def test_rk4_fixed_step_endpoints_1e12_duffing(refill, cases, pkg, oracle):
+    """The north_star gate on the events-free Duffing sweep (C1a): 2516 fixed steps, 4 phases."""
+    wl, phases = cases["poincare_rk4_f64"]
     ref, ratt, racc = oracle.run_oracle(wl, phases=phases)
     out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
     assert np.array_equal(att, ratt) and np.array_equal(acc, racc)          # step counts: exact
     assert np.array_equal(out.ActualTime, ref.ActualTime)
-    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-12          # the north_star gate
-    gold = np.load(os.path.join(GOLDEN, name + ".npz"))                      # and against the reference's own output
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-12
+    gold = np.load(os.path.join(GOLDEN, "poincare_rk4_f64.npz"))            # and against the reference's own output
     assert rel_err(out.ActualState, gold["ActualState"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("refill", [0, 1])
+def test_rk4_fixed_step_lorenz(refill, cases, pkg, oracle):
+    """Lorenz RK4, dt = 1e-3.  Over the full horizon (10 001 steps) rho > 13.9 shows transient chaos, which
+    amplifies the one-rounding difference between fused and unfused multiply-add; so the 1e-12 gate is
+    applied over a short horizon (north_star: "chaotic cases are compared over a short horizon"), the
+    full horizon is held to 1e-12 for the non-chaotic part of the sweep (rho < 13) and to its median
+    elsewhere, and test_strict_build_is_bit_identical removes the FMA difference altogether."""
+    wl, phases = cases["lorenz_rk4_f64"]
+    ref, ratt, racc = oracle.run_oracle(wl, phases=phases)
+    out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
+    assert np.array_equal(att, ratt) and np.array_equal(acc, racc) and (att == 10001).all()
+    assert np.array_equal(out.ActualTime, ref.ActualTime)
+    err = rel_err(out.ActualState, ref.ActualState)
+    calm = wl.buffers.ControlParameters[0] < 13.0
+    assert err[:, calm].max() < 1e-12
+    assert np.median(err) < 1e-14 and err.max() < 1e-8
+    short = copy.copy(wl)
+    short.buffers = wl.buffers.copy()
+    short.buffers.TimeDomain[1, :] = 1.0
+    ref, ratt, _ = oracle.run_oracle(short, phases=1)
+    out, att, _ = pkg.run_workload(short, phases=1, lane_refill=refill)
+    assert np.array_equal(att, ratt)
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-12
+
+
+def test_strict_build_is_bit_identical(cases, pkg, oracle):
+    """The same kernel source compiled with -fmad=false (libmpgos_b200_strict.so) reproduces the reference's
+    own output BIT FOR BIT where the right-hand side has no transcendental function: Lorenz RK4 over
+    10 001 steps (golden vector generated from the reference's kernel source), for both lane mappings."""
+    wl, phases = cases["lorenz_rk4_f64"]
+    gold = np.load(os.path.join(GOLDEN, "lorenz_rk4_f64.npz"))
+    for refill in (0, 1):
+        out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill, strict=True)
+        assert np.array_equal(out.ActualState, gold["ActualState"])
+        assert np.array_equal(out.ActualTime, gold["ActualTime"])
+        assert np.array_equal(att, gold["attempted"]) and np.array_equal(acc, gold["accepted"])
+    # adaptive: only the pow-free step-size formula differs (~1 ulp in dt), everything else is the same arithmetic
+    wl, phases = cases["lorenz_rkck45_f64"]
+    gold = np.load(os.path.join(GOLDEN, "lorenz_rkck45_f64.npz"))
+    out, att, acc = pkg.run_workload(wl, phases=phases, strict=True)
+    assert np.array_equal(att, gold["attempted"]) and np.array_equal(acc, gold["accepted"])
+    assert rel_err(out.ActualState, gold["ActualState"]).max() < 1e-9
 
 
 # name -> (endpoint tolerance, fraction of instances whose step counts must match exactly, max step-count difference)
