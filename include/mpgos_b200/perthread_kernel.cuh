@@ -31,6 +31,9 @@
 namespace mpgos_b200 {
 
 constexpr int kMaxThreadsPerBlock = 256;
+#ifndef MPGOS_B200_MIN_BLOCKS_PER_SM
+#define MPGOS_B200_MIN_BLOCKS_PER_SM 1
+#endif
 constexpr int kAlgRK4 = 0, kAlgRKCK45 = 1;
 
 template <int N> struct AtLeastOne { static constexpr int value = (N > 0 ? N : 1); };
@@ -56,6 +59,7 @@ struct PerThreadArgs
 	int  DeviceMessages;
 	P    InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit;
 	P    DenseOutputMinimumTimeStep;
+	P    MinimumTimeStepGuard;    // MinimumTimeStep * 1.01 (ErrorControllers.cuh:63,72), formed once on the host in P
 	P    RelativeTolerance[SD];
 	P    AbsoluteTolerance[SD];
 	P    EventTolerance[AtLeastOne<NE>::value];
@@ -63,38 +67,71 @@ struct PerThreadArgs
 };
 
 // ---------------------------------------------------------------------------------------------
+// Cash-Karp tableau (Steppers.cuh:167-285) in constant memory.  On sm_100a ptxas feeds FP64
+// instructions with constants from uniform registers; literals are rebuilt with two UMOVs per
+// use once the 63 uniform registers run out (66 UMOVs per step for Lorenz), whereas constant
+// memory is fetched two doubles at a time (LDCU.128).  Same values as the reference's literals.
+enum CashKarp
+{
+	CK_C2, CK_C3, CK_C4, CK_C6,
+	CK_A21, CK_A31, CK_A32, CK_A41, CK_A42, CK_A43, CK_A51, CK_A52, CK_A53, CK_A54,
+	CK_A61, CK_A62, CK_A63, CK_A64, CK_A65,
+	CK_B1, CK_B3, CK_B4, CK_B6,
+	CK_E1, CK_E3, CK_E4, CK_E5, CK_E6,
+	CK_ERRFLOOR, CK_SAFETY,
+	CK_COUNT
+};
+
+#define MPGOS_B200_CK_TABLE(T)                                                                                     \
+	{ (T)(1.0 / 5.0), (T)(3.0 / 10.0), (T)(3.0 / 5.0), (T)(7.0 / 8.0),                                              \
+	  (T)(1.0 / 5.0), (T)(3.0 / 40.0), (T)(9.0 / 40.0), (T)(3.0 / 10.0), (T)(-9.0 / 10.0), (T)(6.0 / 5.0),          \
+	  (T)(-11.0 / 54.0), (T)(5.0 / 2.0), (T)(-70.0 / 27.0), (T)(35.0 / 27.0),                                       \
+	  (T)(1631.0 / 55296.0), (T)(175.0 / 512.0), (T)(575.0 / 13824.0), (T)(44275.0 / 110592.0), (T)(253.0 / 4096.0), \
+	  (T)(37.0 / 378.0), (T)(250.0 / 621.0), (T)(125.0 / 594.0), (T)(512.0 / 1771.0),                               \
+	  (T)(37.0 / 378.0 - 2825.0 / 27648.0), (T)(250.0 / 621.0 - 18575.0 / 48384.0),                                 \
+	  (T)(125.0 / 594.0 - 13525.0 / 55296.0), (T)(0.0 - 277.0 / 14336.0), (T)(512.0 / 1771.0 - 1.0 / 4.0),          \
+	  (T)(1e-18), (T)(0.9) }
+
+static __constant__ double kCashKarpF64[CK_COUNT] = MPGOS_B200_CK_TABLE(double);
+static __constant__ float  kCashKarpF32[CK_COUNT] = MPGOS_B200_CK_TABLE(float);
+
+template <class P> __device__ __forceinline__ P ck(int i);
+template <> __device__ __forceinline__ double ck<double>(int i) { return kCashKarpF64[i]; }
+template <> __device__ __forceinline__ float  ck<float>(int i)  { return kCashKarpF32[i]; }
+
+// SFU approximations without the denormal / special-case wrappers of the CUDA math library
+// (operands are range-checked by the caller).
+__device__ __forceinline__ float sfu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sfu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// ---------------------------------------------------------------------------------------------
 // numeric helpers
 
 template <class P> struct Num;
 
+// `top(x)` is the word that holds sign and exponent; for positive normal numbers it orders like
+// the value, and one unsigned comparison of (top - kLow) against kSpan tests
+// "positive, finite, and 2^-100 <= x < 2^30" (2^-60 <= x < 2^30 in single precision).
 template <> struct Num<double>
 {
 	static __device__ __forceinline__ bool finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
-	static __device__ __forceinline__ int  exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
-	static constexpr int kBias = 1023, kHalfRange = 100, kNewton = 2;
+	static __device__ __forceinline__ unsigned top(double x) { return (unsigned)__double2hiint(x); }
+	static constexpr unsigned kLow = (1023u - 100u) << 20, kSpan = 130u << 20;
+	static constexpr int kRatioLimit = 98 << 20;    // top(tol) - top(err) below this  =>  tol/err < 2^99 < 1e30
+	static constexpr int kNewton = 2;
 	static __device__ __forceinline__ float  narrow(double x) { return __double2float_rn(x); }
 };
 
 template <> struct Num<float>
 {
 	static __device__ __forceinline__ bool finite(float x) { return (__float_as_int(x) & 0x7f800000) != 0x7f800000; }
-	static __device__ __forceinline__ int  exponent(float x) { return (__float_as_int(x) >> 23) & 0xff; }
-	static constexpr int kBias = 127, kHalfRange = 60, kNewton = 1;
+	static __device__ __forceinline__ unsigned top(float x) { return (unsigned)__float_as_int(x); }
+	static constexpr unsigned kLow = (127u - 60u) << 23, kSpan = 90u << 23;
+	static constexpr int kRatioLimit = 98 << 23;
+	static constexpr int kNewton = 1;
 	static __device__ __forceinline__ float  narrow(float x) { return x; }
 };
-
-// True when tol and err are positive normal numbers whose magnitudes, cross products and ratio
-// stay well inside the single-precision range (so the seed below is valid) and whose ratio is
-// below the reference's initial value 1e30 of the running minimum (ErrorControllers.cuh:38).
-template <class P>
-__device__ __forceinline__ bool ratio_in_fast_range(P tol, P err)
-{
-	const int et = Num<P>::exponent(tol), ee = Num<P>::exponent(err);
-	const bool sign_ok = (tol > P(0)) && (err > P(0));
-	return sign_ok && ((unsigned)(et - (Num<P>::kBias - Num<P>::kHalfRange)) < (unsigned)(Num<P>::kHalfRange + 30))
-	               && ((unsigned)(ee - (Num<P>::kBias - Num<P>::kHalfRange)) < (unsigned)(Num<P>::kHalfRange + 30))
-	               && (et - ee < 98);
-}
 
 // y = (tol/err)^(1/5) if accept, (tol/err)^(1/4) otherwise, without FP64 division or pow.
 // With a = err/tol, y = a^(-1/n) is the fixed point of the division-free Newton map
@@ -109,8 +146,8 @@ __device__ __forceinline__ P ratio_root_fast(P tol, P err, bool accept)
 	const float tf  = Num<P>::narrow(tol);
 	const float ef  = Num<P>::narrow(err);
 	const float inv = accept ? 0.2f : 0.25f;
-	P y = (P)exp2f((__log2f(tf) - __log2f(ef)) * inv);
-	const P rn = (P)(__frcp_rn(tf) * inv);
+	P y = (P)sfu_ex2((sfu_lg2(tf) - sfu_lg2(ef)) * inv);
+	const P rn = (P)(sfu_rcp(tf) * inv);
 	#pragma unroll
 	for (int it = 0; it < Num<P>::kNewton; it++)
 	{
@@ -149,7 +186,7 @@ struct LaneState
 // user's PerThread_* functions).
 
 template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL>
-__global__ void __launch_bounds__(kMaxThreadsPerBlock)
+__global__ void __launch_bounds__(kMaxThreadsPerBlock, MPGOS_B200_MIN_BLOCKS_PER_SM)
 perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 {
 	// shared parameters: staged once per block (Solver.cuh:66-88); unlike the reference we
@@ -269,97 +306,113 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 		}
 		else
 		{
-			// Steppers.cuh:122-290 -- Cash-Karp 4(5)
+			// Steppers.cuh:122-290 -- Cash-Karp 4(5); expression shapes as in the reference
 			P X[SD], T, k1[SD], k2[SD], k3[SD], k4[SD], k5[SD], k6[SD], err[SD];
 			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
 
-			T = s.t + dt * P(1.0 / 5.0);
+			T = s.t + dt * ck<P>(CK_C2);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(1.0 / 5.0) * k1[i]);
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A21) * k1[i]);
 			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
 
-			T = s.t + dt * P(3.0 / 10.0);
+			T = s.t + dt * ck<P>(CK_C3);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(3.0 / 40.0) * k1[i] + P(9.0 / 40.0) * k2[i]);
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A31) * k1[i] + ck<P>(CK_A32) * k2[i]);
 			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
 
-			T = s.t + dt * P(3.0 / 5.0);
+			T = s.t + dt * ck<P>(CK_C4);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(3.0 / 10.0) * k1[i] + P(-9.0 / 10.0) * k2[i] + P(6.0 / 5.0) * k3[i]);
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A41) * k1[i] + ck<P>(CK_A42) * k2[i] + ck<P>(CK_A43) * k3[i]);
 			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
 
 			T = s.t + dt;
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(-11.0 / 54.0) * k1[i] + P(5.0 / 2.0) * k2[i] + P(-70.0 / 27.0) * k3[i] + P(35.0 / 27.0) * k4[i]);
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A51) * k1[i] + ck<P>(CK_A52) * k2[i] + ck<P>(CK_A53) * k3[i] + ck<P>(CK_A54) * k4[i]);
 			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
 
-			T = s.t + dt * P(7.0 / 8.0);
+			T = s.t + dt * ck<P>(CK_C6);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (P(1631.0 / 55296.0) * k1[i] + P(175.0 / 512.0) * k2[i] + P(575.0 / 13824.0) * k3[i] + P(44275.0 / 110592.0) * k4[i] + P(253.0 / 4096.0) * k5[i]);
+			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A61) * k1[i] + ck<P>(CK_A62) * k2[i] + ck<P>(CK_A63) * k3[i] + ck<P>(CK_A64) * k4[i] + ck<P>(CK_A65) * k5[i]);
 			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
 
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
-				xn[i] = s.x[i] + dt * (P(37.0 / 378.0) * k1[i] + P(250.0 / 621.0) * k3[i] + P(125.0 / 594.0) * k4[i] + P(512.0 / 1771.0) * k6[i]);
-				const P e = P(37.0 / 378.0 - 2825.0 / 27648.0) * k1[i] + P(250.0 / 621.0 - 18575.0 / 48384.0) * k3[i]
-				          + P(125.0 / 594.0 - 13525.0 / 55296.0) * k4[i] + P(0.0 - 277.0 / 14336.0) * k5[i] + P(512.0 / 1771.0 - 1.0 / 4.0) * k6[i];
-				err[i] = dt * fabs(e) + P(1e-18);
-				finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
+				xn[i] = s.x[i] + dt * (ck<P>(CK_B1) * k1[i] + ck<P>(CK_B3) * k3[i] + ck<P>(CK_B4) * k4[i] + ck<P>(CK_B6) * k6[i]);
+				const P e = ck<P>(CK_E1) * k1[i] + ck<P>(CK_E3) * k3[i] + ck<P>(CK_E4) * k4[i] + ck<P>(CK_E5) * k5[i] + ck<P>(CK_E6) * k6[i];
+				err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
 			}
 
-			// ErrorControllers.cuh:24-86 -- accept test, limiting component, new step size
+			// ErrorControllers.cuh:24-86 -- accept test, limiting component, new step size.
+			// The selects are ordered so that a NaN/Inf in xn or err reaches tol/err unchanged; the
+			// range test below then routes the step to the exact path, which also sets `finite`.
 			P tol[SD];
+			unsigned outside = 0;      // max over all tol_i, err_i of (top - kLow); >= kSpan means "leave the fast path"
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
-				tol[i] = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(s.x[i])), a.AbsoluteTolerance[i]);
+				const P ax = fabs(s.x[i]), an = fabs(xn[i]);
+				const P m  = (ax > an) ? ax : an;
+				const P t  = a.RelativeTolerance[i] * m;
+				tol[i] = (a.AbsoluteTolerance[i] > t) ? a.AbsoluteTolerance[i] : t;
 				update = update && (err[i] < tol[i]);
+				outside = max(outside, max(Num<P>::top(tol[i]) - Num<P>::kLow, Num<P>::top(err[i]) - Num<P>::kLow));
 			}
 			// component with the smallest tol/err: tol_a/err_a < tol_b/err_b  <=>  tol_a err_b < tol_b err_a
 			P tsel = tol[0], esel = err[0];
-			bool fast = ratio_in_fast_range(tol[0], err[0]);
 			#pragma unroll
 			for (int i = 1; i < SD; i++)
 			{
-				fast = fast && ratio_in_fast_range(tol[i], err[i]);
 				const bool less = tol[i] * esel < tsel * err[i];
 				tsel = less ? tol[i] : tsel;
 				esel = less ? err[i] : esel;
 			}
+			const bool fast = (outside < Num<P>::kSpan) && ((int)(Num<P>::top(tsel) - Num<P>::top(esel)) < Num<P>::kRatioLimit);
+			const bool at_minimum = dt < a.MinimumTimeStepGuard;
 			P mult;
-			if (finite && fast)
-				mult = P(0.9) * ratio_root_fast<P>(tsel, esel, update);
-			else
+			if (fast)
 			{
-				P rel = P(1e30);
-				#pragma unroll
-				for (int i = 0; i < SD; i++) rel = fmin(rel, tol[i] / err[i]);
-				mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
-				if (!Num<P>::finite(mult)) finite = false;
-			}
-
-			const bool at_minimum = dt < a.MinimumTimeStep * P(1.01);
-			if (!finite)
-			{
-				mult = a.TimeStepShrinkLimit;
-				update = false;
+				mult = ck<P>(CK_SAFETY) * ratio_root_fast<P>(tsel, esel, update);
 				if (at_minimum)
 				{
-					if (a.DeviceMessages) printf("Error: State is not a finite number even with the minimal step size. Try to use less stringent tolerances. (thread id: %d)\n", gid);
-					terminate = true;
+					if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
+					update = true;
 				}
 			}
-			else if (at_minimum)
+			else
 			{
-				if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
-				update = true;
+				// exact reference arithmetic (division, pow) for exotic operand ranges and non-finite states
+				P rel = P(1e30);
+				#pragma unroll
+				for (int i = 0; i < SD; i++)
+				{
+					finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
+					rel = fmin(rel, fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(s.x[i])), a.AbsoluteTolerance[i]) / err[i]);
+				}
+				mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+				if (!Num<P>::finite(mult)) finite = false;
+				if (!finite)
+				{
+					mult = a.TimeStepShrinkLimit;
+					update = false;
+					if (at_minimum)
+					{
+						if (a.DeviceMessages) printf("Error: State is not a finite number even with the minimal step size. Try to use less stringent tolerances. (thread id: %d)\n", gid);
+						terminate = true;
+					}
+				}
+				else if (at_minimum)
+				{
+					if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
+					update = true;
+				}
 			}
-			mult = fmin(mult, a.TimeStepGrowLimit);
-			mult = fmax(mult, a.TimeStepShrinkLimit);
+			// all operands positive: plain compare-selects instead of fmin/fmax
+			mult = (mult > a.TimeStepGrowLimit) ? a.TimeStepGrowLimit : mult;
+			mult = (mult < a.TimeStepShrinkLimit) ? a.TimeStepShrinkLimit : mult;
 			P dt_new = dt * mult;
-			dt_new = fmin(dt_new, a.MaximumTimeStep);
-			dt_new = fmax(dt_new, a.MinimumTimeStep);
+			dt_new = (dt_new > a.MaximumTimeStep) ? a.MaximumTimeStep : dt_new;
+			dt_new = (dt_new < a.MinimumTimeStep) ? a.MinimumTimeStep : dt_new;
 			s.dt_new = dt_new;
 		}
 
@@ -520,6 +573,7 @@ struct PerThreadLauncher
 		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;
 		a.MinimumTimeStep = (P)L->MinimumTimeStep;  a.TimeStepGrowLimit = (P)L->TimeStepGrowLimit;
 		a.TimeStepShrinkLimit = (P)L->TimeStepShrinkLimit;  a.DenseOutputMinimumTimeStep = (P)L->DenseOutputMinimumTimeStep;
+		a.MinimumTimeStepGuard = a.MinimumTimeStep * P(1.01);
 		for (int i = 0; i < SD; i++) { a.RelativeTolerance[i] = (P)L->RelativeTolerance[i];  a.AbsoluteTolerance[i] = (P)L->AbsoluteTolerance[i]; }
 		for (int i = 0; i < AtLeastOne<NE>::value; i++)
 		{

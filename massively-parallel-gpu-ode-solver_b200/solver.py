@@ -90,6 +90,9 @@ class _Desc(C.Structure):
 
 def library_path(strict: bool = False) -> str:
     """The product library, or (strict) the same sources built with -fmad=false for the parity tests."""
+    override = os.environ.get("MPGOS_B200_LIBRARY")     # development: A/B builds of the same library
+    if override and not strict:
+        return override
     return os.path.join(HERE, "libmpgos_b200_strict.so" if strict else "libmpgos_b200.so")
 
 
