@@ -261,6 +261,22 @@ def keller_miksis_t5(NT: int = 1 << 18, phases: int = 32, ndo: int = 200) -> Wor
     return Workload(name, shape, opt, b, phases, 413, "T5 Keller-Miksis frequency sweep")
 
 
+def vanderpol_example(NT: int = 1536, algorithm: int = RKCK45, phases: int = 2) -> Workload:
+    """The user-written system of examples/vanderpol (drop-in test; not a BASELINE configuration):
+    same options and initial data as examples/vanderpol/vanderpol_dropin.cu."""
+    shape = Shape(SD=2, NCP=1, NSP=2, NISP=1, NE=2, NA=2, NIA=2, NDO=64, Algorithm=algorithm)
+    b = Buffers(shape, NT)
+    b.TimeDomain[1, :] = 1.0e3
+    b.ActualState[0, :] = 2.0
+    b.ControlParameters[0, :] = linspace(0.1, 4.0, NT)
+    b.SharedParameters[:] = (0.5, 1.1)
+    b.IntegerSharedParameters[:] = 3
+    opt = Options(InitialTimeStep=1.0e-2, ThreadsPerBlock=64, DenseOutputMinimumTimeStep=0.0537, DenseOutputSaveFrequency=2,
+                  RelativeTolerance=np.full(2, 1e-9), AbsoluteTolerance=np.full(2, 1e-9),
+                  EventTolerance=np.full(2, 1e-7), EventDirection=np.array([-1, 0], np.int32))
+    return Workload("vanderpol", shape, opt, b, phases, 6 * 9 + 55 * 2 + 9 + 6, "user-defined Van der Pol (examples/vanderpol)")
+
+
 GENERATORS = {
     "lorenz": lorenz,
     "duffing": duffing_t1,

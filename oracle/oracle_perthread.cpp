@@ -124,6 +124,7 @@ int route(const char* system, int algorithm, int precision, int ndo, const oracl
 	if (!std::strcmp(system, "impact"))             return dispatch<Impact>(algorithm, precision, ndo, b, o, shape);
 	if (!std::strcmp(system, "kellermiksis"))       return dispatch<KellerMiksisPlain>(algorithm, precision, ndo, b, o, shape);
 	if (!std::strcmp(system, "kellermiksis_dense")) return dispatch<KellerMiksisDense>(algorithm, precision, ndo, b, o, shape);
+	if (!std::strcmp(system, "vanderpol"))          return dispatch<VanDerPol>(algorithm, precision, ndo, b, o, shape);
 	return 1;
 }
 

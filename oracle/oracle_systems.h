@@ -171,5 +171,47 @@ struct KellerMiksis : NoCallbacks<P>
 	}
 };
 
+// examples/vanderpol/VanDerPol_SystemDefinition.cuh -- a user-written system (not from the reference)
+// used by the drop-in test: forced Van der Pol oscillator with two events, accessories, integer
+// shared parameter, dense output and a Finalization that moves the time domain.
+template <class P, class L>
+struct VanDerPol : NoCallbacks<P>
+{
+	enum { SD = 2, NCP = 1, NSP = 2, NISP = 1, NE = 2, NA = 2, NIA = 2 };
+	static void ode_function(int, int, P* F, P* X, P T, P* cPAR, P* sPAR, int*, P*, int*)
+	{
+		F[0] = X[1];
+		F[1] = cPAR[0] * (L(1.0) - X[0] * X[0]) * X[1] - X[0] + sPAR[0] * std::cos(sPAR[1] * T);
+	}
+	static void event_function(int, int, P* EF, P, P, P*, P* X, P*, P*, int*, P*, int*)
+	{
+		EF[0] = X[0];
+		EF[1] = X[1];
+	}
+	static void action_after_event_detection(int, int, int IDX, int& UDT, P& T, P&, P*, P*, P*, P*, int* sPARi, P* ACC, int* ACCi)
+	{
+		if (IDX == 0)
+		{
+			ACCi[0]++;
+			ACC[1] = T;
+			if (ACCi[0] == sPARi[0]) UDT = 1;
+		}
+	}
+	static void action_after_successful_time_step(int, int, int&, P&, P&, P*, P* X, P*, P*, int*, P* ACC, int* ACCi)
+	{
+		if (X[0] > ACC[0]) ACC[0] = X[0];
+		ACCi[1]++;
+	}
+	static void initialization(int, int, int& DOIDX, P& T, P&, P* TD, P* X, P*, P*, int*, P* ACC, int* ACCi)
+	{
+		T = TD[0];
+		DOIDX = 0;
+		ACC[0] = X[0];
+		ACC[1] = TD[0];
+		ACCi[0] = 0;
+	}
+	static void finalization(int, int, int&, P& T, P&, P* TD, P*, P*, P*, int*, P*, int*) { TD[0] = T; }
+};
+
 } // namespace oracle
 #endif
