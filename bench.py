@@ -51,16 +51,8 @@ def build_workload(W, name: str, precision: str, NT: int, rank: int, world: int)
            "kellermiksis": lambda n: W.keller_miksis_t5(NT=n, ndo=0),
            "kellermiksis_dense": lambda n: W.keller_miksis_t5(NT=n, ndo=200),
            "duffing": lambda n: W.duffing_t1(NT=n, algorithm=W.RK4)}[name]
-    full = gen(NT * world)
-    if world == 1:
-        return full
-    tile = 4096
-    i = np.arange(NT)
-    g = (i // tile) * (world * tile) + rank * tile + (i % tile)
-    import copy
-    wl = copy.copy(full)
-    wl.buffers = full.buffers.take(g)
-    return wl
+    sharding = importlib.import_module("massively-parallel-gpu-ode-solver_b200.sharding")
+    return sharding.shard_workload(gen(NT * world), NT, rank, world)
 
 
 class ClockSampler:
@@ -270,15 +262,10 @@ def main():
     final_state_checksum = float(pinned_out[V.ActualState].double().sum())
 
     # ---- reduce over ranks -------------------------------------------------------------------------
-    if world > 1:
-        t = torch.tensor([region_ms, e2e_s, float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        region_ms, e2e_s, kmean = t.tolist()
-        c = torch.tensor([attempted, accepted, e2e_attempted], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        attempted, accepted, e2e_attempted = [int(x) for x in c.tolist()]
-    else:
-        kmean = float(np.mean(kernel_ms))
+    sharding = importlib.import_module("massively-parallel-gpu-ode-solver_b200.sharding")
+    (region_ms, e2e_s, kmean), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms))],
+                                                                   [attempted, accepted, e2e_attempted], device="cuda")
+    attempted, accepted, e2e_attempted = [int(x) for x in counts]
 
     if rank == 0:
         value = attempted / (region_ms * 1e-3)

@@ -257,7 +257,7 @@ public:
 	{
 		BoundCheck("SetHost", "ProblemNumber", ProblemNumber, 0, NT - 1);
 		if (Variable == ActualTime)      h_ActualTime[ProblemNumber] = (Precision)Value;
-		else if (Variable == DenseIndex) h_DenseOutputIndex[ProblemNumber] = (int)Value;
+		else if (Variable == DenseIndex) { BoundCheck("SetHost", "DenseIndex-Value", (int)Value, 0, NDO - 1); h_DenseOutputIndex[ProblemNumber] = (int)Value; }   // value check as Interface.cuh:770
 		else NotApplicable("SetHost", VariablesToString(Variable));
 	}
 

@@ -267,6 +267,8 @@ class ProblemSolver:
             a = self.host(var)
             if a.ndim != 1 or Variables(var) not in (Variables.ActualTime, Variables.DenseIndex):
                 raise MpgosError(f"SetHost with 3 arguments is not applicable to {Variables(var).name}")
+            if Variables(var) == Variables.DenseIndex:
+                self._bound("DenseIndex-Value", int(value), d.NDO - 1)      # value check as Interface.cuh:770
             a[problem] = value
         else:
             raise TypeError("SetHost takes 3, 4 or 5 arguments")

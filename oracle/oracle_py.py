@@ -136,3 +136,38 @@ def run_oracle(wl, buffers=None, phases: Optional[int] = None, host_threads: int
     if rc != 0:
         raise RuntimeError(f"oracle_perthread_run failed: {rc}")
     return out, att, acc
+
+
+# ---- the reference compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_*.so) -------------------------
+
+def ref_gpu_library_path(wl) -> str:
+    algo = {0: "rk4", 1: "rkck45"}[wl.shape.Algorithm]
+    return os.path.join(HERE, "_ref", f"libref_gpu_{wl.name}_{algo}_{_prec_tag(wl.shape.dtype)}.so")
+
+
+def ref_gpu_available(wl) -> bool:
+    return os.path.exists(ref_gpu_library_path(wl))
+
+
+_REFGPU = {}
+
+
+def run_ref_gpu(wl, buffers=None, phases: Optional[int] = None, threads_per_block: int = 64, repeats: int = 1):
+    """Run the REFERENCE MPGOS kernel on the GPU; returns (buffers_after, kernel_ms) -- kernel_ms is the best
+    device time of the Solve() calls of one run over `repeats` runs (CUDA events, copies excluded)."""
+    path = ref_gpu_library_path(wl)
+    lib = _REFGPU.get(path)
+    if lib is None:
+        lib = _REFGPU[path] = C.CDLL(path)
+    s = _Shape()
+    lib.ref_perthread_shape(C.byref(s))
+    _check_shape(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    if out.NT > lib.ref_perthread_gpu_capacity():
+        raise ValueError("sweep larger than the capacity the reference library was compiled for")
+    cb, co, att, acc, _keep = _pack(wl, out, wl.phases if phases is None else phases, 1)
+    ms = C.c_float()
+    rc = lib.ref_perthread_gpu_run(C.byref(cb), C.byref(co), threads_per_block, repeats, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"ref_perthread_gpu_run failed: {rc}")
+    return out, ms.value
