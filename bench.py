@@ -129,6 +129,7 @@ def main():
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -289,9 +290,21 @@ def main():
                "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_s / args.steps * 1e3, "state_checksum": final_state_checksum},
                "gpu_launches": args.steps, "clocks": clocks}
+        if world == 1 and not args.no_reference_gpu:
+            # reported baseline, not a target: the reference MPGOS compiled for sm_100a, same inputs, same event bracket
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "oracle"))
+                import oracle_py
+                if oracle_py.ref_gpu_available(wl):
+                    _, ref_ms = oracle_py.run_ref_gpu(wl, phases=1, threads_per_block=64, repeats=3)
+                    out["reference_gpu"] = {"kernel_ms": ref_ms, "value": per_rank_attempted_per_launch / (ref_ms * 1e-3), "unit": "system-steps/s",
+                                            "speedup_kernel": ref_ms / kmean,
+                                            "what": "reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a (oracle/_ref), 64 threads/block, best of 3, same inputs; step count taken from our counters"}
+            except Exception as e:   # the baseline must never break the bench line
+                out["reference_gpu"] = {"unavailable": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = args.cpu_sample or (1 << 18 if threads >= 16 else 1 << 16)
+            sample = args.cpu_sample or (1 << 19 if threads >= 16 else 1 << 17)
             n, s, kind, nt = cpu_reference_run(W, args.workload, args.precision, sample, threads)
             out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind,
                                    "sample": f"every {max(NT // nt, 1)}-th instance of the sweep ({nt} instances), one phase, {threads} host threads, {s:.1f} s"}

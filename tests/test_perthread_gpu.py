@@ -194,3 +194,45 @@ def test_full_size_properties_lorenz(pkg, workloads):
     sub.buffers = wl.buffers.take(idx)
     sout, satt, _ = pkg.run_workload(sub, phases=1)
     assert np.array_equal(sout.ActualState, out.ActualState[:, idx]) and np.array_equal(satt, att[idx])
+
+
+# ---- against the REFERENCE MPGOS itself, compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_*.so) --------------
+
+def _need_ref_gpu(oracle, wl):
+    if not oracle.ref_gpu_available(wl):
+        pytest.skip("oracle/_ref/libref_gpu_*.so not built (needs /root/reference at build time)")
+
+
+@pytest.mark.parametrize("name", ["lorenz_rk4_f64", "poincare_rk4_f64", "duffing_rk4_f64"])
+def test_rk4_is_bit_identical_to_reference_mpgos_on_the_same_gpu(name, cases, pkg, oracle):
+    """Same compiler, same math library, same FMA contraction: with the fixed-step scheme (no controller
+    formula involved) our kernel reproduces the reference's kernel BIT FOR BIT -- states, times, accessories,
+    event counters and every stored dense-output point -- including event refinement (duffing)."""
+    wl, phases = cases[name]
+    _need_ref_gpu(oracle, wl)
+    ref, _ = oracle.run_ref_gpu(wl, phases=phases)
+    for refill in (0, 1):
+        out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
+        for f in RESULT_FIELDS:
+            a, b = getattr(out, f), getattr(ref, f)
+            if f in ("DenseTime", "DenseState"):     # slots beyond the dense index are never written by either
+                n = int(ref.DenseIndex.min()) if ref.DenseIndex.size else 0
+                a, b = a[:n], b[:n]
+            assert np.array_equal(a, b, equal_nan=True), (name, f)
+
+
+@pytest.mark.parametrize("name,tol,frac", [("lorenz_rkck45_f64", 1e-9, 0.999), ("kellermiksis_dense_rkck45_f64", 1e-11, 0.999),
+                                           ("duffing_rkck45_f64", 1e-7, 0.95), ("impact_rkck45_f64", 1e-7, 0.95)])
+def test_rkck45_against_reference_mpgos_on_the_same_gpu(name, tol, frac, cases, pkg, oracle):
+    """Adaptive runs differ from the reference's kernel only through the pow-free step-size formula (~1 ulp in
+    dt): at least `frac` of the instances agree to `tol`; the rest are instances whose event refinement or
+    accept/reject decisions sit on a rounding tie (they differ between the reference's own CPU and GPU builds too)."""
+    wl, phases = cases[name]
+    _need_ref_gpu(oracle, wl)
+    ref, _ = oracle.run_ref_gpu(wl, phases=phases)
+    out, att, acc = pkg.run_workload(wl, phases=phases)
+    err = rel_err(out.ActualState, ref.ActualState).max(axis=0)
+    assert (err < tol).mean() >= frac
+    assert np.median(err) < 1e-12
+    if ref.IntegerAccessories.size:
+        assert (out.IntegerAccessories == ref.IntegerAccessories).mean() >= frac
