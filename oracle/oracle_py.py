@@ -171,3 +171,89 @@ def run_ref_gpu(wl, buffers=None, phases: Optional[int] = None, threads_per_bloc
     if rc != 0:
         raise RuntimeError(f"ref_perthread_gpu_run failed: {rc}")
     return out, ms.value
+
+
+# ---- coupled (block-per-system) module ---------------------------------------------------------------------------
+
+class _CShape(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("UPS", "UD", "NC", "CBW", "CCI", "NUP", "NSP", "NGP", "NiGP", "NUA", "NiUA", "NSA", "NiSA", "NE", "NDO",
+                                        "Algorithm", "Precision")]
+
+
+class _COptions(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("InitialTimeStep", "MaximumTimeStep", "MinimumTimeStep", "TimeStepGrowLimit", "TimeStepShrinkLimit",
+                                           "DenseOutputMinimumTimeStep")] + [(n, C.c_int) for n in ("DenseOutputSaveFrequency", "ActiveSystems", "Phases", "HostThreads")]
+
+
+class _CBuffers(C.Structure):
+    _fields_ = [("NS", C.c_int)] + [(n, C.c_void_p) for n in (
+        "TimeDomain", "ActualState", "ActualTime", "UnitParameters", "SystemParameters", "GlobalParameters", "IntegerGlobalParameters",
+        "UnitAccessories", "IntegerUnitAccessories", "SystemAccessories", "IntegerSystemAccessories", "CouplingMatrix", "CouplingStrength",
+        "CouplingIndex", "RelativeTolerance", "AbsoluteTolerance", "EventTolerance", "EventDirection", "DenseOutputIndex",
+        "DenseOutputTimeInstances", "DenseOutputStates", "steps_attempted", "steps_accepted")]
+
+
+def _cpack(wl, b, phases, host_threads):
+    o = wl.options.resolved(wl.shape, b.NS)
+    att, acc = np.zeros(b.NS, np.int64), np.zeros(b.NS, np.int64)
+    keep = [o.RelativeTolerance, o.AbsoluteTolerance, o.EventTolerance, o.EventDirection]
+    cb = _CBuffers(b.NS, _ptr(b.TimeDomain), _ptr(b.ActualState), _ptr(b.ActualTime), _ptr(b.UnitParameters), _ptr(b.SystemParameters),
+                   _ptr(b.GlobalParameters), _ptr(b.IntegerGlobalParameters), _ptr(b.UnitAccessories), _ptr(b.IntegerUnitAccessories),
+                   _ptr(b.SystemAccessories), _ptr(b.IntegerSystemAccessories), _ptr(b.CouplingMatrix), _ptr(b.CouplingStrength),
+                   _ptr(b.CouplingIndex), _ptr(o.RelativeTolerance), _ptr(o.AbsoluteTolerance), _ptr(o.EventTolerance), _ptr(o.EventDirection),
+                   _ptr(b.DenseIndex), _ptr(b.DenseTime), _ptr(b.DenseState), _ptr(att), _ptr(acc))
+    co = _COptions(o.InitialTimeStep, o.MaximumTimeStep, o.MinimumTimeStep, o.TimeStepGrowLimit, o.TimeStepShrinkLimit,
+                   o.DenseOutputMinimumTimeStep, o.DenseOutputSaveFrequency, o.ActiveSystems, phases, host_threads)
+    return cb, co, att, acc, keep
+
+
+def _ccheck(s, wl):
+    sh = wl.shape
+    got = (s.UPS, s.UD, s.NC, s.CBW, s.CCI, s.NUP, s.NSP, s.NGP, s.NiGP, s.NUA, s.NiUA, s.NSA, s.NiSA, s.NE, s.NDO, s.Algorithm)
+    want = (sh.UPS, sh.UD, sh.NC, sh.CBW, sh.CCI, sh.NUP, sh.NSP, sh.NGP, sh.NiGP, sh.NUA, sh.NiUA, sh.NSA, sh.NiSA, sh.NE, sh.NDO, sh.Algorithm)
+    if got != want:
+        raise ValueError(f"coupled checker library shape {got} does not match workload shape {want}")
+
+
+_CLIBS = {}
+
+
+def run_coupled_oracle(wl, buffers=None, phases=None, host_threads: int = 1, fast: bool = False):
+    """Our CPU restatement of the block-per-system phase; returns (buffers_after, attempted, accepted) per system."""
+    path = os.path.join(HERE, "liboracle_coupled_fast.so" if fast else "liboracle_coupled.so")
+    lib = _CLIBS.get(path)
+    if lib is None:
+        lib = _CLIBS[path] = C.CDLL(path)
+    sh = wl.shape
+    s = _CShape()
+    rc = lib.oracle_coupled_query_shape(wl.name.encode(), sh.UPS, sh.CBW, sh.CCI, sh.Algorithm, sh.NDO, C.byref(s))
+    if rc != 0:
+        raise KeyError(f"coupled oracle has no system {wl.name!r} with UPS={sh.UPS} CBW={sh.CBW} CCI={sh.CCI}")
+    _ccheck(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    cb, co, att, acc, _keep = _cpack(wl, out, wl.phases if phases is None else phases, host_threads)
+    rc = lib.oracle_coupled_run(wl.name.encode(), sh.UPS, sh.CBW, sh.CCI, sh.Algorithm, sh.NDO, C.byref(cb), C.byref(co))
+    if rc != 0:
+        raise RuntimeError(f"oracle_coupled_run failed: {rc}")
+    return out, att, acc
+
+
+def coupled_ref_library_path(tag: str, gpu: bool = False) -> str:
+    return os.path.join(HERE, "_ref", f"libref_{'gpu_' if gpu else ''}coupled_{tag}.so")
+
+
+def run_coupled_ref(tag: str, wl, buffers=None, phases=None):
+    """The reference's own coupled kernel source on the host (one std::thread per CUDA thread); `tag` names the build
+    (oracle/Makefile REFCOUPLED list).  Returns buffers_after."""
+    lib = C.CDLL(coupled_ref_library_path(tag))
+    s = _CShape()
+    lib.ref_coupled_shape(C.byref(s))
+    _ccheck(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    if out.NS > lib.ref_coupled_capacity():
+        raise ValueError("more systems than the reference library was compiled for")
+    cb, co, att, acc, _keep = _cpack(wl, out, wl.phases if phases is None else phases, 1)
+    rc = lib.ref_coupled_run(C.byref(cb), C.byref(co))
+    if rc != 0:
+        raise RuntimeError(f"ref_coupled_run failed: {rc}")
+    return out

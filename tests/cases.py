@@ -32,3 +32,22 @@ def make_cases(W):
 
 RESULT_FIELDS = ("TimeDomain", "ActualState", "ActualTime", "ControlParameters", "Accessories",
                  "IntegerAccessories", "DenseIndex", "DenseTime", "DenseState")
+
+
+def make_coupled_cases(WC):
+    """name -> (reference-host build tag, workload, phases) for the block-per-system module.  Between them the builds
+    exercise all four launch variants of the reference (SingleSystem/MultipleSystems x Single/MultipleBlockLaunch) and
+    all four coupling-matrix layouts (full, banded, circulant-banded, full circulant)."""
+    c = {}
+    c["bubble_u8_rkck45"] = ("bubble_ensemble_u8_rkck45", WC.bubble_ensemble(NS=4, UPS=8, amplitude=(0.2, 1.2)), 1)
+    c["bubble_u16_rkck45"] = ("bubble_ensemble_u16_rkck45", WC.bubble_ensemble(NS=5, UPS=16, amplitude=(0.2, 1.2)), 2)
+    c["bubble_u16_rk4"] = ("bubble_ensemble_u16_rk4", WC.bubble_ensemble(NS=2, UPS=16, algorithm=WC.RK4, amplitude=(0.2, 0.6)), 1)
+    c["ring_b1c1_rkck45"] = ("duffing_ring_u14_b1c1_rkck45", WC.duffing_ring(NS=7, CBW=1, CCI=1), 2)
+    c["ring_b1c0_rkck45"] = ("duffing_ring_u14_b1c0_rkck45", WC.duffing_ring(NS=5, CBW=1, CCI=0), 1)
+    c["ring_b0c1_rk4"] = ("duffing_ring_u14_b0c1_rk4", WC.duffing_ring(NS=3, CBW=0, CCI=1, algorithm=WC.RK4), 1)
+    c["ring_b0c0_rkck45"] = ("duffing_ring_u14_b0c0_rkck45", WC.duffing_ring(NS=4, CBW=0, CCI=0), 2)
+    return c
+
+
+COUPLED_RESULT_FIELDS = ("TimeDomain", "ActualState", "ActualTime", "UnitAccessories", "IntegerUnitAccessories", "SystemAccessories",
+                         "IntegerSystemAccessories", "DenseIndex", "DenseTime", "DenseState")
