@@ -1,0 +1,558 @@
+// perblock_kernel.cuh -- block-per-system (coupled systems) ensemble integrator for sm_100a (B200).
+//
+// One thread integrates one UNIT, the units of one system occupy whole warps (a "slot"), several slots share a thread
+// block.  Same algorithm and decision semantics as the reference's coupled module -- the four kernels of
+// SourceCodes/CoupledSystmes_PerBlock_Solver.cuh:11, 787, 1508, 2215 with CoupledSystems_PerBlock_ExplicitRungeKutta_Steppers.cuh,
+// ..._ErrorControllers.cuh (safety 0.8), ..._EventHandling.cuh, ..._DenseOutput.cuh -- on a different machine mapping:
+//
+//  * a slot synchronises with its OWN named barrier (bar.sync id, count) or __syncwarp() when a system fits one warp,
+//    never with __syncthreads(): systems in a block advance independently (the reference's multi-system kernels step all
+//    systems of a block in lockstep behind ~25 block-wide barriers per RKCK45 step; here 9 slot-wide ones);
+//  * the per-system reductions (accept flag, limiting error ratio, earliest event) are warp shuffles plus one
+//    shared-memory word per warp, not shared-memory atomics (atomicAnd / CAS-loop atomicFMIN in the reference);
+//  * every thread evaluates the step-size controller redundantly from the reduced values (no thread-0 serial section,
+//    no broadcast barrier); its pow/division are replaced by the division-free Newton root of perthread_kernel.cuh;
+//  * the coupling matrices live in shared memory once per block, coupling terms are double-buffered (one barrier per
+//    stage instead of two), the column sum runs in ascending order with a single accumulator exactly like
+//    ComputeCouplingValue_* (Steppers.cuh:2551-2713), so results track the reference to rounding;
+//  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid).
+#ifndef MPGOS_B200_PERBLOCK_KERNEL_CUH
+#define MPGOS_B200_PERBLOCK_KERNEL_CUH
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include "../mpgos_b200_coupled.h"
+#include "perthread_kernel.cuh"     // AtLeastOne, Num<P>, ck<P>(), sfu_*, Cash-Karp table
+
+namespace mpgos_b200 {
+
+template <class P, int UD, int NE>
+struct PerBlockArgs
+{
+	P* TimeDomain;  P* ActualState;  P* ActualTime;  P* UnitParameters;  P* SystemParameters;  P* GlobalParameters;  int* IntegerGlobalParameters;
+	P* UnitAccessories;  int* IntegerUnitAccessories;  P* SystemAccessories;  int* IntegerSystemAccessories;
+	P* CouplingMatrix;  P* CouplingStrength;  int* CouplingIndex;
+	int* DenseOutputIndex;  P* DenseOutputTimeInstances;  P* DenseOutputStates;
+	unsigned long long* StepsAttempted;  unsigned long long* StepsAccepted;  unsigned int* WorkQueue;
+	int NS, Active, SystemOffset, DenseCapacity, DenseOutputSaveFrequency, DeviceMessages;
+	P   InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep, MinimumTimeStepGuard;
+	P   RelativeTolerance[UD];  P AbsoluteTolerance[UD];
+	P   EventTolerance[AtLeastOne<NE>::value];  int EventDirection[AtLeastOne<NE>::value];
+};
+
+__host__ __device__ constexpr int packed_matrix_elements(int UPS, int NC, int CBW, int CCI)
+{
+	return (CCI == 0 && CBW == 0) ? NC * UPS * UPS : (CCI == 0) ? NC * UPS * (2 * CBW + 1) : (CBW > 0) ? NC * (2 * CBW + 1) : NC * UPS;
+}
+
+// y = a^(-1/n), n = 5 (accept) or 4, for a = max_i err_i/tol_i of a whole system: the same division-free Newton map
+// as ratio_root_fast with tol = 1, err = a.
+__device__ __forceinline__ double inverse_root_fast(double a, bool accept)
+{
+	const float inv = accept ? 0.2f : 0.25f;
+	double y = (double)sfu_ex2(-sfu_lg2(__double2float_rn(a)) * inv);
+	const double rn = accept ? 0.2 : 0.25;
+	#pragma unroll
+	for (int it = 0; it < 2; it++)
+	{
+		const double y2 = y * y, y4 = y2 * y2;
+		const double yn = accept ? y4 * y : y4;
+		y = fma(y * fma(-a, yn, 1.0), rn, y);
+	}
+	return y;
+}
+
+template <class P, int UPS, int UPSP, int NC, int NSP, int NSA, int NiSA>
+struct SlotShared
+{
+	static constexpr int WPS = UPSP / 32;
+	alignas(16) P cpt[2][AtLeastOne<NC>::value][UPSP];   // coupling terms, double buffered over stages
+	P   t, dt, td[2];
+	P   spar[AtLeastOne<NSP>::value], sacc[AtLeastOne<NSA>::value], strength[AtLeastOne<NC>::value];
+	P   dense_next_time;
+	P   red_ratio[WPS];      // per-warp max of err/tol
+	P   red_evdt[WPS];       // per-warp min of the secant event step
+	int red_flags[WPS];      // bit 0: all accepted, bit 1: all finite
+	int red_corrected[WPS];
+	int isacc[AtLeastOne<NiSA>::value];
+	int dense_index, dense_skipped, udt, next_system;
+};
+
+template <int UPSP>
+__device__ __forceinline__ void slot_barrier(int slot)
+{
+	if (UPSP == 32) __syncwarp();
+	else asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "r"(UPSP) : "memory");
+}
+
+// Steppers.cuh:2551-2713 on the packed matrix; `cpt` is one coupling term of all units of the system.
+template <class P, int UPS, int CBW, int CCI>
+__device__ __forceinline__ P coupling_value(const P* __restrict__ M, const P* cpt, int unit)
+{
+	P v = 0;
+	if (CCI == 0 && CBW == 0)
+	{
+		#pragma unroll 8
+		for (int col = 0; col < UPS; col++) v += M[unit + col * UPS] * cpt[col];
+	}
+	else
+	{
+		constexpr int ND = (CBW > 0) ? 2 * CBW + 1 : UPS;
+		#pragma unroll 8
+		for (int d = 0; d < ND; d++)
+		{
+			int s = unit + d - CBW;
+			if (s >= UPS) s -= UPS;
+			if (s < 0) s += UPS;
+			v += ((CCI == 0) ? M[unit + d * UPS] : M[d]) * cpt[s];
+		}
+	}
+	return v;
+}
+
+template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
+          int NE, bool DENSE, int ALG, int SPBK>
+__global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), 1)
+perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
+{
+	constexpr int UPSP = ((UPS + 31) / 32) * 32;
+	constexpr int WPS = UPSP / 32;
+	constexpr int MSIZE = packed_matrix_elements(UPS, NC, CBW, CCI);
+	constexpr int MSTRIDE = MSIZE / (NC > 0 ? NC : 1);
+	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA>;
+
+	extern __shared__ __align__(16) unsigned char dyn_smem[];
+	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE]
+	P*   s_gpar   = s_matrix + MSIZE;                                   // [NGP]
+	int* s_igpar  = reinterpret_cast<int*>(s_gpar + NGP);               // [NiGP]
+	__shared__ Slot s_slots[SPBK];
+	__shared__ int  s_cidx[AtLeastOne<NC>::value];
+
+	for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
+	for (int i = threadIdx.x; i < NGP; i += blockDim.x)   s_gpar[i] = a.GlobalParameters[i];
+	for (int i = threadIdx.x; i < NiGP; i += blockDim.x)  s_igpar[i] = a.IntegerGlobalParameters[i];
+	for (int i = threadIdx.x; i < NC; i += blockDim.x)    s_cidx[i] = a.CouplingIndex[i];
+	__syncthreads();
+
+	const int  slot = threadIdx.x / UPSP;
+	const int  unit = threadIdx.x % UPSP;
+	const bool live = unit < UPS;            // padding lanes only take part in barriers
+	const int  wis  = unit / 32;             // warp within the slot
+	const int  lane = unit & 31;
+	Slot& S = s_slots[slot];
+	const size_t NU = (size_t)a.NS * UPS;    // unit-scope stride
+
+	int  sys   = blockIdx.x * SPBK + slot;
+	bool first = true;
+
+	for (;;)
+	{
+		// ---- take a system ------------------------------------------------------------------------------
+		if (!first)
+		{
+			if (unit == 0) S.next_system = (int)(gridDim.x * SPBK + atomicAdd(a.WorkQueue, 1u));
+			slot_barrier<UPSP>(slot);
+			sys = S.next_system;
+		}
+		first = false;
+		if (sys >= a.Active) break;
+		const int    gsys = sys + a.SystemOffset;
+		const size_t ug   = (size_t)sys * UPS + (live ? unit : 0);
+
+		// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
+		P   x[UD], upar[AtLeastOne<NUP>::value], uacc[AtLeastOne<NUA>::value], ev[AtLeastOne<NE>::value];
+		int iuacc[AtLeastOne<NiUA>::value];
+		if (unit == 0)
+		{
+			S.td[0] = a.TimeDomain[sys];  S.td[1] = a.TimeDomain[sys + a.NS];
+			S.t = a.ActualTime[sys];  S.dt = a.InitialTimeStep;
+			S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.dense_skipped = 0;  S.udt = 0;  S.dense_next_time = P(0);
+		}
+		if (unit < NSP)  S.spar[unit]     = a.SystemParameters[sys + unit * a.NS];
+		if (unit < NSA)  S.sacc[unit]     = a.SystemAccessories[sys + unit * a.NS];
+		if (unit < NiSA) S.isacc[unit]    = a.IntegerSystemAccessories[sys + unit * a.NS];
+		if (unit < NC)   S.strength[unit] = a.CouplingStrength[sys + unit * a.NS];
+		#pragma unroll
+		for (int i = 0; i < UD; i++)   x[i]     = a.ActualState[ug + i * NU];
+		#pragma unroll
+		for (int i = 0; i < NUP; i++)  upar[i]  = a.UnitParameters[ug + i * NU];
+		#pragma unroll
+		for (int i = 0; i < NUA; i++)  uacc[i]  = a.UnitAccessories[ug + i * NU];
+		#pragma unroll
+		for (int i = 0; i < NiUA; i++) iuacc[i] = a.IntegerUnitAccessories[ug + i * NU];
+		slot_barrier<UPSP>(slot);
+
+		if (live) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+		slot_barrier<UPSP>(slot);
+		if (NE > 0)
+		{
+			if (live) Sys::EventFunction(gsys, unit, ev, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+			slot_barrier<UPSP>(slot);
+		}
+		if (DENSE)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
+		{
+			const int di = S.dense_index;
+			if (di < a.DenseCapacity)
+			{
+				if (live)
+				{
+					#pragma unroll
+					for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
+				}
+				if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
+			}
+			slot_barrier<UPSP>(slot);
+			if (unit == 0) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
+			slot_barrier<UPSP>(slot);
+		}
+
+		P dt_new = a.InitialTimeStep;
+		unsigned attempted = 0, accepted = 0;
+		bool terminated = false;
+		int  buf = 0;
+
+		// right-hand side of this unit including the coupling term; one slot barrier
+		auto rhs = [&](P* F, P* X, P T) {
+			P cpt[AtLeastOne<NC>::value], cpf[AtLeastOne<NC>::value];
+			if (live)
+			{
+				Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
+				#pragma unroll
+				for (int k = 0; k < NC; k++) S.cpt[buf][k][unit] = cpt[k];
+			}
+			slot_barrier<UPSP>(slot);
+			if (live)
+			{
+				#pragma unroll
+				for (int k = 0; k < NC; k++)
+				{
+					const P v = coupling_value<P, UPS, CBW, CCI>(s_matrix + k * MSTRIDE, S.cpt[buf][k], unit);
+					const P add = S.strength[k] * cpf[k] * v;
+					const int ci = s_cidx[k];
+					#pragma unroll
+					for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
+				}
+			}
+			buf ^= 1;
+		};
+
+		while (!terminated)
+		{
+			// ======================= one attempted step of the whole system =================================
+			const P t = S.t;
+			P dt = dt_new;
+			bool end_reached = false;
+			{
+				const P remaining = S.td[1] - t;
+				if (dt > remaining) { dt = remaining; end_reached = true; }
+			}
+			if (unit == 0) S.dt = dt;
+			attempted++;
+			bool update = true, finite = true;
+
+			P xn[UD];
+			if (ALG == kAlgRK4)
+			{
+				// Steppers.cuh:2015-2227 (expression shapes of the coupled stepper)
+				P X[UD], k[UD];
+				rhs(xn, x, t);
+				P T = t + P(0.5) * dt;
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + xn[i] * P(0.5) * dt;
+				rhs(k, X, T);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) { xn[i] += 2 * k[i]; X[i] = x[i] + k[i] * P(0.5) * dt; }
+				rhs(k, X, T);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) { xn[i] += P(2.0) * k[i]; X[i] = x[i] + k[i] * dt; }
+				T = t + dt;
+				rhs(k, X, T);
+				#pragma unroll
+				for (int i = 0; i < UD; i++)
+				{
+					xn[i] = x[i] + dt * (xn[i] + k[i]) * P(1.0 / 6.0);
+					finite = finite && Num<P>::finite(xn[i]);
+				}
+				// per-system "all finite" (ErrorControllers.cuh:421-441): not finite => message, terminate, step not committed
+				int f = finite || !live;
+				f = __all_sync(0xffffffffu, f);
+				if (WPS > 1)
+				{
+					if (lane == 0) S.red_flags[wis] = f;
+					slot_barrier<UPSP>(slot);
+					#pragma unroll
+					for (int w = 0; w < WPS; w++) f = f && S.red_flags[w];
+				}
+				if (!f)
+				{
+					if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number. Try to use smaller step size. (global system id: %d)\n", gsys);
+					terminated = true;  update = false;
+				}
+				dt_new = a.InitialTimeStep;
+			}
+			else
+			{
+				// Steppers.cuh:2228-2544
+				P X[UD], k1[UD], k2[UD], k3[UD], k4[UD], k5[UD], k6[UD], err[UD];
+				rhs(k1, x, t);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A21)) * dt;
+				rhs(k2, X, t + ck<P>(CK_C2) * dt);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A31) + k2[i] * ck<P>(CK_A32)) * dt;
+				rhs(k3, X, t + ck<P>(CK_C3) * dt);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A41) + k2[i] * ck<P>(CK_A42) + k3[i] * ck<P>(CK_A43)) * dt;
+				rhs(k4, X, t + ck<P>(CK_C4) * dt);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A51) + k2[i] * ck<P>(CK_A52) + k3[i] * ck<P>(CK_A53) + k4[i] * ck<P>(CK_A54)) * dt;
+				rhs(k5, X, t + dt);
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A61) + k2[i] * ck<P>(CK_A62) + k3[i] * ck<P>(CK_A63) + k4[i] * ck<P>(CK_A64) + k5[i] * ck<P>(CK_A65)) * dt;
+				rhs(k6, X, t + ck<P>(CK_C6) * dt);
+
+				// per-unit error ratio q = max_i err_i/tol_i, accept flag, finite flag (ErrorControllers.cuh:483-500)
+				P q = P(0);
+				#pragma unroll
+				for (int i = 0; i < UD; i++)
+				{
+					xn[i] = x[i] + (k1[i] * ck<P>(CK_B1) + k3[i] * ck<P>(CK_B3) + k4[i] * ck<P>(CK_B4) + k6[i] * ck<P>(CK_B6)) * dt;
+					const P e = k1[i] * ck<P>(CK_E1) + k3[i] * ck<P>(CK_E3) + k4[i] * ck<P>(CK_E4) + k5[i] * ck<P>(CK_E5) + k6[i] * ck<P>(CK_E6);
+					err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
+					finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
+					const P tol = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(x[i])), a.AbsoluteTolerance[i]);
+					update = update && (err[i] < tol);
+					q = fmax(q, err[i] / tol);
+				}
+				if (!live) { q = P(0); update = true; finite = true; }
+				// slot-wide reduction: shuffles inside the warp, one word per warp across warps
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) q = fmax(q, __shfl_xor_sync(0xffffffffu, q, o));
+				int flags = (__all_sync(0xffffffffu, update) ? 1 : 0) | (__all_sync(0xffffffffu, finite) ? 2 : 0);
+				if (WPS > 1)
+				{
+					if (lane == 0) { S.red_ratio[wis] = q;  S.red_flags[wis] = flags; }
+					slot_barrier<UPSP>(slot);
+					#pragma unroll
+					for (int w = 0; w < WPS; w++) { q = fmax(q, S.red_ratio[w]);  flags &= S.red_flags[w]; }
+				}
+				update = (flags & 1) != 0;
+				finite = (flags & 2) != 0;
+
+				// every thread evaluates the controller (ErrorControllers.cuh:504-539) from the reduced values
+				const bool at_minimum = dt < a.MinimumTimeStepGuard;
+				P mult;
+				const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 <= q < 2^30 (and q > 1e-30: the reference's initial 1e30)
+				if (finite && qt < Num<P>::kSpan)
+					mult = P(0.8) * inverse_root_fast(q, update);
+				else
+				{
+					const P rel = fmin(P(1e30), P(1.0) / q);
+					mult = P(0.8) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+					if (!Num<P>::finite(mult)) finite = false;
+				}
+				if (!finite)
+				{
+					mult = a.TimeStepShrinkLimit;
+					update = false;
+					if (at_minimum)
+					{
+						if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number, minimum step size reached. Try to use less stringent tolerances. (global system id: %d)\n", gsys);
+						terminated = true;
+					}
+				}
+				else if (at_minimum)
+				{
+					if (a.DeviceMessages && unit == 0) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed! (global system id: %d)\n", gsys);
+					update = true;
+				}
+				mult = fmin(mult, a.TimeStepGrowLimit);
+				mult = fmax(mult, a.TimeStepShrinkLimit);
+				dt_new = dt * mult;
+				dt_new = fmin(dt_new, a.MaximumTimeStep);
+				dt_new = fmax(dt_new, a.MinimumTimeStep);
+			}
+
+			// ---- events: the earliest secant estimate over all units and events (EventHandling.cuh:216-268) ----
+			P evn[AtLeastOne<NE>::value];
+			if (NE > 0)
+			{
+				if (live && !terminated)
+					Sys::EventFunction(gsys, unit, evn, t + dt, dt_new, S.td, xn, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+				P dt_event = dt;
+				int corrected = 0;
+				if (live && update && !terminated)
+				{
+					#pragma unroll
+					for (int i = 0; i < NE; i++)
+					{
+						const P et = a.EventTolerance[i];
+						if (((ev[i] > et) && (evn[i] < -et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (evn[i] > et) && (a.EventDirection[i] >= 0)))
+						{
+							dt_event = fmin(dt_event, -ev[i] / (evn[i] - ev[i]) * dt);
+							corrected = 1;
+						}
+					}
+				}
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) dt_event = fmin(dt_event, __shfl_xor_sync(0xffffffffu, dt_event, o));
+				corrected = __any_sync(0xffffffffu, corrected);
+				if (WPS > 1)
+				{
+					if (lane == 0) { S.red_evdt[wis] = dt_event;  S.red_corrected[wis] = corrected; }
+					slot_barrier<UPSP>(slot);
+					#pragma unroll
+					for (int w = 0; w < WPS; w++) { dt_event = fmin(dt_event, S.red_evdt[w]);  corrected |= S.red_corrected[w]; }
+				}
+				if (corrected)
+				{
+					if (dt_event < a.MinimumTimeStep)
+					{
+						if (a.DeviceMessages && unit == 0) printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (global system id: %d)\n", gsys);
+					}
+					else { dt_new = dt_event;  update = false; }
+				}
+			}
+
+			// ---- accepted step (Solver.cuh:2670-2806) ----------------------------------------------------------
+			if (update)
+			{
+				accepted++;
+				if (unit == 0) S.t = t + dt;
+				#pragma unroll
+				for (int i = 0; i < UD; i++) x[i] = xn[i];
+				slot_barrier<UPSP>(slot);
+				if (live) Sys::ActionAfterSuccessfulTimeStep(gsys, unit, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+				slot_barrier<UPSP>(slot);
+				if (NE > 0)
+				{
+					if (live)
+					{
+						#pragma unroll
+						for (int i = 0; i < NE; i++)
+						{
+							const P et = a.EventTolerance[i];
+							if (((ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
+								Sys::ActionAfterEventDetection(gsys, unit, i, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+						}
+					}
+					slot_barrier<UPSP>(slot);
+					if (live) Sys::EventFunction(gsys, unit, ev, S.t, dt_new, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+					slot_barrier<UPSP>(slot);
+				}
+			}
+			const bool user_stop = update && (S.udt == 1);
+
+			if (DENSE)   // DenseOutput.cuh:362-395, then :314-360
+			{
+				const int di = S.dense_index;
+				bool store = false;
+				if (update)
+				{
+					const bool room = di < a.DenseCapacity;
+					store = room && (S.dense_next_time < S.t) && (S.dense_skipped >= (a.DenseOutputSaveFrequency - 1));
+					if (room && (end_reached || user_stop)) store = true;
+				}
+				if (store)
+				{
+					if (live)
+					{
+						#pragma unroll
+						for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
+					}
+					if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
+				}
+				slot_barrier<UPSP>(slot);
+				if (unit == 0)
+				{
+					if (store) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
+					else if (update) S.dense_skipped++;
+				}
+				slot_barrier<UPSP>(slot);
+			}
+
+			if (update && (end_reached || user_stop)) terminated = true;
+		}
+
+		// ---- end of the phase for this system (Solver.cuh:2812-2887) -------------------------------------------
+		slot_barrier<UPSP>(slot);
+		if (live) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+		slot_barrier<UPSP>(slot);
+		if (live)
+		{
+			#pragma unroll
+			for (int i = 0; i < UD; i++)   a.ActualState[ug + i * NU] = x[i];
+			#pragma unroll
+			for (int i = 0; i < NUA; i++)  a.UnitAccessories[ug + i * NU] = uacc[i];
+			#pragma unroll
+			for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[ug + i * NU] = iuacc[i];
+		}
+		if (unit < NSA)  a.SystemAccessories[sys + unit * a.NS] = S.sacc[unit];
+		if (unit < NiSA) a.IntegerSystemAccessories[sys + unit * a.NS] = S.isacc[unit];
+		if (unit == 0)
+		{
+			a.ActualTime[sys] = S.t;
+			a.TimeDomain[sys] = S.td[0];  a.TimeDomain[sys + a.NS] = S.td[1];
+			if (DENSE) a.DenseOutputIndex[sys] = S.dense_index;
+			a.StepsAttempted[sys] += attempted;
+			a.StepsAccepted[sys]  += accepted;
+		}
+		slot_barrier<UPSP>(slot);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
+          int NE, bool DENSE, int ALG>
+struct PerBlockLauncher
+{
+	static constexpr int UPSP = ((UPS + 31) / 32) * 32;
+	// slots per block: fill 512 threads (one block per SM at <= 128 registers), at most 15 named barriers
+	static constexpr int SPBK = (512 / UPSP) < 1 ? 1 : ((512 / UPSP) > 15 ? 15 : (512 / UPSP));
+	static_assert(UPSP <= 1024, "UnitsPerSystem above 1024 would need several threads' worth of units per thread (not built)");
+	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
+
+	static int launch(const mpgos_coupled_launch* L, void* stream_v)
+	{
+		cudaStream_t stream = (cudaStream_t)stream_v;
+		const mpgos_coupled_desc& d = L->desc;
+		if (d.UPS != UPS || d.UD != UD || d.NC != NC || d.CBW != CBW || d.CCI != CCI || d.NUP != NUP || d.NSP != NSP || d.NGP != NGP || d.NiGP != NiGP ||
+		    d.NUA != NUA || d.NiUA != NiUA || d.NSA != NSA || d.NiSA != NiSA || d.NE != NE || d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
+			return (int)cudaErrorInvalidValue;
+		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SPBK>;
+		PerBlockArgs<P, UD, NE> a;
+		a.TimeDomain = (P*)L->d_TimeDomain;  a.ActualState = (P*)L->d_ActualState;  a.ActualTime = (P*)L->d_ActualTime;  a.UnitParameters = (P*)L->d_UnitParameters;
+		a.SystemParameters = (P*)L->d_SystemParameters;  a.GlobalParameters = (P*)L->d_GlobalParameters;  a.IntegerGlobalParameters = L->d_IntegerGlobalParameters;
+		a.UnitAccessories = (P*)L->d_UnitAccessories;  a.IntegerUnitAccessories = L->d_IntegerUnitAccessories;  a.SystemAccessories = (P*)L->d_SystemAccessories;
+		a.IntegerSystemAccessories = L->d_IntegerSystemAccessories;  a.CouplingMatrix = (P*)L->d_CouplingMatrix;  a.CouplingStrength = (P*)L->d_CouplingStrength;
+		a.CouplingIndex = L->d_CouplingIndex;  a.DenseOutputIndex = L->d_DenseOutputIndex;  a.DenseOutputTimeInstances = (P*)L->d_DenseOutputTimeInstances;
+		a.DenseOutputStates = (P*)L->d_DenseOutputStates;  a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
+		a.NS = d.NS;  a.Active = L->ActiveSystems < d.NS ? L->ActiveSystems : d.NS;  a.SystemOffset = d.SystemOffset;  a.DenseCapacity = d.NDO;
+		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;  a.DeviceMessages = L->DeviceMessages;
+		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;  a.MinimumTimeStep = (P)L->MinimumTimeStep;
+		a.TimeStepGrowLimit = (P)L->TimeStepGrowLimit;  a.TimeStepShrinkLimit = (P)L->TimeStepShrinkLimit;  a.DenseOutputMinimumTimeStep = (P)L->DenseOutputMinimumTimeStep;
+		a.MinimumTimeStepGuard = a.MinimumTimeStep * P(1.01);
+		for (int i = 0; i < UD; i++) { a.RelativeTolerance[i] = (P)L->RelativeTolerance[i];  a.AbsoluteTolerance[i] = (P)L->AbsoluteTolerance[i]; }
+		for (int i = 0; i < AtLeastOne<NE>::value; i++) { a.EventTolerance[i] = (i < NE) ? (P)L->EventTolerance[i] : P(0);  a.EventDirection[i] = (i < NE) ? L->EventDirection[i] : 0; }
+		if (a.Active <= 0) return (int)cudaSuccess;
+
+		const size_t smem = sizeof(P) * (packed_matrix_elements(UPS, NC, CBW, CCI) + NGP) + sizeof(int) * NiGP + 16;
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		int per_sm = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPBK * UPSP, smem);
+		if (e != cudaSuccess) return (int)e;
+		if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+		int grid = (a.Active + SPBK - 1) / SPBK;
+		const int resident = per_sm * (L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148);
+		if (grid > resident) grid = resident;
+		e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
+		if (e != cudaSuccess) return (int)e;
+		kernel<<<grid, SPBK * UPSP, smem, stream>>>(a);
+		return (int)cudaGetLastError();
+	}
+};
+
+} // namespace mpgos_b200
+#endif

@@ -11,6 +11,9 @@ from .solver import (ProblemSolver, MpgosError, load_library, library_path, buil
                      Variables, Options, Algorithms, run_workload, ABI_SYMBOLS, probe_fma_peak,
                      apply_workload, read_back)
 from . import workloads
+from . import workloads_coupled
+from .solver_coupled import (CoupledProblemSolver, CoupledVariables, CoupledOptions, COUPLED_ABI_SYMBOLS, run_coupled_workload,
+                             apply_coupled_workload, read_back_coupled)
 
 __all__ = ["ProblemSolver", "MpgosError", "load_library", "library_path", "build_library", "Variables",
            "Options", "Algorithms", "run_workload", "workloads", "ABI_SYMBOLS", "probe_fma_peak", "apply_workload", "read_back"]

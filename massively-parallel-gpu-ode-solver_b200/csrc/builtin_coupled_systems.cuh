@@ -1,0 +1,90 @@
+// builtin_coupled_systems.cuh -- the coupled tutorial systems compiled into the library.  Static device functions with
+// the argument lists of the reference's CoupledSystems_PerBlock_* callbacks; literals in the run's precision.
+//   BubbleEnsemble : Tutorials_CoupledSystems_PerBlock/T2_BubbleEnsemble/BubbleEnsemble_SystemDefinition.cuh:7-95
+//   DuffingRing    : Tutorials_CoupledSystems_PerBlock/T1_RingOfDuffingOscillators/RingOfDuffingOscillators_SystemDefinition.cuh:7-105
+#ifndef MPGOS_B200_BUILTIN_COUPLED_SYSTEMS_CUH
+#define MPGOS_B200_BUILTIN_COUPLED_SYSTEMS_CUH
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mpgos_b200 {
+namespace builtin {
+
+#define MPGOS_C_ODE_ARGS(P)   int sid, int uid, P* F, P* X, P T, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC, P* CPT, P* CPF
+#define MPGOS_C_EV_ARGS(P)    int sid, int uid, P* EF, P T, P dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC
+#define MPGOS_C_EVACT_ARGS(P) int sid, int uid, int IDX, int& UDT, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC
+#define MPGOS_C_STEP_ARGS(P)  int sid, int uid, int& UDT, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC
+#define MPGOS_C_INIT_ARGS(P)  int sid, int uid, int& DOIDX, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC
+#define MPGOS_C_DEV           static __device__ __forceinline__ void
+
+template <class P>
+struct BubbleEnsemble
+{
+	enum { UD = 2, NC = 1, NUP = 21, NSP = 0, NGP = 0, NiGP = 0, NUA = 0, NiUA = 0, NSA = 0, NiSA = 0, NE = 0 };
+	MPGOS_C_DEV OdeFunction(MPGOS_C_ODE_ARGS(P))
+	{
+		const P PI = P(3.14159265358979323846);
+		const P rx1 = P(1.0) / X[0];
+		const P p = pow(rx1, uPAR[10]);
+		P s1, c1;
+		sincospi(P(2.0) * T, &s1, &c1);
+		const P s2 = sin(P(2.0) * uPAR[11] * PI * T + uPAR[12]);
+		const P c2 = cos(P(2.0) * uPAR[11] * PI * T + uPAR[12]);
+		const P N = (uPAR[0] + uPAR[1] * X[1]) * p - uPAR[2] * (P(1.0) + uPAR[9] * X[1]) - uPAR[3] * rx1 - uPAR[4] * X[1] * rx1
+		          - P(1.5) * (P(1.0) - uPAR[9] * X[1] / P(3.0)) * X[1] * X[1] - (uPAR[5] * s1 + uPAR[6] * s2) * (P(1.0) + uPAR[9] * X[1])
+		          - X[0] * (uPAR[7] * c1 + uPAR[8] * c2);
+		const P D = X[0] - uPAR[9] * X[0] * X[1] + uPAR[4] * uPAR[9];
+		const P rD = P(1.0) / D;
+		F[0] = X[1];
+		F[1] = N * rD;
+		CPT[0] = -(2 * X[0] * X[1] * X[1] + X[0] * X[0] * N * rD);
+		CPF[0] = rD;
+	}
+	MPGOS_C_DEV EventFunction(MPGOS_C_EV_ARGS(P)) {}
+	MPGOS_C_DEV ActionAfterEventDetection(MPGOS_C_EVACT_ARGS(P)) {}
+	MPGOS_C_DEV ActionAfterSuccessfulTimeStep(MPGOS_C_STEP_ARGS(P)) {}
+	MPGOS_C_DEV Initialization(MPGOS_C_INIT_ARGS(P)) { if (uid == 0) T = TD[0]; }
+	MPGOS_C_DEV Finalization(MPGOS_C_INIT_ARGS(P)) {}
+};
+
+template <class P>
+struct DuffingRing
+{
+	enum { UD = 2, NC = 2, NUP = 3, NSP = 0, NGP = 1, NiGP = 0, NUA = 3, NiUA = 1, NSA = 2, NiSA = 1, NE = 1 };
+	MPGOS_C_DEV OdeFunction(MPGOS_C_ODE_ARGS(P))
+	{
+		F[0] = X[1] - gPAR[0] * X[0];
+		F[1] = -uPAR[1] * X[1] + X[0] - X[0] * X[0] * X[0] + uPAR[2] * cos(uPAR[0] * T) - gPAR[0] * X[1];
+		CPT[0] = X[0];
+		CPF[0] = P(1.0);
+		CPT[1] = X[1];
+		CPF[1] = P(1.0);
+	}
+	MPGOS_C_DEV EventFunction(MPGOS_C_EV_ARGS(P)) { EF[0] = X[1]; }
+	MPGOS_C_DEV ActionAfterEventDetection(MPGOS_C_EVACT_ARGS(P))
+	{
+		iuACC[0]++;
+		if (iuACC[0] == 2) { UDT = 1; uACC[2] = X[0]; }
+	}
+	MPGOS_C_DEV ActionAfterSuccessfulTimeStep(MPGOS_C_STEP_ARGS(P))
+	{
+		if (uid == 0)
+		{
+			if (sACC[0] > dT) sACC[0] = dT;
+			if (sACC[1] < dT) sACC[1] = dT;
+			isACC[0]++;
+		}
+	}
+	MPGOS_C_DEV Initialization(MPGOS_C_INIT_ARGS(P))
+	{
+		if (uid == 0) { sACC[0] = dT; sACC[1] = dT; isACC[0] = 0; T = TD[0]; DOIDX = 0; }
+		uACC[2] = X[0];
+		iuACC[0] = 0;
+	}
+	MPGOS_C_DEV Finalization(MPGOS_C_INIT_ARGS(P)) {}
+};
+
+} // namespace builtin
+} // namespace mpgos_b200
+#endif

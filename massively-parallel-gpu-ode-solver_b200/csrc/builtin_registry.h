@@ -4,6 +4,7 @@
 #define MPGOS_B200_BUILTIN_REGISTRY_H
 
 #include "../../include/mpgos_b200.h"
+#include "../../include/mpgos_b200_coupled.h"
 
 namespace mpgos_b200 {
 
@@ -20,6 +21,16 @@ const BuiltinEntry* builtin_entries_lorenz(int* n);
 const BuiltinEntry* builtin_entries_duffing(int* n);        // "poincare" and "duffing"
 const BuiltinEntry* builtin_entries_impact(int* n);
 const BuiltinEntry* builtin_entries_kellermiksis(int* n);   // "kellermiksis" and "kellermiksis_dense"
+
+struct CoupledBuiltinEntry
+{
+	const char* name;
+	int UPS, CBW, CCI, UD, NC, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE;
+	int Algorithm;
+	bool Dense;
+	mpgos_coupled_launcher launcher;
+};
+const CoupledBuiltinEntry* builtin_entries_coupled(int* n);
 
 } // namespace mpgos_b200
 

@@ -32,6 +32,20 @@ int fail(int code, const char* fmt, ...)
 	return code;
 }
 
+} // namespace
+namespace mpgos_b200 {
+// shared with runtime_coupled.cu
+int set_error(int code, const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+	return code;
+}
+}
+namespace {
+
 #define CUDA_TRY(call)                                                                                   \
 	do {                                                                                                 \
 		cudaError_t e_ = (call);                                                                         \

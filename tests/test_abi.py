@@ -11,10 +11,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    text = open(os.path.join(ROOT, "include", "mpgos_b200.h")).read()
+def header_functions(name="mpgos_b200.h"):
+    text = open(os.path.join(ROOT, "include", name)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mpgos_[a-z0-9_]+)\s*\(", text)) - {"mpgos_perthread_launcher"})
+    return sorted(set(re.findall(r"\b(mpgos_[a-z0-9_]+)\s*\(", text)) - {"mpgos_perthread_launcher", "mpgos_coupled_launcher"})
 
 
 def test_library_exports_every_declared_symbol(pkg):
@@ -25,6 +25,39 @@ def test_library_exports_every_declared_symbol(pkg):
         assert hasattr(lib, name), f"{name} declared in include/mpgos_b200.h but not exported"
     assert sorted(pkg.ABI_SYMBOLS) == declared
     assert lib.mpgos_abi_version() == 1
+
+
+def test_library_exports_every_declared_coupled_symbol(pkg):
+    lib = pkg.load_library()
+    declared = header_functions("mpgos_b200_coupled.h")
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mpgos_b200_coupled.h but not exported"
+    assert sorted(pkg.COUPLED_ABI_SYMBOLS) == declared
+    strict = pkg.load_library(strict=True)
+    for name in declared + header_functions():
+        assert hasattr(strict, name)
+
+
+def test_coupled_builtins_and_descriptor_checks(pkg):
+    from importlib import import_module
+    sc = import_module(pkg.__name__ + ".solver_coupled")
+    lib = pkg.load_library()
+    sc._bind(lib)
+    d = sc._CDesc()
+    assert lib.mpgos_coupled_builtin_desc(b"bubble_ensemble", 64, 0, 0, C.byref(d)) == 0
+    assert (d.UD, d.NC, d.NUP, d.NE) == (2, 1, 21, 0)
+    assert lib.mpgos_coupled_builtin_desc(b"duffing_ring", 14, 1, 1, C.byref(d)) == 0
+    assert (d.UD, d.NC, d.NUP, d.NGP, d.NUA, d.NiUA, d.NSA, d.NiSA, d.NE) == (2, 2, 3, 1, 3, 1, 2, 1, 1)
+    assert lib.mpgos_coupled_builtin_desc(b"bubble_ensemble", 63, 0, 0, C.byref(d)) == -5
+    assert lib.mpgos_coupled_builtin_launcher(b"bubble_ensemble", 64, 0, 0, 1, 0)
+    assert lib.mpgos_coupled_builtin_launcher(b"duffing_ring", 14, 1, 1, 1, 1)
+    assert not lib.mpgos_coupled_builtin_launcher(b"duffing_ring", 14, 1, 1, 1, 0)
+    h = C.c_void_p()
+    bad = sc._CDesc(NS=4, UPS=14, UD=2, NC=2, CBW=9, CCI=0, PrecisionBytes=8, Algorithm=1)
+    assert lib.mpgos_coupled_create(C.byref(bad), C.byref(h)) == -1            # band wider than the ring
+    bad = sc._CDesc(NS=4, UPS=14, UD=2, NC=2, PrecisionBytes=4, Algorithm=1)
+    assert lib.mpgos_coupled_create(C.byref(bad), C.byref(h)) == -1            # FP32 coupled not built
 
 
 def test_builtin_systems_and_shapes(pkg):

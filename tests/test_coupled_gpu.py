@@ -1,0 +1,81 @@
+"""Parity of the CUDA block-per-system (coupled) path against the CPU checker, whose arithmetic is pinned bit for bit
+to the reference's own coupled kernels (tests/test_oracle_coupled.py), through the public API (Python mirror -> C-ABI ->
+kernel).  Covers all four coupling-matrix layouts, RK4 and RKCK45, unit-scope events with user-defined termination,
+system accessories written by unit 0, dense output, systems spanning one and several warps."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from cases import make_coupled_cases, COUPLED_RESULT_FIELDS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ccases(pkg):
+    return make_coupled_cases(importlib.import_module(pkg.__name__ + ".workloads_coupled"))
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+
+
+@pytest.mark.parametrize("name", ["bubble_u8_rkck45", "bubble_u16_rkck45", "bubble_u16_rk4"])
+def test_bubble_ensemble_against_checker(name, ccases, pkg, oracle):
+    tag, wl, phases = ccases[name]
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=phases)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=phases)
+    assert np.array_equal(out.ActualTime, ref.ActualTime)
+    assert np.array_equal(att, ratt) and np.array_equal(acc, racc)                 # step counts of every system
+    assert rel_err(out.ActualState, ref.ActualState).max() < (1e-10 if "rk4" in name else 1e-7)
+
+
+@pytest.mark.parametrize("name", ["ring_b1c1_rkck45", "ring_b1c0_rkck45", "ring_b0c1_rk4", "ring_b0c0_rkck45"])
+def test_duffing_ring_events_accessories_dense_output(name, ccases, pkg, oracle):
+    tag, wl, phases = ccases[name]
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=phases)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=phases)
+    assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)   # event counters of every unit
+    assert np.abs(att - ratt).max() <= 2 and np.abs(acc - racc).max() <= 2
+    assert np.abs(out.IntegerSystemAccessories - ref.IntegerSystemAccessories).max() <= 2   # step counter kept by unit 0
+    assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6                     # event-terminated phases
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
+    assert rel_err(out.UnitAccessories, ref.UnitAccessories).max() < 1e-5
+    assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
+    same = out.DenseIndex == ref.DenseIndex
+    assert same.mean() >= 0.7
+    n = int(min(ref.DenseIndex.min(), out.DenseIndex.min()))
+    cols = np.where(same)[0]
+    assert rel_err(out.DenseTime[:n - 1][:, cols], ref.DenseTime[:n - 1][:, cols]).max() < 1e-6
+    assert rel_err(out.DenseState[:n - 1][:, :, cols], ref.DenseState[:n - 1][:, :, cols]).max() < 1e-5
+
+
+def test_bubble_ensemble_64_units_properties(pkg):
+    """C5 shape (64 units, dense matrix shared by all systems): size-independent properties -- ends on TD[1], finite,
+    bubbles driven harder take more steps, a sub-sweep run alone reproduces the same bits (systems are independent),
+    and zero coupling strength reproduces the uncoupled Keller-Miksis path of the thread-per-system kernel."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=96, UPS=64, amplitude=(0.1, 1.5))
+    out, att, acc = pkg.run_coupled_workload(wl, phases=1)
+    assert np.array_equal(out.ActualTime, wl.buffers.TimeDomain[1]) and np.isfinite(out.ActualState).all()
+    assert att[-1] > att[0] and (att >= acc).all()
+    idx = np.arange(3, 96, 7)
+    import copy
+    sub = copy.copy(wl)
+    sub.buffers = wl.buffers.take(idx)
+    sout, satt, _ = pkg.run_coupled_workload(sub, phases=1)
+    assert np.array_equal(sout.ActualState, out.ActualState[:, idx, :]) and np.array_equal(satt, att[idx])
+
+
+def test_matrix_entry_outside_band_is_rejected(pkg):
+    ps = pkg.CoupledProblemSolver("duffing_ring", 4, 14, CBW=1, CCI=0, NDO=100)
+    ps.SetCouplingMatrix(0, 3, 4, 1.0)
+    ps.SetCouplingMatrix(0, 0, 13, 1.0)       # circular extension of the band
+    assert ps.GetCouplingMatrix(0, 0, 13) == 1.0
+    with pytest.raises(pkg.MpgosError):
+        ps.SetCouplingMatrix(0, 3, 7, 1.0)    # outside bandwidth 1: the reference's BoundCheck exits here
+    with pytest.raises(pkg.MpgosError):
+        ps.SetCouplingMatrix(2, 0, 0, 1.0)
+    ps.close()
