@@ -25,6 +25,13 @@
 #include "../mpgos_b200_coupled.h"
 #include "perthread_kernel.cuh"     // AtLeastOne, Num<P>, ck<P>(), sfu_*, Cash-Karp table
 
+#ifndef MPGOS_B200_COUPLING_ACCUMULATORS
+#define MPGOS_B200_COUPLING_ACCUMULATORS 4
+#endif
+#ifndef MPGOS_B200_COUPLED_THREADS
+#define MPGOS_B200_COUPLED_THREADS 512
+#endif
+
 namespace mpgos_b200 {
 
 template <class P, int UD, int NE>
@@ -93,8 +100,20 @@ __device__ __forceinline__ P coupling_value(const P* __restrict__ M, const P* cp
 	P v = 0;
 	if (CCI == 0 && CBW == 0)
 	{
-		#pragma unroll 8
-		for (int col = 0; col < UPS; col++) v += M[unit + col * UPS] * cpt[col];
+		// MPGOS_B200_COUPLING_ACCUMULATORS independent partial sums over interleaved columns break the UPS-long chain of
+		// dependent FMAs (8 cycles each); 1 reproduces the reference's summation order exactly.
+		constexpr int NA = (UPS % MPGOS_B200_COUPLING_ACCUMULATORS == 0) ? MPGOS_B200_COUPLING_ACCUMULATORS : 1;
+		P acc[NA];
+		#pragma unroll
+		for (int j = 0; j < NA; j++) acc[j] = 0;
+		#pragma unroll 4
+		for (int col = 0; col < UPS; col += NA)
+		{
+			#pragma unroll
+			for (int j = 0; j < NA; j++) acc[j] += M[unit + (col + j) * UPS] * cpt[col + j];
+		}
+		#pragma unroll
+		for (int j = 0; j < NA; j++) v += acc[j];
 	}
 	else
 	{
@@ -509,7 +528,7 @@ struct PerBlockLauncher
 {
 	static constexpr int UPSP = ((UPS + 31) / 32) * 32;
 	// slots per block: fill 512 threads (one block per SM at <= 128 registers), at most 15 named barriers
-	static constexpr int SPBK = (512 / UPSP) < 1 ? 1 : ((512 / UPSP) > 15 ? 15 : (512 / UPSP));
+	static constexpr int SPBK = (MPGOS_B200_COUPLED_THREADS / UPSP) < 1 ? 1 : ((MPGOS_B200_COUPLED_THREADS / UPSP) > 15 ? 15 : (MPGOS_B200_COUPLED_THREADS / UPSP));
 	static_assert(UPSP <= 1024, "UnitsPerSystem above 1024 would need several threads' worth of units per thread (not built)");
 	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
 

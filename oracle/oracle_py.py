@@ -257,3 +257,23 @@ def run_coupled_ref(tag: str, wl, buffers=None, phases=None):
     if rc != 0:
         raise RuntimeError(f"ref_coupled_run failed: {rc}")
     return out
+
+
+def run_coupled_ref_gpu(tag: str, wl, buffers=None, phases=None, shared_matrices: int = 0, repeats: int = 1):
+    """The REFERENCE MPGOS coupled module on the GPU (oracle/_ref/libref_gpu_coupled_<tag>.so); returns (buffers_after, kernel_ms)."""
+    path = coupled_ref_library_path(tag, gpu=True)
+    lib = _REFGPU.get(path)
+    if lib is None:
+        lib = _REFGPU[path] = C.CDLL(path)
+    s = _CShape()
+    lib.ref_coupled_shape(C.byref(s))
+    _ccheck(s, wl)
+    out = (buffers if buffers is not None else wl.buffers).copy()
+    if out.NS > lib.ref_coupled_capacity():
+        raise ValueError("more systems than the reference library was compiled for")
+    cb, co, att, acc, _keep = _cpack(wl, out, wl.phases if phases is None else phases, 1)
+    ms = C.c_float()
+    rc = lib.ref_coupled_gpu_run(C.byref(cb), C.byref(co), shared_matrices, repeats, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"ref_coupled_gpu_run failed: {rc}")
+    return out, ms.value

@@ -69,6 +69,20 @@ def test_bubble_ensemble_64_units_properties(pkg):
     assert np.array_equal(sout.ActualState, out.ActualState[:, idx, :]) and np.array_equal(satt, att[idx])
 
 
+@pytest.mark.parametrize("name,tag,tol", [("bubble_u16_rkck45", "bubble_ensemble_u16", 1e-11), ("ring_b1c1_rkck45", "duffing_ring_b1c1", 1e-9)])
+def test_against_reference_mpgos_coupled_kernels_on_the_same_gpu(name, tag, tol, ccases, pkg, oracle):
+    """GPU vs GPU: the reference's own coupled kernels compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_coupled_*.so)."""
+    _, wl, phases = ccases[name]
+    if not os.path.exists(oracle.coupled_ref_library_path(tag, gpu=True)):
+        pytest.skip("oracle/_ref/libref_gpu_coupled_*.so not built (needs /root/reference at build time)")
+    ref, _ = oracle.run_coupled_ref_gpu(tag, wl, phases=phases)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=phases)
+    assert rel_err(out.ActualState, ref.ActualState).max() < tol
+    assert rel_err(out.ActualTime, ref.ActualTime).max() < tol
+    assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)
+    assert np.array_equal(out.DenseIndex, ref.DenseIndex)
+
+
 def test_matrix_entry_outside_band_is_rejected(pkg):
     ps = pkg.CoupledProblemSolver("duffing_ring", 4, 14, CBW=1, CCI=0, NDO=100)
     ps.SetCouplingMatrix(0, 3, 4, 1.0)
