@@ -66,8 +66,9 @@ typedef enum mpgos_option
 	MPGOS_OPT_EventTolerance, MPGOS_OPT_EventDirection, MPGOS_OPT_DenseOutputMinimumTimeStep,
 	MPGOS_OPT_DenseOutputSaveFrequency, MPGOS_OPT_PreferSharedMemory,
 	MPGOS_OPT_LaneRefill,       /* 0: one thread integrates one instance (reference mapping);
-	                               1 (default): persistent warps, a lane that finishes its
-	                               instance takes the next one from a device-side queue */
+	                               n = 1..32: persistent warps; when a warp ballot counts >= n idle
+	                               lanes they take the next n instances from a device-side queue
+	                               together (1 = every finished lane at once, 32 = whole warps) */
 	MPGOS_OPT_DeviceMessages    /* 1: device-side printf of the reference's warnings; 0 (default) */
 } mpgos_option;
 

@@ -15,7 +15,14 @@
 //  * the coupling matrices live in shared memory once per block, coupling terms are double-buffered (one barrier per
 //    stage instead of two), the column sum runs in ascending order with a single accumulator exactly like
 //    ComputeCouplingValue_* (Steppers.cuh:2551-2713), so results track the reference to rounding;
-//  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid).
+//  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid);
+//  * TENSOR-CORE COUPLING (MMA variant; dense matrices shared by all systems, FP64, UPS = 32 or 64): the column sums of the
+//    8 systems of a block are ONE matrix product  V[UPS x 8] = M[UPS x UPS] . CPT[UPS x 8]  per stage, issued as
+//    mma.sync.m8n8k4.f64 (DMMA) by all warps of the block; the matrix sits in shared memory in fragment order.  The scalar
+//    form needs one 8-byte shared-memory operand per FMA and is bound by shared-memory bandwidth (ncu: 45 % of the LSU
+//    wavefront peak at 44 % FP64-pipe activity, profiles/); one DMMA performs 256 FMAs on two 8-byte operands per lane.
+//    The 8 systems then advance in lockstep through the stages (two block barriers per stage); everything else stays
+//    per slot.
 #ifndef MPGOS_B200_PERBLOCK_KERNEL_CUH
 #define MPGOS_B200_PERBLOCK_KERNEL_CUH
 
@@ -70,11 +77,11 @@ __device__ __forceinline__ double inverse_root_fast(double a, bool accept)
 	return y;
 }
 
-template <class P, int UPS, int UPSP, int NC, int NSP, int NSA, int NiSA>
+template <class P, int UPS, int UPSP, int NC, int NSP, int NSA, int NiSA, bool MMA>
 struct SlotShared
 {
 	static constexpr int WPS = UPSP / 32;
-	alignas(16) P cpt[2][AtLeastOne<NC>::value][UPSP];   // coupling terms, double buffered over stages
+	alignas(16) P cpt[2][AtLeastOne<NC>::value][MMA ? 2 : UPSP];   // coupling terms, double buffered over stages (scalar variant)
 	P   t, dt, td[2];
 	P   spar[AtLeastOne<NSP>::value], sacc[AtLeastOne<NSA>::value], strength[AtLeastOne<NC>::value];
 	P   dense_next_time;
@@ -130,8 +137,52 @@ __device__ __forceinline__ P coupling_value(const P* __restrict__ M, const P* cp
 	return v;
 }
 
+// ---- tensor-core coupling -------------------------------------------------------------------------------------------
+// D[8x8] += A[8x4] . B[4x8] in FP64.  Fragments (PTX ISA, mma.m8n8k4 .f64): lane l holds A[l/4][l%4], B[l%4][l/4] and
+// D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b)
+{
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Geometry of the block-wide product for UPS units and 8 systems (= SLOTS warps-groups of UPS threads).
+template <int UPS>
+struct MmaGeometry
+{
+	static constexpr int SLOTS = 8;                    // the N extent of the instruction
+	static constexpr int RT = UPS / 8;                 // row tiles of the matrix
+	static constexpr int KT = UPS / 4;                 // column (k) tiles
+	static constexpr int WARPS = SLOTS * UPS / 32;
+	static constexpr int KG = WARPS / RT;              // a warp owns one row tile and 1/KG of the k tiles
+	static constexpr int KPG = KT / KG;
+	static constexpr int CS = UPS + 4;                 // stride of a system's coupling terms  (conflict-free B fragment loads)
+	static constexpr int VS = UPS + 2;                 // stride of a system's partial sums    (conflict-free D fragment stores)
+	static_assert(UPS % 32 == 0 && WARPS % RT == 0 && KT % KG == 0 && KPG % 2 == 0, "unsupported shape for the tensor-core coupling");
+};
+
+// One coupling term of all 8 systems.  frag: the matrix in fragment order [RT][KT][32]; cpt: [8][CS]; vpart: [KG][8][VS].
+template <int UPS>
+__device__ __forceinline__ void mma_coupling_product(const double* __restrict__ frag, const double* cpt, double* vpart, int warp, int lane)
+{
+	using G = MmaGeometry<UPS>;
+	const int rt = warp % G::RT, kg = warp / G::RT;
+	const double* A = frag + (size_t)(rt * G::KT + kg * G::KPG) * 32 + lane;
+	const double* B = cpt + (lane >> 2) * G::CS + kg * G::KPG * 4 + (lane & 3);
+	double c0 = 0, c1 = 0, e0 = 0, e1 = 0;             // two independent accumulator pairs hide the DMMA latency
+	#pragma unroll
+	for (int j = 0; j < G::KPG; j += 2)
+	{
+		const double a0 = A[j * 32], b0 = B[j * 4], a1 = A[(j + 1) * 32], b1 = B[(j + 1) * 4];
+		dmma_8x8x4(c0, c1, a0, b0);
+		dmma_8x8x4(e0, e1, a1, b1);
+	}
+	double* V = vpart + (size_t)kg * G::SLOTS * G::VS + rt * 8 + (lane >> 2);
+	V[(2 * (lane & 3)) * G::VS]     = c0 + e0;
+	V[(2 * (lane & 3) + 1) * G::VS] = c1 + e1;
+}
+
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
-          int NE, bool DENSE, int ALG, int SPBK>
+          int NE, bool DENSE, int ALG, int SPBK, bool MMA>
 __global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), 1)
 perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 {
@@ -139,16 +190,33 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	constexpr int WPS = UPSP / 32;
 	constexpr int MSIZE = packed_matrix_elements(UPS, NC, CBW, CCI);
 	constexpr int MSTRIDE = MSIZE / (NC > 0 ? NC : 1);
-	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA>;
+	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA, MMA>;
+	using G = MmaGeometry<MMA ? UPS : 32>;
+	constexpr int CPT_ELEMS = MMA ? NC * G::SLOTS * G::CS : 0;             // coupling terms of the 8 systems (MMA variant)
+	constexpr int V_ELEMS   = MMA ? NC * G::KG * G::SLOTS * G::VS : 0;     // partial column sums per k group
+	static_assert(!MMA || (SPBK == G::SLOTS && CBW == 0 && CCI == 0 && NC > 0 && sizeof(P) == 8), "tensor-core coupling: dense FP64 matrices, 8 systems per block");
 
 	extern __shared__ __align__(16) unsigned char dyn_smem[];
-	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE]
-	P*   s_gpar   = s_matrix + MSIZE;                                   // [NGP]
+	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE]  packed (scalar) or in fragment order (MMA)
+	P*   s_cptm   = s_matrix + MSIZE;                                   // [CPT_ELEMS]
+	P*   s_vpart  = s_cptm + CPT_ELEMS;                                 // [V_ELEMS]
+	P*   s_gpar   = s_vpart + V_ELEMS;                                  // [NGP]
 	int* s_igpar  = reinterpret_cast<int*>(s_gpar + NGP);               // [NiGP]
 	__shared__ Slot s_slots[SPBK];
 	__shared__ int  s_cidx[AtLeastOne<NC>::value];
 
-	for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
+	if (MMA)
+	{
+		// fragment order: tile (rt, kt) = rows 8 rt .. 8 rt + 7, columns 4 kt .. 4 kt + 3; lane l holds M[8 rt + l/4][4 kt + l%4]
+		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x)
+		{
+			const int k = i / (UPS * UPS), r = i % (UPS * UPS), tile = r / 32, l = r % 32;
+			const int row = (tile / G::KT) * 8 + (l >> 2), col = (tile % G::KT) * 4 + (l & 3);
+			s_matrix[i] = a.CouplingMatrix[(size_t)k * UPS * UPS + row + col * UPS];
+		}
+	}
+	else
+		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
 	for (int i = threadIdx.x; i < NGP; i += blockDim.x)   s_gpar[i] = a.GlobalParameters[i];
 	for (int i = threadIdx.x; i < NiGP; i += blockDim.x)  s_igpar[i] = a.IntegerGlobalParameters[i];
 	for (int i = threadIdx.x; i < NC; i += blockDim.x)    s_cidx[i] = a.CouplingIndex[i];
@@ -156,63 +224,375 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 
 	const int  slot = threadIdx.x / UPSP;
 	const int  unit = threadIdx.x % UPSP;
-	const bool live = unit < UPS;            // padding lanes only take part in barriers
+	const bool is_unit = unit < UPS;         // padding lanes only take part in barriers
 	const int  wis  = unit / 32;             // warp within the slot
 	const int  lane = unit & 31;
+	const int  warp = threadIdx.x / 32;
 	Slot& S = s_slots[slot];
 	const size_t NU = (size_t)a.NS * UPS;    // unit-scope stride
 
-	int  sys   = blockIdx.x * SPBK + slot;
-	bool first = true;
+	// unit-scope data of the slot's current system: registers
+	P   x[UD], upar[AtLeastOne<NUP>::value], uacc[AtLeastOne<NUA>::value], ev[AtLeastOne<NE>::value];
+	int iuacc[AtLeastOne<NiUA>::value];
+	P   dt_new = a.InitialTimeStep;
+	unsigned attempted = 0, accepted = 0;
+	int    sys = blockIdx.x * SPBK + slot, gsys = 0;
+	size_t ug = 0;
+	bool   have = false, dry = false, first = true;
+	int    buf = 0;
 
+	// One trip of this loop = one attempted step of the slot's system.  Scalar variant: slots are independent.  MMA variant:
+	// the 8 slots of the block pass through the stages together (a slot without a system only takes part in the barriers
+	// and in the matrix product) until no slot has a system left.
 	for (;;)
 	{
 		// ---- take a system ------------------------------------------------------------------------------
-		if (!first)
+		if (!have && !dry)
 		{
-			if (unit == 0) S.next_system = (int)(gridDim.x * SPBK + atomicAdd(a.WorkQueue, 1u));
-			slot_barrier<UPSP>(slot);
-			sys = S.next_system;
-		}
-		first = false;
-		if (sys >= a.Active) break;
-		const int    gsys = sys + a.SystemOffset;
-		const size_t ug   = (size_t)sys * UPS + (live ? unit : 0);
+			if (!first)
+			{
+				if (unit == 0) S.next_system = (int)(gridDim.x * SPBK + atomicAdd(a.WorkQueue, 1u));
+				slot_barrier<UPSP>(slot);
+				sys = S.next_system;
+			}
+			first = false;
+			if (sys >= a.Active) dry = true;
+			else
+			{
+				gsys = sys + a.SystemOffset;
+				ug   = (size_t)sys * UPS + (is_unit ? unit : 0);
+				// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
+				if (unit == 0)
+				{
+					S.td[0] = a.TimeDomain[sys];  S.td[1] = a.TimeDomain[sys + a.NS];
+					S.t = a.ActualTime[sys];  S.dt = a.InitialTimeStep;
+					S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.dense_skipped = 0;  S.udt = 0;  S.dense_next_time = P(0);
+				}
+				if (unit < NSP)  S.spar[unit]     = a.SystemParameters[sys + unit * a.NS];
+				if (unit < NSA)  S.sacc[unit]     = a.SystemAccessories[sys + unit * a.NS];
+				if (unit < NiSA) S.isacc[unit]    = a.IntegerSystemAccessories[sys + unit * a.NS];
+				if (unit < NC)   S.strength[unit] = a.CouplingStrength[sys + unit * a.NS];
+				#pragma unroll
+				for (int i = 0; i < UD; i++)   x[i]     = a.ActualState[ug + i * NU];
+				#pragma unroll
+				for (int i = 0; i < NUP; i++)  upar[i]  = a.UnitParameters[ug + i * NU];
+				#pragma unroll
+				for (int i = 0; i < NUA; i++)  uacc[i]  = a.UnitAccessories[ug + i * NU];
+				#pragma unroll
+				for (int i = 0; i < NiUA; i++) iuacc[i] = a.IntegerUnitAccessories[ug + i * NU];
+				slot_barrier<UPSP>(slot);
 
-		// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
-		P   x[UD], upar[AtLeastOne<NUP>::value], uacc[AtLeastOne<NUA>::value], ev[AtLeastOne<NE>::value];
-		int iuacc[AtLeastOne<NiUA>::value];
-		if (unit == 0)
+				if (is_unit) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+				slot_barrier<UPSP>(slot);
+				if (NE > 0)
+				{
+					if (is_unit) Sys::EventFunction(gsys, unit, ev, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+					slot_barrier<UPSP>(slot);
+				}
+				if (DENSE)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
+				{
+					const int di = S.dense_index;
+					if (di < a.DenseCapacity)
+					{
+						if (is_unit)
+						{
+							#pragma unroll
+							for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
+						}
+						if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
+					}
+					slot_barrier<UPSP>(slot);
+					if (unit == 0) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
+					slot_barrier<UPSP>(slot);
+				}
+				dt_new = a.InitialTimeStep;
+				attempted = 0;  accepted = 0;
+				have = true;
+			}
+		}
+		if (MMA) { if (!__syncthreads_or(have ? 1 : 0)) break; }
+		else if (!have) break;
+		const bool live = have && is_unit;
+
+		// right-hand side of this unit including the coupling term
+		auto rhs = [&](P* F, P* X, P T) {
+			P cpt[AtLeastOne<NC>::value], cpf[AtLeastOne<NC>::value];
+			if (MMA)
+			{
+				// all 8 systems of the block at once on the tensor cores; two block barriers
+				if (live)
+				{
+					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
+					#pragma unroll
+					for (int k = 0; k < NC; k++) s_cptm[(k * G::SLOTS + slot) * G::CS + unit] = cpt[k];
+				}
+				__syncthreads();
+				#pragma unroll
+				for (int k = 0; k < NC; k++)
+					mma_coupling_product<MMA ? UPS : 32>((const double*)s_matrix + (size_t)k * UPS * UPS, (const double*)s_cptm + k * G::SLOTS * G::CS,
+					                                     (double*)s_vpart + k * G::KG * G::SLOTS * G::VS, warp, threadIdx.x & 31);
+				__syncthreads();
+				if (live)
+				{
+					#pragma unroll
+					for (int k = 0; k < NC; k++)
+					{
+						P v = 0;
+						#pragma unroll
+						for (int g = 0; g < G::KG; g++) v += s_vpart[((k * G::KG + g) * G::SLOTS + slot) * G::VS + unit];
+						const P add = S.strength[k] * cpf[k] * v;
+						const int ci = s_cidx[k];
+						#pragma unroll
+						for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
+					}
+				}
+			}
+			else
+			{
+				// one slot barrier
+				if (live)
+				{
+					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
+					#pragma unroll
+					for (int k = 0; k < NC; k++) S.cpt[buf][k][unit] = cpt[k];
+				}
+				slot_barrier<UPSP>(slot);
+				if (live)
+				{
+					#pragma unroll
+					for (int k = 0; k < NC; k++)
+					{
+						const P v = coupling_value<P, UPS, CBW, CCI>(s_matrix + k * MSTRIDE, S.cpt[buf][k], unit);
+						const P add = S.strength[k] * cpf[k] * v;
+						const int ci = s_cidx[k];
+						#pragma unroll
+						for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
+					}
+				}
+				buf ^= 1;
+			}
+		};
+
+		// ======================= one attempted step of the whole system =====================================
+		bool terminated = false;
+		const P t = S.t;
+		P dt = dt_new;
+		bool end_reached = false;
 		{
-			S.td[0] = a.TimeDomain[sys];  S.td[1] = a.TimeDomain[sys + a.NS];
-			S.t = a.ActualTime[sys];  S.dt = a.InitialTimeStep;
-			S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.dense_skipped = 0;  S.udt = 0;  S.dense_next_time = P(0);
+			const P remaining = S.td[1] - t;
+			if (dt > remaining) { dt = remaining; end_reached = true; }
 		}
-		if (unit < NSP)  S.spar[unit]     = a.SystemParameters[sys + unit * a.NS];
-		if (unit < NSA)  S.sacc[unit]     = a.SystemAccessories[sys + unit * a.NS];
-		if (unit < NiSA) S.isacc[unit]    = a.IntegerSystemAccessories[sys + unit * a.NS];
-		if (unit < NC)   S.strength[unit] = a.CouplingStrength[sys + unit * a.NS];
-		#pragma unroll
-		for (int i = 0; i < UD; i++)   x[i]     = a.ActualState[ug + i * NU];
-		#pragma unroll
-		for (int i = 0; i < NUP; i++)  upar[i]  = a.UnitParameters[ug + i * NU];
-		#pragma unroll
-		for (int i = 0; i < NUA; i++)  uacc[i]  = a.UnitAccessories[ug + i * NU];
-		#pragma unroll
-		for (int i = 0; i < NiUA; i++) iuacc[i] = a.IntegerUnitAccessories[ug + i * NU];
-		slot_barrier<UPSP>(slot);
+		if (unit == 0) S.dt = dt;
+		attempted++;
+		bool update = true, finite = true;
 
-		if (live) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-		slot_barrier<UPSP>(slot);
+		P xn[UD];
+		if (ALG == kAlgRK4)
+		{
+			// Steppers.cuh:2015-2227 (expression shapes of the coupled stepper)
+			P X[UD], k[UD];
+			rhs(xn, x, t);
+			P T = t + P(0.5) * dt;
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + xn[i] * P(0.5) * dt;
+			rhs(k, X, T);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) { xn[i] += 2 * k[i]; X[i] = x[i] + k[i] * P(0.5) * dt; }
+			rhs(k, X, T);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) { xn[i] += P(2.0) * k[i]; X[i] = x[i] + k[i] * dt; }
+			T = t + dt;
+			rhs(k, X, T);
+			#pragma unroll
+			for (int i = 0; i < UD; i++)
+			{
+				xn[i] = x[i] + dt * (xn[i] + k[i]) * P(1.0 / 6.0);
+				finite = finite && Num<P>::finite(xn[i]);
+			}
+			// per-system "all finite" (ErrorControllers.cuh:421-441): not finite => message, terminate, step not committed
+			int f = finite || !live;
+			f = __all_sync(0xffffffffu, f);
+			if (WPS > 1)
+			{
+				if (lane == 0) S.red_flags[wis] = f;
+				slot_barrier<UPSP>(slot);
+				#pragma unroll
+				for (int w = 0; w < WPS; w++) f = f && S.red_flags[w];
+			}
+			if (!f)
+			{
+				if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number. Try to use smaller step size. (global system id: %d)\n", gsys);
+				terminated = true;  update = false;
+			}
+			dt_new = a.InitialTimeStep;
+		}
+		else
+		{
+			// Steppers.cuh:2228-2544
+			P X[UD], k1[UD], k2[UD], k3[UD], k4[UD], k5[UD], k6[UD], err[UD];
+			rhs(k1, x, t);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A21)) * dt;
+			rhs(k2, X, t + ck<P>(CK_C2) * dt);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A31) + k2[i] * ck<P>(CK_A32)) * dt;
+			rhs(k3, X, t + ck<P>(CK_C3) * dt);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A41) + k2[i] * ck<P>(CK_A42) + k3[i] * ck<P>(CK_A43)) * dt;
+			rhs(k4, X, t + ck<P>(CK_C4) * dt);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A51) + k2[i] * ck<P>(CK_A52) + k3[i] * ck<P>(CK_A53) + k4[i] * ck<P>(CK_A54)) * dt;
+			rhs(k5, X, t + dt);
+			#pragma unroll
+			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A61) + k2[i] * ck<P>(CK_A62) + k3[i] * ck<P>(CK_A63) + k4[i] * ck<P>(CK_A64) + k5[i] * ck<P>(CK_A65)) * dt;
+			rhs(k6, X, t + ck<P>(CK_C6) * dt);
+
+			// per-unit error ratio q = max_i err_i/tol_i, accept flag, finite flag (ErrorControllers.cuh:483-500)
+			P q = P(0);
+			#pragma unroll
+			for (int i = 0; i < UD; i++)
+			{
+				xn[i] = x[i] + (k1[i] * ck<P>(CK_B1) + k3[i] * ck<P>(CK_B3) + k4[i] * ck<P>(CK_B4) + k6[i] * ck<P>(CK_B6)) * dt;
+				const P e = k1[i] * ck<P>(CK_E1) + k3[i] * ck<P>(CK_E3) + k4[i] * ck<P>(CK_E4) + k5[i] * ck<P>(CK_E5) + k6[i] * ck<P>(CK_E6);
+				err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
+				finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
+				const P tol = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(x[i])), a.AbsoluteTolerance[i]);
+				update = update && (err[i] < tol);
+				q = fmax(q, err[i] / tol);
+			}
+			if (!live) { q = P(0); update = true; finite = true; }
+			// slot-wide reduction: shuffles inside the warp, one word per warp across warps
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) q = fmax(q, __shfl_xor_sync(0xffffffffu, q, o));
+			int flags = (__all_sync(0xffffffffu, update) ? 1 : 0) | (__all_sync(0xffffffffu, finite) ? 2 : 0);
+			if (WPS > 1)
+			{
+				if (lane == 0) { S.red_ratio[wis] = q;  S.red_flags[wis] = flags; }
+				slot_barrier<UPSP>(slot);
+				#pragma unroll
+				for (int w = 0; w < WPS; w++) { q = fmax(q, S.red_ratio[w]);  flags &= S.red_flags[w]; }
+			}
+			update = (flags & 1) != 0;
+			finite = (flags & 2) != 0;
+
+			// every thread evaluates the controller (ErrorControllers.cuh:504-539) from the reduced values
+			const bool at_minimum = dt < a.MinimumTimeStepGuard;
+			P mult;
+			const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 <= q < 2^30 (and q > 1e-30: the reference's initial 1e30)
+			if (finite && qt < Num<P>::kSpan)
+				mult = P(0.8) * inverse_root_fast(q, update);
+			else if (MMA && !have)
+				mult = P(1.0);                                      // a slot without a system: nothing to control
+			else
+			{
+				const P rel = fmin(P(1e30), P(1.0) / q);
+				mult = P(0.8) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+				if (!Num<P>::finite(mult)) finite = false;
+			}
+			if (!finite)
+			{
+				mult = a.TimeStepShrinkLimit;
+				update = false;
+				if (at_minimum)
+				{
+					if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number, minimum step size reached. Try to use less stringent tolerances. (global system id: %d)\n", gsys);
+					terminated = true;
+				}
+			}
+			else if (at_minimum)
+			{
+				if (a.DeviceMessages && unit == 0 && have) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed! (global system id: %d)\n", gsys);
+				update = true;
+			}
+			mult = fmin(mult, a.TimeStepGrowLimit);
+			mult = fmax(mult, a.TimeStepShrinkLimit);
+			dt_new = dt * mult;
+			dt_new = fmin(dt_new, a.MaximumTimeStep);
+			dt_new = fmax(dt_new, a.MinimumTimeStep);
+		}
+		if (MMA && !have) { update = false;  terminated = false; }     // idle slot: no commit, no store
+
+		// ---- events: the earliest secant estimate over all units and events (EventHandling.cuh:216-268) ----
+		P evn[AtLeastOne<NE>::value];
 		if (NE > 0)
 		{
-			if (live) Sys::EventFunction(gsys, unit, ev, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-			slot_barrier<UPSP>(slot);
+			if (live && !terminated)
+				Sys::EventFunction(gsys, unit, evn, t + dt, dt_new, S.td, xn, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+			P dt_event = dt;
+			int corrected = 0;
+			if (live && update && !terminated)
+			{
+				#pragma unroll
+				for (int i = 0; i < NE; i++)
+				{
+					const P et = a.EventTolerance[i];
+					if (((ev[i] > et) && (evn[i] < -et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (evn[i] > et) && (a.EventDirection[i] >= 0)))
+					{
+						dt_event = fmin(dt_event, -ev[i] / (evn[i] - ev[i]) * dt);
+						corrected = 1;
+					}
+				}
+			}
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) dt_event = fmin(dt_event, __shfl_xor_sync(0xffffffffu, dt_event, o));
+			corrected = __any_sync(0xffffffffu, corrected);
+			if (WPS > 1)
+			{
+				if (lane == 0) { S.red_evdt[wis] = dt_event;  S.red_corrected[wis] = corrected; }
+				slot_barrier<UPSP>(slot);
+				#pragma unroll
+				for (int w = 0; w < WPS; w++) { dt_event = fmin(dt_event, S.red_evdt[w]);  corrected |= S.red_corrected[w]; }
+			}
+			if (corrected)
+			{
+				if (dt_event < a.MinimumTimeStep)
+				{
+					if (a.DeviceMessages && unit == 0) printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (global system id: %d)\n", gsys);
+				}
+				else { dt_new = dt_event;  update = false; }
+			}
 		}
-		if (DENSE)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
+
+		// ---- accepted step (Solver.cuh:2670-2806) ----------------------------------------------------------
+		if (update)
+		{
+			accepted++;
+			if (unit == 0) S.t = t + dt;
+			#pragma unroll
+			for (int i = 0; i < UD; i++) x[i] = xn[i];
+			slot_barrier<UPSP>(slot);
+			if (live) Sys::ActionAfterSuccessfulTimeStep(gsys, unit, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+			slot_barrier<UPSP>(slot);
+			if (NE > 0)
+			{
+				if (live)
+				{
+					#pragma unroll
+					for (int i = 0; i < NE; i++)
+					{
+						const P et = a.EventTolerance[i];
+						if (((ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
+							Sys::ActionAfterEventDetection(gsys, unit, i, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+					}
+				}
+				slot_barrier<UPSP>(slot);
+				if (live) Sys::EventFunction(gsys, unit, ev, S.t, dt_new, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+				slot_barrier<UPSP>(slot);
+			}
+		}
+		const bool user_stop = update && (S.udt == 1);
+
+		if (DENSE && have)   // DenseOutput.cuh:362-395, then :314-360
 		{
 			const int di = S.dense_index;
-			if (di < a.DenseCapacity)
+			bool store = false;
+			if (update)
+			{
+				const bool room = di < a.DenseCapacity;
+				store = room && (S.dense_next_time < S.t) && (S.dense_skipped >= (a.DenseOutputSaveFrequency - 1));
+				if (room && (end_reached || user_stop)) store = true;
+			}
+			if (store)
 			{
 				if (live)
 				{
@@ -222,302 +602,44 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
 			}
 			slot_barrier<UPSP>(slot);
-			if (unit == 0) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
+			if (unit == 0)
+			{
+				if (store) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
+				else if (update) S.dense_skipped++;
+			}
 			slot_barrier<UPSP>(slot);
 		}
 
-		P dt_new = a.InitialTimeStep;
-		unsigned attempted = 0, accepted = 0;
-		bool terminated = false;
-		int  buf = 0;
-
-		// right-hand side of this unit including the coupling term; one slot barrier
-		auto rhs = [&](P* F, P* X, P T) {
-			P cpt[AtLeastOne<NC>::value], cpf[AtLeastOne<NC>::value];
-			if (live)
-			{
-				Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
-				#pragma unroll
-				for (int k = 0; k < NC; k++) S.cpt[buf][k][unit] = cpt[k];
-			}
-			slot_barrier<UPSP>(slot);
-			if (live)
-			{
-				#pragma unroll
-				for (int k = 0; k < NC; k++)
-				{
-					const P v = coupling_value<P, UPS, CBW, CCI>(s_matrix + k * MSTRIDE, S.cpt[buf][k], unit);
-					const P add = S.strength[k] * cpf[k] * v;
-					const int ci = s_cidx[k];
-					#pragma unroll
-					for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
-				}
-			}
-			buf ^= 1;
-		};
-
-		while (!terminated)
-		{
-			// ======================= one attempted step of the whole system =================================
-			const P t = S.t;
-			P dt = dt_new;
-			bool end_reached = false;
-			{
-				const P remaining = S.td[1] - t;
-				if (dt > remaining) { dt = remaining; end_reached = true; }
-			}
-			if (unit == 0) S.dt = dt;
-			attempted++;
-			bool update = true, finite = true;
-
-			P xn[UD];
-			if (ALG == kAlgRK4)
-			{
-				// Steppers.cuh:2015-2227 (expression shapes of the coupled stepper)
-				P X[UD], k[UD];
-				rhs(xn, x, t);
-				P T = t + P(0.5) * dt;
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + xn[i] * P(0.5) * dt;
-				rhs(k, X, T);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) { xn[i] += 2 * k[i]; X[i] = x[i] + k[i] * P(0.5) * dt; }
-				rhs(k, X, T);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) { xn[i] += P(2.0) * k[i]; X[i] = x[i] + k[i] * dt; }
-				T = t + dt;
-				rhs(k, X, T);
-				#pragma unroll
-				for (int i = 0; i < UD; i++)
-				{
-					xn[i] = x[i] + dt * (xn[i] + k[i]) * P(1.0 / 6.0);
-					finite = finite && Num<P>::finite(xn[i]);
-				}
-				// per-system "all finite" (ErrorControllers.cuh:421-441): not finite => message, terminate, step not committed
-				int f = finite || !live;
-				f = __all_sync(0xffffffffu, f);
-				if (WPS > 1)
-				{
-					if (lane == 0) S.red_flags[wis] = f;
-					slot_barrier<UPSP>(slot);
-					#pragma unroll
-					for (int w = 0; w < WPS; w++) f = f && S.red_flags[w];
-				}
-				if (!f)
-				{
-					if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number. Try to use smaller step size. (global system id: %d)\n", gsys);
-					terminated = true;  update = false;
-				}
-				dt_new = a.InitialTimeStep;
-			}
-			else
-			{
-				// Steppers.cuh:2228-2544
-				P X[UD], k1[UD], k2[UD], k3[UD], k4[UD], k5[UD], k6[UD], err[UD];
-				rhs(k1, x, t);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A21)) * dt;
-				rhs(k2, X, t + ck<P>(CK_C2) * dt);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A31) + k2[i] * ck<P>(CK_A32)) * dt;
-				rhs(k3, X, t + ck<P>(CK_C3) * dt);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A41) + k2[i] * ck<P>(CK_A42) + k3[i] * ck<P>(CK_A43)) * dt;
-				rhs(k4, X, t + ck<P>(CK_C4) * dt);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A51) + k2[i] * ck<P>(CK_A52) + k3[i] * ck<P>(CK_A53) + k4[i] * ck<P>(CK_A54)) * dt;
-				rhs(k5, X, t + dt);
-				#pragma unroll
-				for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A61) + k2[i] * ck<P>(CK_A62) + k3[i] * ck<P>(CK_A63) + k4[i] * ck<P>(CK_A64) + k5[i] * ck<P>(CK_A65)) * dt;
-				rhs(k6, X, t + ck<P>(CK_C6) * dt);
-
-				// per-unit error ratio q = max_i err_i/tol_i, accept flag, finite flag (ErrorControllers.cuh:483-500)
-				P q = P(0);
-				#pragma unroll
-				for (int i = 0; i < UD; i++)
-				{
-					xn[i] = x[i] + (k1[i] * ck<P>(CK_B1) + k3[i] * ck<P>(CK_B3) + k4[i] * ck<P>(CK_B4) + k6[i] * ck<P>(CK_B6)) * dt;
-					const P e = k1[i] * ck<P>(CK_E1) + k3[i] * ck<P>(CK_E3) + k4[i] * ck<P>(CK_E4) + k5[i] * ck<P>(CK_E5) + k6[i] * ck<P>(CK_E6);
-					err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
-					finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
-					const P tol = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(x[i])), a.AbsoluteTolerance[i]);
-					update = update && (err[i] < tol);
-					q = fmax(q, err[i] / tol);
-				}
-				if (!live) { q = P(0); update = true; finite = true; }
-				// slot-wide reduction: shuffles inside the warp, one word per warp across warps
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) q = fmax(q, __shfl_xor_sync(0xffffffffu, q, o));
-				int flags = (__all_sync(0xffffffffu, update) ? 1 : 0) | (__all_sync(0xffffffffu, finite) ? 2 : 0);
-				if (WPS > 1)
-				{
-					if (lane == 0) { S.red_ratio[wis] = q;  S.red_flags[wis] = flags; }
-					slot_barrier<UPSP>(slot);
-					#pragma unroll
-					for (int w = 0; w < WPS; w++) { q = fmax(q, S.red_ratio[w]);  flags &= S.red_flags[w]; }
-				}
-				update = (flags & 1) != 0;
-				finite = (flags & 2) != 0;
-
-				// every thread evaluates the controller (ErrorControllers.cuh:504-539) from the reduced values
-				const bool at_minimum = dt < a.MinimumTimeStepGuard;
-				P mult;
-				const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 <= q < 2^30 (and q > 1e-30: the reference's initial 1e30)
-				if (finite && qt < Num<P>::kSpan)
-					mult = P(0.8) * inverse_root_fast(q, update);
-				else
-				{
-					const P rel = fmin(P(1e30), P(1.0) / q);
-					mult = P(0.8) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
-					if (!Num<P>::finite(mult)) finite = false;
-				}
-				if (!finite)
-				{
-					mult = a.TimeStepShrinkLimit;
-					update = false;
-					if (at_minimum)
-					{
-						if (a.DeviceMessages && unit == 0) printf("Error: State is not a finite number, minimum step size reached. Try to use less stringent tolerances. (global system id: %d)\n", gsys);
-						terminated = true;
-					}
-				}
-				else if (at_minimum)
-				{
-					if (a.DeviceMessages && unit == 0) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed! (global system id: %d)\n", gsys);
-					update = true;
-				}
-				mult = fmin(mult, a.TimeStepGrowLimit);
-				mult = fmax(mult, a.TimeStepShrinkLimit);
-				dt_new = dt * mult;
-				dt_new = fmin(dt_new, a.MaximumTimeStep);
-				dt_new = fmax(dt_new, a.MinimumTimeStep);
-			}
-
-			// ---- events: the earliest secant estimate over all units and events (EventHandling.cuh:216-268) ----
-			P evn[AtLeastOne<NE>::value];
-			if (NE > 0)
-			{
-				if (live && !terminated)
-					Sys::EventFunction(gsys, unit, evn, t + dt, dt_new, S.td, xn, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-				P dt_event = dt;
-				int corrected = 0;
-				if (live && update && !terminated)
-				{
-					#pragma unroll
-					for (int i = 0; i < NE; i++)
-					{
-						const P et = a.EventTolerance[i];
-						if (((ev[i] > et) && (evn[i] < -et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (evn[i] > et) && (a.EventDirection[i] >= 0)))
-						{
-							dt_event = fmin(dt_event, -ev[i] / (evn[i] - ev[i]) * dt);
-							corrected = 1;
-						}
-					}
-				}
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1) dt_event = fmin(dt_event, __shfl_xor_sync(0xffffffffu, dt_event, o));
-				corrected = __any_sync(0xffffffffu, corrected);
-				if (WPS > 1)
-				{
-					if (lane == 0) { S.red_evdt[wis] = dt_event;  S.red_corrected[wis] = corrected; }
-					slot_barrier<UPSP>(slot);
-					#pragma unroll
-					for (int w = 0; w < WPS; w++) { dt_event = fmin(dt_event, S.red_evdt[w]);  corrected |= S.red_corrected[w]; }
-				}
-				if (corrected)
-				{
-					if (dt_event < a.MinimumTimeStep)
-					{
-						if (a.DeviceMessages && unit == 0) printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (global system id: %d)\n", gsys);
-					}
-					else { dt_new = dt_event;  update = false; }
-				}
-			}
-
-			// ---- accepted step (Solver.cuh:2670-2806) ----------------------------------------------------------
-			if (update)
-			{
-				accepted++;
-				if (unit == 0) S.t = t + dt;
-				#pragma unroll
-				for (int i = 0; i < UD; i++) x[i] = xn[i];
-				slot_barrier<UPSP>(slot);
-				if (live) Sys::ActionAfterSuccessfulTimeStep(gsys, unit, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-				slot_barrier<UPSP>(slot);
-				if (NE > 0)
-				{
-					if (live)
-					{
-						#pragma unroll
-						for (int i = 0; i < NE; i++)
-						{
-							const P et = a.EventTolerance[i];
-							if (((ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
-								Sys::ActionAfterEventDetection(gsys, unit, i, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-						}
-					}
-					slot_barrier<UPSP>(slot);
-					if (live) Sys::EventFunction(gsys, unit, ev, S.t, dt_new, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-					slot_barrier<UPSP>(slot);
-				}
-			}
-			const bool user_stop = update && (S.udt == 1);
-
-			if (DENSE)   // DenseOutput.cuh:362-395, then :314-360
-			{
-				const int di = S.dense_index;
-				bool store = false;
-				if (update)
-				{
-					const bool room = di < a.DenseCapacity;
-					store = room && (S.dense_next_time < S.t) && (S.dense_skipped >= (a.DenseOutputSaveFrequency - 1));
-					if (room && (end_reached || user_stop)) store = true;
-				}
-				if (store)
-				{
-					if (live)
-					{
-						#pragma unroll
-						for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
-					}
-					if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
-				}
-				slot_barrier<UPSP>(slot);
-				if (unit == 0)
-				{
-					if (store) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
-					else if (update) S.dense_skipped++;
-				}
-				slot_barrier<UPSP>(slot);
-			}
-
-			if (update && (end_reached || user_stop)) terminated = true;
-		}
+		if (update && (end_reached || user_stop)) terminated = true;
 
 		// ---- end of the phase for this system (Solver.cuh:2812-2887) -------------------------------------------
-		slot_barrier<UPSP>(slot);
-		if (live) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-		slot_barrier<UPSP>(slot);
-		if (live)
+		if (terminated)
 		{
-			#pragma unroll
-			for (int i = 0; i < UD; i++)   a.ActualState[ug + i * NU] = x[i];
-			#pragma unroll
-			for (int i = 0; i < NUA; i++)  a.UnitAccessories[ug + i * NU] = uacc[i];
-			#pragma unroll
-			for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[ug + i * NU] = iuacc[i];
+			slot_barrier<UPSP>(slot);
+			if (live) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+			slot_barrier<UPSP>(slot);
+			if (live)
+			{
+				#pragma unroll
+				for (int i = 0; i < UD; i++)   a.ActualState[ug + i * NU] = x[i];
+				#pragma unroll
+				for (int i = 0; i < NUA; i++)  a.UnitAccessories[ug + i * NU] = uacc[i];
+				#pragma unroll
+				for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[ug + i * NU] = iuacc[i];
+			}
+			if (unit < NSA)  a.SystemAccessories[sys + unit * a.NS] = S.sacc[unit];
+			if (unit < NiSA) a.IntegerSystemAccessories[sys + unit * a.NS] = S.isacc[unit];
+			if (unit == 0)
+			{
+				a.ActualTime[sys] = S.t;
+				a.TimeDomain[sys] = S.td[0];  a.TimeDomain[sys + a.NS] = S.td[1];
+				if (DENSE) a.DenseOutputIndex[sys] = S.dense_index;
+				a.StepsAttempted[sys] += attempted;
+				a.StepsAccepted[sys]  += accepted;
+			}
+			slot_barrier<UPSP>(slot);
+			have = false;
 		}
-		if (unit < NSA)  a.SystemAccessories[sys + unit * a.NS] = S.sacc[unit];
-		if (unit < NiSA) a.IntegerSystemAccessories[sys + unit * a.NS] = S.isacc[unit];
-		if (unit == 0)
-		{
-			a.ActualTime[sys] = S.t;
-			a.TimeDomain[sys] = S.td[0];  a.TimeDomain[sys + a.NS] = S.td[1];
-			if (DENSE) a.DenseOutputIndex[sys] = S.dense_index;
-			a.StepsAttempted[sys] += attempted;
-			a.StepsAccepted[sys]  += accepted;
-		}
-		slot_barrier<UPSP>(slot);
 	}
 }
 
@@ -532,6 +654,31 @@ struct PerBlockLauncher
 	static_assert(UPSP <= 1024, "UnitsPerSystem above 1024 would need several threads' worth of units per thread (not built)");
 	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
 
+	// tensor-core coupling: dense FP64 matrices shared by all systems, whole-warp systems, 8 systems x UPS threads <= 512
+	static constexpr bool kCanMMA = (sizeof(P) == 8) && CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64);
+
+	template <int SLOTS, bool MMA>
+	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
+	{
+		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA>;
+		using G = MmaGeometry<MMA ? UPS : 32>;
+		const size_t extra = MMA ? (size_t)NC * G::SLOTS * G::CS + (size_t)NC * G::KG * G::SLOTS * G::VS : 0;
+		const size_t smem = sizeof(P) * (packed_matrix_elements(UPS, NC, CBW, CCI) + extra + NGP) + sizeof(int) * NiGP + 16;
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		int per_sm = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SLOTS * UPSP, smem);
+		if (e != cudaSuccess) return (int)e;
+		if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+		int grid = (a.Active + SLOTS - 1) / SLOTS;
+		const int resident = per_sm * (L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148);
+		if (grid > resident) grid = resident;
+		e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
+		if (e != cudaSuccess) return (int)e;
+		kernel<<<grid, SLOTS * UPSP, smem, stream>>>(a);
+		return (int)cudaGetLastError();
+	}
+
 	static int launch(const mpgos_coupled_launch* L, void* stream_v)
 	{
 		cudaStream_t stream = (cudaStream_t)stream_v;
@@ -539,7 +686,6 @@ struct PerBlockLauncher
 		if (d.UPS != UPS || d.UD != UD || d.NC != NC || d.CBW != CBW || d.CCI != CCI || d.NUP != NUP || d.NSP != NSP || d.NGP != NGP || d.NiGP != NiGP ||
 		    d.NUA != NUA || d.NiUA != NiUA || d.NSA != NSA || d.NiSA != NiSA || d.NE != NE || d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
 			return (int)cudaErrorInvalidValue;
-		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SPBK>;
 		PerBlockArgs<P, UD, NE> a;
 		a.TimeDomain = (P*)L->d_TimeDomain;  a.ActualState = (P*)L->d_ActualState;  a.ActualTime = (P*)L->d_ActualTime;  a.UnitParameters = (P*)L->d_UnitParameters;
 		a.SystemParameters = (P*)L->d_SystemParameters;  a.GlobalParameters = (P*)L->d_GlobalParameters;  a.IntegerGlobalParameters = L->d_IntegerGlobalParameters;
@@ -555,21 +701,11 @@ struct PerBlockLauncher
 		for (int i = 0; i < UD; i++) { a.RelativeTolerance[i] = (P)L->RelativeTolerance[i];  a.AbsoluteTolerance[i] = (P)L->AbsoluteTolerance[i]; }
 		for (int i = 0; i < AtLeastOne<NE>::value; i++) { a.EventTolerance[i] = (i < NE) ? (P)L->EventTolerance[i] : P(0);  a.EventDirection[i] = (i < NE) ? L->EventDirection[i] : 0; }
 		if (a.Active <= 0) return (int)cudaSuccess;
-
-		const size_t smem = sizeof(P) * (packed_matrix_elements(UPS, NC, CBW, CCI) + NGP) + sizeof(int) * NiGP + 16;
-		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
-		int per_sm = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPBK * UPSP, smem);
-		if (e != cudaSuccess) return (int)e;
-		if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
-		int grid = (a.Active + SPBK - 1) / SPBK;
-		const int resident = per_sm * (L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148);
-		if (grid > resident) grid = resident;
-		e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
-		if (e != cudaSuccess) return (int)e;
-		kernel<<<grid, SPBK * UPSP, smem, stream>>>(a);
-		return (int)cudaGetLastError();
+		if constexpr (kCanMMA)
+		{
+			if (L->TensorCoreCoupling) return enqueue<8, true>(L, a, stream);
+		}
+		return enqueue<SPBK, false>(L, a, stream);
 	}
 };
 

@@ -13,10 +13,13 @@
 //  * the RKCK45 controller needs no FP64 division and no pow(): the limiting component is found
 //    by cross-multiplication and (tol/err)^(1/5 | 1/4) by division-free Newton steps from a
 //    single-precision seed (error ~1 ulp; exotic operand ranges take the exact slow path);
-//  * LaneRefill: persistent warps; a lane that finishes its instance stores it and takes the
-//    next instance id from a device-side queue, so a warp never idles behind its slowest lane
-//    (the "tailing effect" the reference's README describes).  Per-instance arithmetic does not
-//    depend on the lane an instance runs on, so results are identical in both mappings.
+//  * LaneRefill = n: persistent warps.  Lanes that finish their instance store it and go idle;
+//    once a warp ballot counts at least n idle lanes, the warp takes that many instance ids from
+//    a device-side queue with ONE atomic and the idle lanes load them together (coalesced when
+//    n is large), so a warp never idles long behind its slowest lane (the "tailing effect" the
+//    reference's README describes) and never pays the divergent load/store path once per lane.
+//    Per-instance arithmetic does not depend on the lane an instance runs on, so results are
+//    identical in all mappings.
 //
 // The kernel is instantiated in the translation unit that defines the callbacks; the host side
 // reaches it through a plain function pointer (mpgos_perthread_launcher, mpgos_b200.h).
@@ -32,7 +35,7 @@ namespace mpgos_b200 {
 
 constexpr int kMaxThreadsPerBlock = 256;
 #ifndef MPGOS_B200_MIN_BLOCKS_PER_SM
-#define MPGOS_B200_MIN_BLOCKS_PER_SM 1
+#define MPGOS_B200_MIN_BLOCKS_PER_SM 2
 #endif
 constexpr int kAlgRK4 = 0, kAlgRKCK45 = 1;
 
@@ -57,6 +60,7 @@ struct PerThreadArgs
 	int  DenseCapacity;      // NDO
 	int  DenseOutputSaveFrequency;
 	int  DeviceMessages;
+	int  RefillThreshold;    // LaneRefill: idle lanes per warp that trigger a refill (1..32)
 	P    InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit;
 	P    DenseOutputMinimumTimeStep;
 	P    MinimumTimeStepGuard;    // MinimumTimeStep * 1.01 (ErrorControllers.cuh:63,72), formed once on the host in P
@@ -185,8 +189,8 @@ struct LaneState
 // argument lists (see include/SingleSystem_PerThread_Interface.cuh for the adapter that binds the
 // user's PerThread_* functions).
 
-template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL>
-__global__ void __launch_bounds__(kMaxThreadsPerBlock, MPGOS_B200_MIN_BLOCKS_PER_SM)
+template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL, int MINB>
+__global__ void __launch_bounds__(kMaxThreadsPerBlock, MINB)
 perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 {
 	// shared parameters: staged once per block (Solver.cuh:66-88); unlike the reference we
@@ -202,26 +206,50 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 
 	const int NTG    = a.GlobalInstances;
 	const int stride = a.Stride;
-	const unsigned grid_threads = gridDim.x * blockDim.x;
 
 	LaneState<P, SD, NCP, NE, NA, NIA> s;
 	int  inst  = blockIdx.x * blockDim.x + threadIdx.x;
 	bool alive = false;
 	bool first = true;
+	bool queue_empty = false;       // REFILL: warp-uniform
 
 	for (;;)
 	{
-		if (!alive)
+		bool take = false;
+		if (REFILL)
 		{
-			// ---- take an instance ------------------------------------------------------------
-			if (!first)
+			// ---- warp ballot: refill the idle lanes together once there are enough of them -------
+			const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+			if (idle != 0u)
 			{
-				if (!REFILL) break;
-				inst = (int)(grid_threads + atomicAdd(a.WorkQueue, 1u));
+				const int n = __popc(idle);
+				if (!queue_empty && (n >= a.RefillThreshold || n == 32))
+				{
+					const int lane = threadIdx.x & 31;
+					const int leader = __ffs(idle) - 1;
+					unsigned base = 0;
+					if (lane == leader) base = atomicAdd(a.WorkQueue, (unsigned)n);
+					base = __shfl_sync(0xffffffffu, base, leader);
+					if (!alive)
+					{
+						inst = (int)(base + (unsigned)__popc(idle & ((1u << lane) - 1u)));
+						take = inst < a.Active;
+					}
+					queue_empty = (base + (unsigned)n) >= (unsigned)a.Active;
+				}
+				if (idle == 0xffffffffu && !__any_sync(0xffffffffu, take)) break;
 			}
+		}
+		else if (!alive)
+		{
+			if (!first) break;
 			first = false;
 			if (inst >= a.Active) break;
+			take = true;
+		}
 
+		if (take)
+		{
 			// ---- load (coalesced on the first fill), Solver.cuh:117-142 ----------------------
 			#pragma unroll
 			for (int i = 0; i < 2; i++)   s.td[i]   = a.TimeDomain[inst + i * stride];
@@ -260,6 +288,8 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				s.dense_next_time = fmin(s.t + a.DenseOutputMinimumTimeStep, s.td[1]);
 			}
 		}
+
+		if (REFILL && !alive) continue;
 
 		// ======================== one attempted step (Solver.cuh:197-394) =====================
 		const int gid = inst + a.InstanceOffset;
@@ -518,13 +548,18 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 // ---------------------------------------------------------------------------------------------
 // Host-side launcher generated next to the kernel.
 
-template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG>
+// MINB = resident 256-thread blocks per SM the kernel is compiled for, i.e. its register cap: 1 -> 255, 2 -> 128,
+// 3 -> 80, 4 -> 64 registers per thread.  Measured on B200 (profiles/): small systems (Lorenz, the impact
+// oscillator) run fastest at 80 registers, a transcendental-heavy right-hand side (Keller-Miksis) at 128; the
+// compiler's own choice without a cap (120 / 144) is slower in both cases.  Default 2; the built-in systems state
+// theirs; a user translation unit may #define MPGOS_B200_MIN_BLOCKS_PER_SM before including the interface header.
+template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, int MINB = MPGOS_B200_MIN_BLOCKS_PER_SM>
 struct PerThreadLauncher
 {
 	template <bool REFILL>
 	static cudaError_t enqueue(const mpgos_perthread_launch* L, const PerThreadArgs<P, SD, NE>& args, cudaStream_t stream)
 	{
-		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL>;
+		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL, MINB>;
 		int block = L->ThreadsPerBlock;
 		if (block < 32) block = 32;
 		if (block > kMaxThreadsPerBlock) block = kMaxThreadsPerBlock;
@@ -570,6 +605,7 @@ struct PerThreadLauncher
 		a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;
 		a.DeviceMessages = L->DeviceMessages;
+		a.RefillThreshold = L->LaneRefill < 1 ? 1 : (L->LaneRefill > 32 ? 32 : L->LaneRefill);
 		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;
 		a.MinimumTimeStep = (P)L->MinimumTimeStep;  a.TimeStepGrowLimit = (P)L->TimeStepGrowLimit;
 		a.TimeStepShrinkLimit = (P)L->TimeStepShrinkLimit;  a.DenseOutputMinimumTimeStep = (P)L->DenseOutputMinimumTimeStep;

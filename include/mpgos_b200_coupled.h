@@ -44,7 +44,8 @@ typedef enum mpgos_coupled_option
 	MPGOS_COPT_TimeStepGrowLimit, MPGOS_COPT_TimeStepShrinkLimit, MPGOS_COPT_RelativeTolerance, MPGOS_COPT_AbsoluteTolerance,
 	MPGOS_COPT_EventTolerance, MPGOS_COPT_EventDirection, MPGOS_COPT_DenseOutputSaveFrequency, MPGOS_COPT_DenseOutputMinimumTimeStep,
 	MPGOS_COPT_SharedGlobalVariables, MPGOS_COPT_SharedCouplingMatrices,
-	MPGOS_COPT_DeviceMessages
+	MPGOS_COPT_DeviceMessages,
+	MPGOS_COPT_TensorCoreCoupling   /* 1 (default): dense shared coupling matrices go through FP64 tensor-core MMA where the shape allows; 0: scalar sums */
 } mpgos_coupled_option;
 
 /* Template arguments of the reference's coupled ProblemSolver (CP/Interface.cuh:135-136) as run-time data.  TPB and SPB
@@ -72,6 +73,7 @@ typedef struct mpgos_coupled_launch
 	const double* RelativeTolerance;  const double* AbsoluteTolerance;  const double* EventTolerance;  const int* EventDirection;   /* host */
 	double InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep;
 	int    DenseOutputSaveFrequency, ActiveSystems, DeviceMessages, MultiProcessorCount;
+	int    TensorCoreCoupling;
 } mpgos_coupled_launch;
 
 typedef int (*mpgos_coupled_launcher)(const mpgos_coupled_launch* args, void* stream);
@@ -106,7 +108,7 @@ int   mpgos_coupled_save_state(mpgos_coupled_solver* s);
 int   mpgos_coupled_restore_state(mpgos_coupled_solver* s);
 void* mpgos_coupled_stream(mpgos_coupled_solver* s);
 
-/* systems compiled into the library: "bubble_ensemble" (UPS 8, 16, 64, 128), "duffing_ring" (UPS 14; CBW/CCI 1/1, 1/0, 0/1, 0/0) */
+/* systems compiled into the library: "bubble_ensemble" (UPS 8, 16, 32, 64, 128), "duffing_ring" (UPS 14; CBW/CCI 1/1, 1/0, 0/1, 0/0) */
 int   mpgos_coupled_builtin_desc(const char* system, int ups, int cbw, int cci, mpgos_coupled_desc* desc);
 mpgos_coupled_launcher mpgos_coupled_builtin_launcher(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output);
 

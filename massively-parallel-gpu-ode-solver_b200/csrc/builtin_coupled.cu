@@ -16,7 +16,9 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 8, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 16, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 16, 0, 0, kAlgRK4, false),
+	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 32, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 64, 0, 0, kAlgRKCK45, false),
+	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 64, 0, 0, kAlgRK4, false),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 64, 0, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 128, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 1, 1, kAlgRKCK45, true),

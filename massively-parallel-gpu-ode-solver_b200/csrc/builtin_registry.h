@@ -34,9 +34,10 @@ const CoupledBuiltinEntry* builtin_entries_coupled(int* n);
 
 } // namespace mpgos_b200
 
-// Entry for system template S (builtin_systems.cuh), precision P, algorithm ALG, dense flag D.
-#define MPGOS_BUILTIN_ENTRY(NAME, S, P, ALG, D)                                                                       \
+// Entry for system template S (builtin_systems.cuh), precision P, algorithm ALG, dense flag D, register cap MINB
+// (resident 256-thread blocks per SM, see PerThreadLauncher).
+#define MPGOS_BUILTIN_ENTRY(NAME, S, P, ALG, D, MINB)                                                                 \
 	{ NAME, S<P>::SD, S<P>::NCP, S<P>::NSP, S<P>::NISP, S<P>::NE, S<P>::NA, S<P>::NIA, ALG, (int)sizeof(P), D,        \
-	  &mpgos_b200::PerThreadLauncher<S<P>, P, S<P>::SD, S<P>::NCP, S<P>::NSP, S<P>::NISP, S<P>::NE, S<P>::NA, S<P>::NIA, D, ALG>::launch }
+	  &mpgos_b200::PerThreadLauncher<S<P>, P, S<P>::SD, S<P>::NCP, S<P>::NSP, S<P>::NISP, S<P>::NE, S<P>::NA, S<P>::NIA, D, ALG, MINB>::launch }
 
 #endif

@@ -141,7 +141,7 @@ struct mpgos_perthread_solver
 	int    ThreadsPerBlock = 128;
 	int    ActiveNumberOfThreads = 0;
 	int    PreferSharedMemory = 1;
-	int    LaneRefill = 1;
+	int    LaneRefill = 0;      // measured on B200: the direct mapping wins once the register cap gives >= 5 warps per sub-partition (profiles/)
 	int    DeviceMessages = 0;
 	std::vector<double> rtol, atol, evtol;
 	std::vector<int>    evdir;
@@ -293,7 +293,7 @@ int mpgos_perthread_set_option(mpgos_perthread_solver* s, int option, double val
 		case MPGOS_OPT_DenseOutputMinimumTimeStep: s->DenseOutputMinimumTimeStep = value; break;
 		case MPGOS_OPT_DenseOutputSaveFrequency:   s->DenseOutputSaveFrequency = (int)value; break;
 		case MPGOS_OPT_PreferSharedMemory:         s->PreferSharedMemory = (int)value; break;
-		case MPGOS_OPT_LaneRefill:                 s->LaneRefill = (int)value != 0; break;
+		case MPGOS_OPT_LaneRefill:                 s->LaneRefill = (int)value < 0 ? 0 : ((int)value > 32 ? 32 : (int)value); break;
 		case MPGOS_OPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
 		default: return fail(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
 	}

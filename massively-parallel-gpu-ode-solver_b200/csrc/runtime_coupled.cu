@@ -38,7 +38,7 @@ struct mpgos_coupled_solver
 	unsigned int* d_queue = nullptr;
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12, TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1;
 	double DenseOutputMinimumTimeStep = 0.0;
-	int DenseOutputSaveFrequency = 1, ActiveSystems = 0, DeviceMessages = 0, SharedGlobalVariables = 1, SharedCouplingMatrices = 0;
+	int DenseOutputSaveFrequency = 1, ActiveSystems = 0, DeviceMessages = 0, SharedGlobalVariables = 1, SharedCouplingMatrices = 0, TensorCoreCoupling = 1;
 	std::vector<double> rtol, atol, evtol;
 	std::vector<int> evdir;
 };
@@ -198,6 +198,7 @@ int mpgos_coupled_set_option(mpgos_coupled_solver* s, int option, double value)
 		case MPGOS_COPT_SharedGlobalVariables:      s->SharedGlobalVariables = (int)value; break;     // accepted, ignored: always shared
 		case MPGOS_COPT_SharedCouplingMatrices:     s->SharedCouplingMatrices = (int)value; break;    // accepted, ignored: always shared
 		case MPGOS_COPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
+		case MPGOS_COPT_TensorCoreCoupling:         s->TensorCoreCoupling = (int)value != 0; break;
 		default: return CFAIL(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
 	}
 	return MPGOS_OK;
@@ -255,7 +256,7 @@ static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();  L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
 	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
 	L.TimeStepGrowLimit = s->TimeStepGrowLimit;  L.TimeStepShrinkLimit = s->TimeStepShrinkLimit;  L.DenseOutputMinimumTimeStep = s->DenseOutputMinimumTimeStep;
-	L.DenseOutputSaveFrequency = s->DenseOutputSaveFrequency;  L.ActiveSystems = s->ActiveSystems;  L.DeviceMessages = s->DeviceMessages;
+	L.DenseOutputSaveFrequency = s->DenseOutputSaveFrequency;  L.ActiveSystems = s->ActiveSystems;  L.DeviceMessages = s->DeviceMessages;  L.TensorCoreCoupling = s->TensorCoreCoupling;
 	L.MultiProcessorCount = s->sm_count;
 }
 

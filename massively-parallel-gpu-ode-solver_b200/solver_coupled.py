@@ -50,6 +50,7 @@ class CoupledOptions(enum.IntEnum):       # CoupledSystems_PerBlock_Interface.cu
     SharedGlobalVariables = 12
     SharedCouplingMatrices = 13
     DeviceMessages = 14
+    TensorCoreCoupling = 15
 
 
 COUPLED_ABI_SYMBOLS = (
@@ -272,13 +273,15 @@ def read_back_coupled(ps: CoupledProblemSolver, wl):
     return out
 
 
-def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device: int = 0):
+def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device: int = 0, tensor_core_coupling: Optional[int] = None):
     """Integrate a coupled workload on the GPU through the public API; returns (buffers_after, attempted, accepted)."""
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
     with CoupledProblemSolver(wl.name, b.NS, sh.UPS, CBW=sh.CBW, CCI=sh.CCI, NDO=sh.NDO, Algorithm=sh.Algorithm, Device=device,
                               TPB=sh.TPB, SPB=sh.SPB) as ps:
         apply_coupled_workload(ps, wl, b)
+        if tensor_core_coupling is not None:
+            ps.SolverOption(CoupledOptions.TensorCoreCoupling, tensor_core_coupling)
         ps.SynchroniseFromHostToDevice(CoupledVariables.All)
         for _ in range(wl.phases if phases is None else phases):
             ps.Solve()

@@ -130,6 +130,7 @@ int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo,
 	{
 		if (ups == 8)  return dispatch<BubbleEnsemble<double, 8> >(algorithm, ndo, b, o, shape);
 		if (ups == 16) return dispatch<BubbleEnsemble<double, 16> >(algorithm, ndo, b, o, shape);
+		if (ups == 32) return dispatch<BubbleEnsemble<double, 32> >(algorithm, ndo, b, o, shape);
 		if (ups == 64) return dispatch<BubbleEnsemble<double, 64> >(algorithm, ndo, b, o, shape);
 		if (ups == 128) return dispatch<BubbleEnsemble<double, 128> >(algorithm, ndo, b, o, shape);
 	}

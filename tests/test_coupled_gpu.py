@@ -69,6 +69,25 @@ def test_bubble_ensemble_64_units_properties(pkg):
     assert np.array_equal(sout.ActualState, out.ActualState[:, idx, :]) and np.array_equal(satt, att[idx])
 
 
+@pytest.mark.parametrize("ups,ns", [(32, 21), (64, 13)])
+def test_tensor_core_coupling_against_checker_and_scalar_path(ups, ns, pkg, oracle):
+    """Dense shared matrix, FP64, UPS 32/64: the column sums of the 8 systems of a block are one DMMA product
+    (mma.sync.m8n8k4.f64).  Checked against the CPU checker (reference summation order) and against our scalar path;
+    NS is not a multiple of 8, so blocks also run with idle slots.  The product sums in a different order than the
+    reference's single accumulator: endpoints agree to rounding (stated tolerance 1e-9), step counts exactly."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=ns, UPS=ups, amplitude=(0.2, 1.2))
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=1, host_threads=8)
+    tc, tatt, tacc = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=1)
+    sc, satt, sacc = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=0)
+    for out, att, acc in ((tc, tatt, tacc), (sc, satt, sacc)):
+        assert np.array_equal(out.ActualTime, ref.ActualTime)
+        assert np.abs(att - ratt).max() <= 1 and np.abs(acc - racc).max() <= 1
+        assert rel_err(out.ActualState, ref.ActualState).max() < 1e-9
+    assert rel_err(tc.ActualState, sc.ActualState).max() < 1e-9
+    assert not np.array_equal(tc.ActualState, sc.ActualState) or ups < 32    # the two paths really are different code
+
+
 @pytest.mark.parametrize("name,tag,tol", [("bubble_u16_rkck45", "bubble_ensemble_u16", 1e-11), ("ring_b1c1_rkck45", "duffing_ring_b1c1", 1e-9)])
 def test_against_reference_mpgos_coupled_kernels_on_the_same_gpu(name, tag, tol, ccases, pkg, oracle):
     """GPU vs GPU: the reference's own coupled kernels compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_coupled_*.so)."""

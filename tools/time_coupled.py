@@ -9,6 +9,7 @@ NS = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 wl = WC.bubble_ensemble(NS=NS, UPS=64)
 with pkg.CoupledProblemSolver("bubble_ensemble", NS, 64) as ps:
     pkg.apply_coupled_workload(ps, wl)
+    ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, int(os.environ.get('TC', '1')))
     best = None
     for rep in range(4):
         ps.SynchroniseFromHostToDevice(pkg.CoupledVariables.All)
@@ -17,4 +18,4 @@ with pkg.CoupledProblemSolver("bubble_ensemble", NS, 64) as ps:
         best = ms if best is None else min(best, ms)
     att, acc = ps.StepCounters()
     out = pkg.read_back_coupled(ps, wl)
-print(f"lib={os.environ.get('MPGOS_B200_LIBRARY','(default)'):34s} NS={NS}: {best:.2f} ms  {int(att.sum())/best/1e3:.3f} M system-steps/s  checksum {out.ActualState.sum():.12e}")
+print(f"TC={os.environ.get('TC','1')} lib={os.environ.get('MPGOS_B200_LIBRARY','(default)'):34s} NS={NS}: {best:.2f} ms  {int(att.sum())/best/1e3:.3f} M system-steps/s  checksum {out.ActualState.sum():.12e}")
