@@ -1,27 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- system-steps/sec of the thread-per-system ensemble integrator on B200.
+"""bench.py -- system-steps/sec of the B200-native ensemble ODE integrator.
 
     python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...   # reference arm: the reference's own
                                                               # kernel source on the host cores
 
-Workload at every N: BASELINE.json configs[1] -- T2_Lorenz, RKCK45 adaptive, 2^20 rho-sweep
-instances per GPU, FP64 (``--precision f32`` / ``--workload impact|kellermiksis`` select the other
-configurations).  One "step" = one integration phase (one Solve()) of all instances from the
-tutorial's initial condition.  Metric: system-steps/sec, a system-step being one stepper
-invocation (accepted or rejected, 6 right-hand-side evaluations) of one instance.
+Workload at every N (default): BASELINE.json configs[1] -- T2_Lorenz, RKCK45 adaptive, 2^20 rho-sweep
+instances per GPU, FP64.  ``--workload`` selects the other configurations:
+    duffing (C1), lorenz / lorenz_rk4 (C2, --precision f32 for the FP32 run), impact (C3),
+    kellermiksis / kellermiksis_dense (C4), coupled (C5: 8192 systems of 64 coupled bubbles per GPU).
+One "step" = ``--phases`` integration phases (Solve() calls, default 1) of all instances from the
+tutorial's initial condition.  Metric: system-steps/sec, a system-step being one stepper invocation
+(accepted or rejected; 6 right-hand-side evaluations for RKCK45, 4 for RK4) of one instance (for the
+coupled module: of one whole system of 64 units).
 
 Timed regions (all after W >= 3 warm-up steps):
   value : inputs resident in HBM; each step restores the initial condition device-to-device and
-          launches the phase; CUDA events on the solver's stream, barrier + synchronize on both
+          launches the phase(s); CUDA events on the solver's stream, barrier + synchronize on both
           sides, max over ranks.
-  e2e   : the same K steps through the public API with HOST buffers: every step uploads the
-          inputs from pinned host memory, integrates, and downloads state + time; host wall
+  e2e   : the same K steps through the public API with HOST buffers: every step uploads the inputs
+          from pinned host memory, integrates, and downloads state + time.  The sweep is driven as
+          ``--e2e-chunks`` solver objects with their own streams so that copies overlap kernels --
+          the double-buffering pattern of the reference's own tutorial
+          (Tutorials_SingleSystem_PerThread/T7_DoubleBuffering/DoubleBuffering.cu:89-144); host wall
           clock between synchronisation points, max over ranks.
-Multi-GPU: one process per GPU (torchrun); instances are independent, so each rank integrates its
-own 2^20-instance tile-cyclic shard of a (N x 2^20)-instance sweep with no collective on the data
-path (weak scaling); torch.distributed/NCCL only carries the barrier and the reduction of the
-timings.
+Multi-GPU: one process per GPU (torchrun); instances are independent, so each rank integrates its own
+tile-cyclic shard of a (N x per-GPU)-instance sweep with no collective on the data path (weak
+scaling); torch.distributed/NCCL only carries the barrier and the reduction of the timings.
 """
 from __future__ import annotations
 
@@ -41,18 +46,40 @@ sys.path.insert(0, ROOT)
 
 FLOPS_NOTE = "algorithmic flops per system-step, SURVEY.md 8(d): add/sub/mul/div/sqrt = 1, FMA = 2, transcendentals 0"
 
+# name -> (module kind, BASELINE config, instances (systems) per GPU, flops per system-step, algorithm label)
+WORKLOADS = {
+    "lorenz":             ("perthread", "configs[1] T2_Lorenz rho-sweep", 1 << 20, 236, "RKCK45"),
+    "lorenz_rk4":         ("perthread", "T2_Lorenz as shipped (RK4, dt=1e-3)", 1 << 20, 79, "RK4"),
+    "impact":             ("perthread", "configs[2] T6_ImpactDynamics", 1 << 20, 230, "RKCK45"),
+    "kellermiksis":       ("perthread", "configs[3] T5 Keller-Miksis without dense output", 1 << 18, 413, "RKCK45"),
+    "kellermiksis_dense": ("perthread", "configs[3] T5 Keller-Miksis + dense output (200 points)", 1 << 18, 413, "RKCK45"),
+    "duffing":            ("perthread", "configs[0] T1_Reference Duffing, RK4", 10000, 58, "RK4"),
+    "coupled":            ("coupled", "configs[4] T2_BubbleEnsemble, 64 units, dense coupling matrix", 8192, 78857, "RKCK45"),
+}
+COUPLED_TILE = 64
 
-def build_workload(W, name: str, precision: str, NT: int, rank: int, world: int):
-    """This rank's shard: tile-cyclic slices (4096 instances) of the global (world x NT) sweep."""
+
+def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int):
+    """This rank's shard: tile-cyclic slices of the global (world x n)-instance sweep."""
+    W = pkg.workloads
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    if name == "coupled":
+        full = pkg.workloads_coupled.bubble_ensemble(NS=n * world, UPS=64)
+        if world > 1:
+            import copy
+            wl = copy.copy(full)
+            wl.buffers = full.buffers.take(sharding.shard_indices(n, rank, world, COUPLED_TILE))
+            return wl
+        return full
     dtype = np.float64 if precision == "f64" else np.float32
-    gen = {"lorenz": lambda n: W.lorenz(NT=n, algorithm=W.RKCK45, dtype=dtype),
-           "lorenz_rk4": lambda n: W.lorenz(NT=n, algorithm=W.RK4, dtype=dtype),
-           "impact": lambda n: W.impact_t6(NT=n),
-           "kellermiksis": lambda n: W.keller_miksis_t5(NT=n, ndo=0),
-           "kellermiksis_dense": lambda n: W.keller_miksis_t5(NT=n, ndo=200),
-           "duffing": lambda n: W.duffing_t1(NT=n, algorithm=W.RK4)}[name]
-    sharding = importlib.import_module("massively-parallel-gpu-ode-solver_b200.sharding")
-    return sharding.shard_workload(gen(NT * world), NT, rank, world)
+    gen = {"lorenz": lambda m: W.lorenz(NT=m, algorithm=W.RKCK45, dtype=dtype),
+           "lorenz_rk4": lambda m: W.lorenz(NT=m, algorithm=W.RK4, dtype=dtype),
+           "impact": lambda m: W.impact_t6(NT=m),
+           "kellermiksis": lambda m: W.keller_miksis_t5(NT=m, ndo=0),
+           "kellermiksis_dense": lambda m: W.keller_miksis_t5(NT=m, ndo=200),
+           "duffing": lambda m: W.duffing_t1(NT=m, algorithm=W.RK4)}[name]
+    tile = sharding.TILE if n % sharding.TILE == 0 else 1
+    return sharding.shard_workload(gen(n * world), n, rank, world, tile)
 
 
 class ClockSampler:
@@ -62,7 +89,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -95,25 +122,108 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(W, name: str, precision: str, sample: int, threads: int):
-    """The reference's own kernel source compiled for the host (oracle/_ref, kind "reference"), or
-    our CPU restatement of it when that library is absent (kind "port"), over every k-th instance
-    of the sweep, on `threads` host threads.  Returns (system-steps, seconds, kind)."""
+def cpu_reference_run(pkg, name: str, precision: str, sample: int, threads: int, phases: int):
+    """The reference's own kernel source compiled for the host (oracle/_ref, kind "reference"), or our
+    CPU restatement of it when that library is absent / for the coupled module (kind "port"), over every
+    k-th instance of the sweep, on `threads` host threads.  Returns (system-steps, seconds, kind, instances)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py
+    n_full = WORKLOADS[name][2]
+    full = build_workload(pkg, name, precision, n_full, 0, 1)
+    if name == "coupled":
+        import copy
+        idx = np.unique(np.linspace(0, n_full - 1, sample).round().astype(np.int64))
+        wl = copy.copy(full)
+        wl.buffers = full.buffers.take(idx)
+        if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_coupled_fast.so")):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_coupled_fast.so"], check=True, capture_output=True)
+        t0 = time.perf_counter()
+        _, att, _ = oracle_py.run_coupled_oracle(wl, phases=phases, host_threads=threads, fast=True)
+        return int(att.sum()), time.perf_counter() - t0, "port", int(idx.size)
     from cases import subsample
-    full = build_workload(W, name, precision, 1 << 20 if "keller" not in name else 1 << 18, 0, 1)
     wl = subsample(full, sample)
     if oracle_py.ref_available(wl, fast=True):
-        run, kind = (lambda: oracle_py.run_ref(wl, phases=1, host_threads=threads, fast=True)), "reference"
+        run, kind = (lambda: oracle_py.run_ref(wl, phases=phases, host_threads=threads, fast=True)), "reference"
     else:
         if not os.path.exists(oracle_py.oracle_library_path(fast=True)):
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle_perthread_fast.so"], check=True, capture_output=True)
-        run, kind = (lambda: oracle_py.run_oracle(wl, phases=1, host_threads=threads, fast=True, double_literals=True)), "port"
+        run, kind = (lambda: oracle_py.run_oracle(wl, phases=phases, host_threads=threads, fast=True, double_literals=True)), "port"
     t0 = time.perf_counter()
     _, att, _ = run()
     return int(att.sum()), time.perf_counter() - t0, kind, wl.NT
+
+
+class Arm:
+    """One solver object of either module behind a common face (what bench needs of the public API)."""
+
+    def __init__(self, pkg, wl, kind: str, device: int, args):
+        self.pkg, self.wl, self.kind = pkg, wl, kind
+        sh = wl.shape
+        if kind == "coupled":
+            self.V = pkg.CoupledVariables
+            self.ps = pkg.CoupledProblemSolver(wl.name, wl.buffers.NS, sh.UPS, CBW=sh.CBW, CCI=sh.CCI, NDO=sh.NDO, Algorithm=sh.Algorithm, Device=device,
+                                               TPB=sh.TPB, SPB=sh.SPB)
+            pkg.apply_coupled_workload(self.ps, wl)
+            if args.tensor_core_coupling >= 0:
+                self.ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, args.tensor_core_coupling)
+            self.in_vars = [self.V.TimeDomain, self.V.ActualState, self.V.ActualTime, self.V.UnitParameters, self.V.CouplingStrength]
+            self.out_vars = [self.V.ActualState, self.V.ActualTime]
+        else:
+            self.V = pkg.Variables
+            self.ps = pkg.ProblemSolver(wl.name, wl.NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=device)
+            pkg.apply_workload(self.ps, wl)
+            if args.lane_refill >= 0:
+                self.ps.SolverOption(pkg.Options.LaneRefill, args.lane_refill)
+            if args.threads_per_block:
+                self.ps.SolverOption(pkg.Options.ThreadsPerBlock, args.threads_per_block)
+            V = self.V
+            self.in_vars = [V.TimeDomain, V.ActualState, V.ActualTime, V.ControlParameters, V.SharedParameters, V.Accessories, V.IntegerAccessories, V.DenseIndex]
+            self.out_vars = [V.ActualState, V.ActualTime, V.Accessories, V.IntegerAccessories]
+        self.ps.SynchroniseFromHostToDevice(self.V.All)
+        self.ps.SynchroniseDevice()
+
+    def total_steps(self):
+        att, acc = self.ps.StepCounters()
+        return int(att.sum()), int(acc.sum())
+
+    # ---- e2e: caller-owned pinned host arrays -> device -> caller-owned pinned host arrays ------------
+    def make_host_buffers(self, torch):
+        self.user_in = {v: torch.from_numpy(np.ascontiguousarray(self.ps.host(v)).copy()).pin_memory() for v in self.in_vars if self.ps.host(v).size}
+        self.user_out = {v: torch.empty_like(torch.from_numpy(np.ascontiguousarray(self.ps.host(v)).copy())).pin_memory() for v in self.out_vars if self.ps.host(v).size}
+        h2d = sum(t.numel() * t.element_size() for t in self.user_in.values())
+        d2h = sum(t.numel() * t.element_size() for t in self.user_out.values())
+        return h2d, d2h
+
+    def enqueue_e2e(self, phases: int):
+        ps = self.ps
+        if self.kind == "coupled":
+            # the reference's flow: fill the solver's pinned mirrors (SetHost), SynchroniseFromHostToDevice, Solve,
+            # SynchroniseFromDeviceToHost, read the mirrors (GetHost)
+            for v, t in self.user_in.items():
+                np.copyto(ps.host(v), t.numpy().reshape(ps.host(v).shape))
+                ps.SynchroniseFromHostToDevice(v)
+            for _ in range(phases):
+                ps.Solve()
+            for v in self.user_out:
+                ps.SynchroniseFromDeviceToHost(v)
+        else:
+            for v, t in self.user_in.items():
+                ps.Upload(v, t.data_ptr(), t.numel() * t.element_size())
+            for _ in range(phases):
+                ps.Solve()
+            for v, t in self.user_out.items():
+                ps.Download(v, t.data_ptr(), t.numel() * t.element_size())
+        ps.InsertSynchronisationPoint()
+
+    def finish_e2e(self):
+        self.ps.SynchroniseSolver()
+        if self.kind == "coupled":
+            for v, t in self.user_out.items():
+                np.copyto(t.numpy().reshape(self.ps.host(v).shape), self.ps.host(v))
+
+    def close(self):
+        self.ps.close()
 
 
 def main():
@@ -122,11 +232,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="lorenz")
+    ap.add_argument("--workload", default="lorenz", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--instances", type=int, default=0, help="instances per GPU (default: the BASELINE size)")
+    ap.add_argument("--instances", type=int, default=0, help="instances (systems) per GPU (default: the BASELINE size)")
+    ap.add_argument("--phases", type=int, default=1, help="integration phases (Solve() calls) per step")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="solver objects the e2e sweep is double-buffered over")
     ap.add_argument("--lane-refill", type=int, default=-1)
     ap.add_argument("--threads-per-block", type=int, default=0)
+    ap.add_argument("--tensor-core-coupling", type=int, default=-1)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
@@ -137,14 +250,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     pkg = importlib.import_module("massively-parallel-gpu-ode-solver_b200")
-    W = pkg.workloads
-    NT = args.instances or ((1 << 18) if "keller" in args.workload else (1 << 20))
-    flops_per_step = {"lorenz": 236, "lorenz_rk4": 79, "impact": 230, "kellermiksis": 413, "kellermiksis_dense": 413, "duffing": 58}[args.workload]
-    metric = "system-steps/sec (%s %s)" % ("FP64" if args.precision == "f64" else "FP32", "RK4" if args.workload in ("lorenz_rk4", "duffing") else "RKCK45")
-    config = {"workload": f"{args.workload}: {NT} instances per GPU x {world} GPU(s), one integration phase per step "
-                          f"(BASELINE configs[1] T2_Lorenz rho-sweep)" if args.workload == "lorenz" else f"{args.workload}: {NT} instances per GPU x {world}",
-              "instances_per_gpu": NT, "sharding": "tile-cyclic (4096), no collective on the data path",
-              "l2": "inputs + outputs per step exceed nothing cached: state is restored device-to-device from a snapshot before every step; kernel is FMA-pipe bound, HBM traffic < 1% of time",
+    kind, cfg_name, n_default, flops_per_step, alg = WORKLOADS[args.workload]
+    N = args.instances or n_default
+    unit = "systems" if kind == "coupled" else "instances"
+    metric = "system-steps/sec (%s %s)" % ("FP64" if args.precision == "f64" else "FP32", alg)
+    config = {"workload": f"{args.workload}: {N} {unit} per GPU x {world} GPU(s), {args.phases} integration phase(s) per step (BASELINE {cfg_name})",
+              f"{unit}_per_gpu": N, "phases_per_step": args.phases,
+              "sharding": "tile-cyclic, no collective on the data path",
+              "l2": "state is restored device-to-device from a snapshot before every step; the kernel is FP64-pipe bound, its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
               "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
 
     # ------------------------------------------------------------------ reference arm (CPU) ------
@@ -152,20 +265,21 @@ def main():
         if rank != 0:
             return
         threads = os.cpu_count() or 1
-        sample = args.cpu_sample or (1 << 16)
+        sample = args.cpu_sample or {"coupled": 256, "kellermiksis": 1 << 14, "kellermiksis_dense": 1 << 14, "duffing": 10000}.get(args.workload, 1 << 16)
+        sample = min(sample, N)
         for _ in range(args.warmup):
-            cpu_reference_run(W, args.workload, args.precision, max(sample // 8, 256), threads)
-        steps_total, secs, kind = 0, 0.0, "reference"
+            cpu_reference_run(pkg, args.workload, args.precision, max(sample // 8, 32), threads, args.phases)
+        steps_total, secs, kind_cpu, nt = 0, 0.0, "reference", sample
         for _ in range(args.steps):
-            n, s, kind, nt = cpu_reference_run(W, args.workload, args.precision, sample, threads)
+            n, s, kind_cpu, nt = cpu_reference_run(pkg, args.workload, args.precision, sample, threads, args.phases)
             steps_total += n
             secs += s
         v = steps_total / secs
         print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "system-steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "system-steps/s", "cores": threads, "kind": kind,
-                                           "sample": f"every {max(NT // sample, 1)}-th instance of the sweep ({sample} instances) per step, {threads} host threads"},
+                          "cpu_baseline": {"value": v, "unit": "system-steps/s", "cores": threads, "kind": kind_cpu,
+                                           "sample": f"every {max(N // nt, 1)}-th {unit[:-1]} of the sweep ({nt} {unit}) per step, {threads} host threads"},
                           "e2e": {"value": v, "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
         return
@@ -183,24 +297,16 @@ def main():
         if world > 1:
             dist.barrier()
 
-    wl = build_workload(W, args.workload, args.precision, NT, rank, world)
-    sh = wl.shape
-    ps = pkg.ProblemSolver(wl.name, NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=local_rank)
-    pkg.apply_workload(ps, wl)
-    if args.lane_refill >= 0:
-        ps.SolverOption(pkg.Options.LaneRefill, args.lane_refill)
-    if args.threads_per_block:
-        ps.SolverOption(pkg.Options.ThreadsPerBlock, args.threads_per_block)
-    ps.SynchroniseFromHostToDevice(pkg.Variables.All)
+    wl = build_workload(pkg, args.workload, args.precision, N, rank, world)
+    arm = Arm(pkg, wl, kind, local_rank, args)
+    ps = arm.ps
     ps.SaveState()
     stream = torch.cuda.ExternalStream(ps.stream, device=local_rank)
 
-    def step_device():
-        ps.RestoreState()
-        ps.Solve()
-
     for _ in range(args.warmup):
-        step_device()
+        ps.RestoreState()
+        for _ in range(args.phases):
+            ps.Solve()
     ps.SynchroniseDevice()
     ps.ResetStepCounters()
 
@@ -214,56 +320,58 @@ def main():
     for k in range(args.steps):
         ps.RestoreState()
         ev[2 + 2 * k].record(stream)
-        ps.Solve()
+        for _ in range(args.phases):
+            ps.Solve()
         ev[3 + 2 * k].record(stream)
     ev[1].record(stream)
     torch.cuda.synchronize(); barrier()
     t_host1 = time.time()
     clocks = sampler.stop(t_host0, t_host1)
     region_ms = ev[0].elapsed_time(ev[1])
-    kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps)]
-    attempted, accepted = ps.TotalSteps()
+    kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) / args.phases for k in range(args.steps)]
+    attempted, accepted = arm.total_steps()
 
-    # ---- e2e: host buffers through the public API ------------------------------------------------
-    V = pkg.Variables
-    in_vars = [V.TimeDomain, V.ActualState, V.ActualTime, V.ControlParameters, V.SharedParameters, V.Accessories, V.IntegerAccessories, V.DenseIndex]
-    out_vars = [V.ActualState, V.ActualTime, V.Accessories, V.IntegerAccessories]
-    pinned_in, pinned_out = {}, {}
-    for v in in_vars:
-        a = ps.host(v)
-        if a.size:
-            t = torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory()
-            pinned_in[v] = t
-    for v in out_vars:
-        a = ps.host(v)
-        if a.size:
-            pinned_out[v] = torch.empty_like(torch.from_numpy(np.ascontiguousarray(a).copy())).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in pinned_in.values())
-    d2h = sum(t.numel() * t.element_size() for t in pinned_out.values())
+    # ---- e2e: host buffers through the public API, double-buffered over `chunks` solver objects ----
+    chunks = max(1, args.e2e_chunks)
+    while N % chunks or (kind == "perthread" and N // chunks < 1):
+        chunks -= 1
+    if chunks == 1:
+        e2e_arms = [arm]
+    else:
+        import copy
+        sharding = importlib.import_module(pkg.__name__ + ".sharding")
+        e2e_arms = []
+        for c in range(chunks):
+            w = copy.copy(wl)
+            w.buffers = wl.buffers.take(sharding.shard_indices(N // chunks, c, chunks, 1))
+            e2e_arms.append(Arm(pkg, w, kind, local_rank, args))
+    h2d = d2h = 0
+    for a in e2e_arms:
+        hi, do = a.make_host_buffers(torch)
+        h2d += hi
+        d2h += do
 
     def step_e2e():
-        for v, t in pinned_in.items():
-            ps.Upload(v, t.data_ptr(), t.numel() * t.element_size())
-        ps.Solve()
-        for v, t in pinned_out.items():
-            ps.Download(v, t.data_ptr(), t.numel() * t.element_size())
-        ps.InsertSynchronisationPoint()
-        ps.SynchroniseSolver()
+        for a in e2e_arms:
+            a.enqueue_e2e(args.phases)
+        for a in e2e_arms:
+            a.finish_e2e()
 
     for _ in range(2):
         step_e2e()
-    ps.ResetStepCounters()
+    for a in e2e_arms:
+        a.ps.ResetStepCounters()
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize(); barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_attempted, _ = ps.TotalSteps()
-    final_state_checksum = float(pinned_out[V.ActualState].double().sum())
+    e2e_attempted = sum(a.total_steps()[0] for a in e2e_arms)
+    final_state_checksum = float(sum(a.user_out[a.V.ActualState].double().sum() for a in e2e_arms))
 
     # ---- reduce over ranks -------------------------------------------------------------------------
-    sharding = importlib.import_module("massively-parallel-gpu-ode-solver_b200.sharding")
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
     (region_ms, e2e_s, kmean), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms))],
                                                                    [attempted, accepted, e2e_attempted], device="cuda")
     attempted, accepted, e2e_attempted = [int(x) for x in counts]
@@ -272,7 +380,7 @@ def main():
         value = attempted / (region_ms * 1e-3)
         precision_bytes = 8 if args.precision == "f64" else 4
         peak_tf = pkg.probe_fma_peak(local_rank, precision_bytes)
-        per_rank_attempted_per_launch = attempted / world / args.steps
+        per_rank_attempted_per_launch = attempted / world / args.steps / args.phases
         achieved_tf = per_rank_attempted_per_launch * flops_per_step / (kmean * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -288,28 +396,43 @@ def main():
                             "peak_source": "measured on this GPU by mpgos_probe_fma_peak (register-resident FMA chains, CUDA events); MEASURED_PEAKS.json carries no FP64/FP32 FMA figure",
                             "kernel_ms": kmean, "algorithmic_flops_per_launch": per_rank_attempted_per_launch * flops_per_step},
                "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e2e_s / args.steps * 1e3, "state_checksum": final_state_checksum},
-               "gpu_launches": args.steps, "clocks": clocks}
+                       "ms_per_step": e2e_s / args.steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
+               "gpu_launches": args.steps * args.phases, "clocks": clocks}
         if world == 1 and not args.no_reference_gpu:
             # reported baseline, not a target: the reference MPGOS compiled for sm_100a, same inputs, same event bracket
             try:
                 sys.path.insert(0, os.path.join(ROOT, "oracle"))
                 import oracle_py
-                if oracle_py.ref_gpu_available(wl):
-                    _, ref_ms = oracle_py.run_ref_gpu(wl, phases=1, threads_per_block=64, repeats=3)
+                ref_ms = None
+                if kind == "coupled":
+                    tag = "bubble_ensemble_u64_s2"
+                    if N == 8192 and os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
+                        _, ref_ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=args.phases, shared_matrices=1, repeats=3)
+                        what = "reference MPGOS CoupledSystems_PerBlock kernel (TPB 128, SPB 2, SharedCouplingMatrices 1: its fastest setting here) compiled unmodified by nvcc for sm_100a"
+                elif oracle_py.ref_gpu_available(wl):
+                    _, ref_ms = oracle_py.run_ref_gpu(wl, phases=args.phases, threads_per_block=64, repeats=3)
+                    what = "reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a, 64 threads/block"
+                if ref_ms is not None:
+                    ref_ms /= args.phases
                     out["reference_gpu"] = {"kernel_ms": ref_ms, "value": per_rank_attempted_per_launch / (ref_ms * 1e-3), "unit": "system-steps/s",
                                             "speedup_kernel": ref_ms / kmean,
-                                            "what": "reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a (oracle/_ref), 64 threads/block, best of 3, same inputs; step count taken from our counters"}
+                                            "what": what + " (oracle/_ref), best of 3, same inputs; step count taken from our counters"}
             except Exception as e:   # the baseline must never break the bench line
                 out["reference_gpu"] = {"unavailable": str(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sample = args.cpu_sample or (1 << 19 if threads >= 16 else 1 << 17)
-            n, s, kind, nt = cpu_reference_run(W, args.workload, args.precision, sample, threads)
-            out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind,
-                                   "sample": f"every {max(NT // nt, 1)}-th instance of the sweep ({nt} instances), one phase, {threads} host threads, {s:.1f} s"}
+            big = threads >= 16
+            sample = args.cpu_sample or {"coupled": 512 if big else 128, "kellermiksis": 1 << 15, "kellermiksis_dense": 1 << 15,
+                                         "duffing": 10000, "impact": 1 << 17 if big else 1 << 15}.get(args.workload, 1 << 19 if big else 1 << 17)
+            sample = min(sample, N)
+            n, s, kind_cpu, nt = cpu_reference_run(pkg, args.workload, args.precision, sample, threads, args.phases)
+            out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind_cpu,
+                                   "sample": f"every {max(N // nt, 1)}-th {unit[:-1]} of the sweep ({nt} {unit}), {args.phases} phase(s), {threads} host threads, {s:.1f} s"}
         print(json.dumps(out))
-    ps.close()
+    for a in e2e_arms:
+        if a is not arm:
+            a.close()
+    arm.close()
     if world > 1:
         dist.destroy_process_group()
 
