@@ -247,3 +247,35 @@ def duffing_ring(NS: int = 9, CBW: int = 1, CCI: int = 1, algorithm: int = RKCK4
     opt = CoupledOptions(InitialTimeStep=1e-2, RelativeTolerance=np.array([1e-8, 1e-8]), AbsoluteTolerance=np.array([1e-8, 1e-8]),
                          EventDirection=np.array([-1], np.int32), DenseOutputMinimumTimeStep=1e-6)
     return CoupledWorkload("duffing_ring", sh, opt, b, phases, 0, "T1_RingOfDuffingOscillators")
+
+
+def swing_ring(NS: int = 37, phases: int = 2, t_end: float = 30.0) -> CoupledWorkload:
+    """examples/swing_ring: the user-defined coupled system of the drop-in example (ring of second-order phase
+    oscillators, two couplings through a banded wrap-around matrix, one event per unit, the third local maximum of
+    unit 0 ends a phase, Finalization moves the time domain).  Same inputs as examples/swing_ring/swing_ring_dropin.cu
+    receives from the test."""
+    UPS, CBW = 40, 2
+    sh = CoupledShape(UPS=UPS, UD=2, NC=2, CBW=CBW, CCI=0, NUP=2, NSP=1, NGP=1, NiGP=1, NUA=1, NiUA=1, NSA=1, NiSA=1, NE=1, NDO=32,
+                      Algorithm=RKCK45, TPB=64, SPB=1)
+    b = CoupledBuffers(sh, NS)
+    u = np.arange(UPS)
+    b.TimeDomain[1, :] = t_end
+    b.UnitParameters[0] = (0.4 * np.sin(2.0 * np.pi * u / UPS + 1.0))[None, :]
+    b.UnitParameters[1] = (0.25 + 0.1 * np.cos(2.0 * np.pi * u / UPS))[None, :]
+    gain = _linspace(0.6, 3.0, NS)
+    b.CouplingStrength[0], b.CouplingStrength[1] = gain, gain
+    b.ActualState[0] = 0.8 * np.cos(2.0 * np.pi * u / UPS)[None, :] * (1.0 + np.arange(NS)[:, None] / NS)
+    b.GlobalParameters[0] = 1.3
+    b.IntegerGlobalParameters[0] = 1
+    b.CouplingIndex[:] = (1, 1)
+    A = np.zeros((2, UPS, UPS))
+    for r in range(UPS):
+        for d in range(-CBW, CBW + 1):
+            if d != 0:
+                A[0, r, (r + d) % UPS] = 1.0 / (1.0 + abs(d))
+                A[1, r, (r + d) % UPS] = (1.0 + 0.05 * d) / (1.0 + abs(d))
+    b.CouplingMatrix[0] = A[0].T
+    b.CouplingMatrix[1] = A[1].T
+    opt = CoupledOptions(InitialTimeStep=1e-3, RelativeTolerance=np.array([1e-9, 1e-9]), AbsoluteTolerance=np.array([1e-9, 1e-9]),
+                         EventTolerance=np.array([1e-7]), EventDirection=np.array([-1], np.int32), DenseOutputMinimumTimeStep=0.05)
+    return CoupledWorkload("swing_ring", sh, opt, b, phases, 0, "examples/swing_ring")

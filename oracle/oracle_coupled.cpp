@@ -141,6 +141,7 @@ int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo,
 		if (cbw == 0 && cci == 1) return dispatch<DuffingRing<double, 14, 0, 1> >(algorithm, ndo, b, o, shape);
 		if (cbw == 0 && cci == 0) return dispatch<DuffingRing<double, 14, 0, 0> >(algorithm, ndo, b, o, shape);
 	}
+	if (!std::strcmp(system, "swing_ring") && ups == 40 && cbw == 2 && cci == 0) return dispatch<SwingRing<double, 40, 2, 0> >(algorithm, ndo, b, o, shape);
 	return 1;
 }
 } // namespace

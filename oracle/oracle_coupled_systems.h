@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- CPU restatement of the coupled tutorial system definitions.
 //   BubbleEnsemble : Tutorials_CoupledSystems_PerBlock/T2_BubbleEnsemble/BubbleEnsemble_SystemDefinition.cuh:7-95
 //   DuffingRing    : Tutorials_CoupledSystems_PerBlock/T1_RingOfDuffingOscillators/RingOfDuffingOscillators_SystemDefinition.cuh:7-105
+//   SwingRing      : examples/swing_ring/SwingRing_SystemDefinition.cuh (the user-defined system of the coupled drop-in example)
 // Static members with the argument meaning of the reference's CoupledSystems_PerBlock_* callbacks.
 #ifndef MPGOS_B200_ORACLE_COUPLED_SYSTEMS_H
 #define MPGOS_B200_ORACLE_COUPLED_SYSTEMS_H
@@ -87,6 +88,45 @@ struct DuffingRing
 		iuACC[0] = 0;
 	}
 	static void finalization(OC_INIT_ARGS) {}
+};
+
+// examples/swing_ring/SwingRing_SystemDefinition.cuh -- the user-defined system of the coupled drop-in example
+template <class P, int UPS_, int CBW_, int CCI_>
+struct SwingRing
+{
+	enum { UPS = UPS_, UD = 2, NC = 2, CBW = CBW_, CCI = CCI_, NUP = 2, NSP = 1, NGP = 1, NiGP = 1, NUA = 1, NiUA = 1, NSA = 1, NiSA = 1, NE = 1 };
+	static void ode_function(OC_ODE_ARGS)
+	{
+		const P rm = 1.0 / gPAR[0];
+		const P a = igPAR[0] * X[0];
+		const P s = std::sin(a);
+		const P c = std::cos(a);
+		F[0] = X[1];
+		F[1] = (uPAR[0] + sPAR[0] - uPAR[1] * X[1]) * rm;
+		CPT[0] = s;  CPF[0] = c * rm;
+		CPT[1] = c;  CPF[1] = -s * rm;
+	}
+	static void event_function(OC_EV_ARGS) { EF[0] = X[1]; }
+	static void action_after_event_detection(OC_EVACT_ARGS)
+	{
+		iuACC[0]++;
+		if (uid == 0 && iuACC[0] == 3) UDT = 1;
+	}
+	static void action_after_successful_time_step(OC_STEP_ARGS)
+	{
+		if (std::fabs(X[1]) > uACC[0]) uACC[0] = std::fabs(X[1]);
+		if (uid == 0) { isACC[0]++; sACC[0] += dT; }
+	}
+	static void initialization(OC_INIT_ARGS)
+	{
+		if (uid == 0) { T = TD[0]; DOIDX = 0; isACC[0] = 0; sACC[0] = 0.0; }
+		uACC[0] = std::fabs(X[1]);
+		iuACC[0] = 0;
+	}
+	static void finalization(OC_INIT_ARGS)
+	{
+		if (uid == 0) { const P span = TD[1] - TD[0]; TD[0] = T; TD[1] = T + span; }
+	}
 };
 
 } // namespace oracle_coupled

@@ -73,3 +73,77 @@ def test_user_defined_system_through_the_dropin_header(algorithm, workloads, ora
         assert header in dense
     series = dense.split("Time series:\n")[1].strip().split("\n")
     assert len(series) == int(out["didx"][7]) and len(series[0].split(",")) == 3
+
+
+# ---- the coupled module through its drop-in header ----------------------------------------------------------------
+
+SWING_LIB = os.path.join(ROOT, "examples", "swing_ring", "libswing_ring_dropin.so")
+
+
+def test_user_defined_coupled_system_through_the_dropin_header(pkg, oracle):
+    """examples/swing_ring: a user program against include/CoupledSystems_PerBlock_Interface.cuh (all six SetHost /
+    GetHost overloads, banded wrap-around coupling matrices through SetHost(k, CouplingMatrix, row, col, v), two
+    couplings, unit / system / global / integer-global scopes, events with user-defined termination, dense output,
+    Finalization that moves the time domain, Print formats).  Its system is not built into the library.  Checked
+    against the CPU restatement of the reference's coupled algorithm."""
+    import importlib
+    if not os.path.exists(SWING_LIB):
+        pytest.fail("examples/swing_ring/libswing_ring_dropin.so missing: run __graft_entry__.build()")
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.swing_ring()
+    sh, b = wl.shape, wl.buffers
+    NS, UPS, UD, NDO = b.NS, sh.UPS, sh.UD, sh.NDO
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=wl.phases, host_threads=8)
+
+    lib = C.CDLL(SWING_LIB)
+    shape = (C.c_int * 16)()
+    lib.swing_ring_shape(shape)
+    assert list(shape) == [NS, UPS, UD, sh.NC, sh.CBW, sh.CCI, sh.NUP, sh.NSP, sh.NGP, sh.NiGP, sh.NUA, sh.NiUA, sh.NSA, sh.NiSA, sh.NE, NDO]
+    out = dict(state=np.zeros((UD, NS, UPS)), time=np.zeros(NS), td=np.zeros((2, NS)), uacc=np.zeros((NS, UPS)), iuacc=np.zeros((NS, UPS), np.int32),
+               sacc=np.zeros(NS), isacc=np.zeros(NS, np.int32), didx=np.zeros(NS, np.int32), dtime=np.zeros((NDO, NS)),
+               dstate=np.zeros((NDO, UD, NS, UPS)), att=np.zeros(NS, np.uint64), acc=np.zeros(NS, np.uint64))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    omega = np.ascontiguousarray(b.UnitParameters[0, 0]); damping = np.ascontiguousarray(b.UnitParameters[1, 0])
+    gain = np.ascontiguousarray(b.CouplingStrength[0]); theta0 = np.ascontiguousarray(b.ActualState[0])
+    matrix = np.ascontiguousarray(np.transpose(b.CouplingMatrix, (0, 2, 1)))     # [k][row][col]
+    lib.swing_ring_run.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_int, C.c_double] + [C.c_void_p] * 12
+    cwd = os.getcwd()
+    os.chdir(os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "/tmp")
+    try:
+        rc = lib.swing_ring_run(wl.phases, p(omega), p(damping), p(gain), p(theta0), p(matrix), float(b.GlobalParameters[0]), int(b.IntegerGlobalParameters[0]),
+                                float(b.TimeDomain[1, 0]), p(out["state"]), p(out["time"]), p(out["td"]), p(out["uacc"]), p(out["iuacc"]), p(out["sacc"]),
+                                p(out["isacc"]), p(out["didx"]), p(out["dtime"]), p(out["dstate"]), p(out["att"]), p(out["acc"]))
+        files = {f: open(f).read() for f in ("ActualStateInSolverObject.txt", "CouplingStrengthInSolverObject.txt", "CouplingMatrixInSolverObject_0.txt",
+                                             "DenseOutput_5.txt") if os.path.exists(f)}
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    assert np.array_equal(out["iuacc"], ref.IntegerUnitAccessories[0])                 # event counts of every unit
+    assert (out["iuacc"][:, 0] == 3).any() and (out["iuacc"][:, 0] < 3).any()          # some phases end by the user-defined termination, others at TD[1]
+    assert np.abs(out["att"].astype(np.int64) - ratt).max() <= 3 and np.abs(out["isacc"] - ref.IntegerSystemAccessories[0]).max() <= 3
+    assert rel_err(out["time"], ref.ActualTime).max() < 1e-6                           # event-terminated phases (secant refinement to 1e-7)
+    assert rel_err(out["td"], ref.TimeDomain).max() < 1e-6                             # moved by Finalization
+    assert rel_err(out["sacc"], ref.SystemAccessories[0]).max() < 1e-6
+    assert rel_err(out["state"], ref.ActualState).max() < 1e-5
+    # max |v| over the ACCEPTED steps: a sampled maximum, it moves with the step sequence (median agreement 1e-13)
+    assert rel_err(out["uacc"], ref.UnitAccessories[0]).max() < 1e-3 and np.median(rel_err(out["uacc"], ref.UnitAccessories[0])) < 1e-9
+    same = out["didx"] == ref.DenseIndex
+    assert same.mean() > 0.9
+    n = int(min(out["didx"].min(), ref.DenseIndex.min())) - 1
+    cols = np.where(same)[0]
+    # stored points sit on accepted steps; after an event the step sequences agree to the event tolerance (1e-7 in v)
+    assert rel_err(out["dtime"][:n][:, cols], ref.DenseTime[:n][:, cols]).max() < 1e-5
+    assert rel_err(out["dstate"][:n][:, :, cols], ref.DenseState[:n][:, :, cols]).max() < 1e-3
+    assert np.median(rel_err(out["dstate"][:n][:, :, cols], ref.DenseState[:n][:, :, cols])) < 1e-9
+    # Print(): the reference's formats -- unit scope: one row per logical thread INCLUDING its per-block padding rows
+    rows = files["ActualStateInSolverObject.txt"].rstrip("\n").split("\n")
+    assert len(rows) == NS * 64 and rows[40].count("PADDING") == UD and len(rows[0].split(",")[0]) == 18
+    assert abs(float(rows[64 * 3 + 7].split(",")[1]) - out["state"][1, 3, 7]) < 1e-9 * max(1.0, abs(out["state"][1, 3, 7]))
+    rows = files["CouplingMatrixInSolverObject_0.txt"].rstrip("\n").split("\n")
+    assert len(rows) == UPS and abs(float(rows[5].split(",")[6]) - matrix[0, 5, 6]) < 1e-12 and float(rows[5].split(",")[20]) == 0.0
+    dense = files["DenseOutput_5.txt"]
+    for header in ("UnitParameters:", "UnitAccessories:", "IntegerUnitAccessories:", "SystemParameters:", "SystemAccessories:",
+                   "IntegerSystemAccessories:", "GlobalParameters:", "IntegerGlobalParameters:", "Time series:"):
+        assert header in dense
+    series = dense.split("Time series:\n")[1].strip().split("\n")
+    assert len(series) == 1 + int(out["didx"][5]) and len(series[1].split(",")) == 1 + UPS * UD

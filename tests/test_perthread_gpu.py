@@ -222,6 +222,8 @@ def test_rk4_is_bit_identical_to_reference_mpgos_on_the_same_gpu(name, cases, pk
     for refill in (0, 1):
         out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
         for f in RESULT_FIELDS:
+            if f == "DenseIndex" and wl.shape.NDO == 0:
+                continue      # without dense output the reference never initialises this buffer (it reads and writes back cudaMalloc garbage)
             a, b = getattr(out, f), getattr(ref, f)
             if f in ("DenseTime", "DenseState"):     # slots beyond the dense index are never written by either
                 n = int(ref.DenseIndex.min()) if ref.DenseIndex.size else 0
