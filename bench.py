@@ -330,6 +330,12 @@ def main():
     region_ms = ev[0].elapsed_time(ev[1])
     kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) / args.phases for k in range(args.steps)]
     attempted, accepted = arm.total_steps()
+    dense_samples = None
+    if kind == "perthread" and wl.shape.NDO > 0:
+        # points stored by the last phase (the built-in dense systems restart the index every phase) x phases per step
+        ps.SynchroniseFromDeviceToHost(arm.V.DenseIndex)
+        ps.SynchroniseDevice()
+        dense_samples = int(np.minimum(ps.host(arm.V.DenseIndex), wl.shape.NDO).sum()) * args.phases
 
     # ---- e2e: host buffers through the public API, double-buffered over `chunks` solver objects ----
     chunks = max(1, args.e2e_chunks)
@@ -398,6 +404,17 @@ def main():
                "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_s / args.steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
                "gpu_launches": args.steps * args.phases, "clocks": clocks}
+        if dense_samples is not None:
+            # the only HBM stream that matters on this path: (SD + 1) words per stored point (24 B for Keller-Miksis)
+            bytes_per_sample = (wl.shape.SD + 1) * precision_bytes
+            hbm_peak = None
+            mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(mp):
+                hbm_peak = json.load(open(mp)).get("hbm_gbs")
+            gbs = dense_samples * bytes_per_sample / (kmean * args.phases * 1e-3) / 1e9
+            out["dense_output"] = {"stored_points_per_step_per_gpu": dense_samples, "bytes_per_point": bytes_per_sample, "achieved_gbs": gbs,
+                                   "hbm_peak_gbs": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None,
+                                   "note": "rank 0; algorithmic bytes of the dense-output stream over the kernel time -- the kernel is FP64-pipe bound, the stream is far from the HBM roof"}
         if world == 1 and not args.no_reference_gpu:
             # reported baseline, not a target: the reference MPGOS compiled for sm_100a, same inputs, same event bracket
             try:
