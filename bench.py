@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--instances", type=int, default=0, help="instances (systems) per GPU (default: the BASELINE size)")
     ap.add_argument("--phases", type=int, default=1, help="integration phases (Solve() calls) per step")
-    ap.add_argument("--e2e-chunks", type=int, default=2, help="solver objects the e2e sweep is double-buffered over")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="solver objects the e2e sweep is double-buffered over")
     ap.add_argument("--lane-refill", type=int, default=-1)
     ap.add_argument("--threads-per-block", type=int, default=0)
     ap.add_argument("--tensor-core-coupling", type=int, default=-1)

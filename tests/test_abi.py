@@ -127,3 +127,20 @@ def test_workload_generators(workloads):
     assert km.shape.NCP == 13 and km.buffers.ControlParameters.shape == (13, 128) and np.isfinite(km.buffers.ControlParameters).all()
     sub = km.buffers.take([0, 5, 127])
     assert sub.NT == 3 and np.array_equal(sub.ControlParameters[:, 1], km.buffers.ControlParameters[:, 5])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host cores only (no CUDA) and prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--workload", "coupled"]):
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "64"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["unit"] == "system-steps/s" and line["value"] > 0
+        assert line["e2e"] == {"value": line["value"], "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+        assert "workload" in line["config"] and line["higher_is_better"] is True

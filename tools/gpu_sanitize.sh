@@ -1,0 +1,31 @@
+# compute-sanitizer over small parity cases: memcheck (out-of-bounds, misaligned) and racecheck (shared-memory hazards)
+mkdir -p gpurun_out
+cat > /tmp/san_case.py <<'PY'
+import importlib, sys, os
+import numpy as np
+sys.path[:0] = [os.getcwd(), "oracle", "tests"]
+pkg = importlib.import_module("massively-parallel-gpu-ode-solver_b200")
+from cases import make_cases, make_coupled_cases
+WC = pkg.workloads_coupled
+which = sys.argv[1]
+if which == "coupled":
+    for ups, ns, tc in ((64, 13, 1), (32, 21, 1), (64, 5, 0)):
+        wl = WC.bubble_ensemble(NS=ns, UPS=ups, amplitude=(0.2, 1.2)); wl.buffers.TimeDomain[1][:] = 0.05
+        out, att, acc = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=tc); print("bubble", ups, ns, tc, int(att.sum()))
+    cc = make_coupled_cases(WC)
+    for name in ("ring_b1c1_rkck45", "ring_b0c0_rkck45", "bubble_u16_rkck45"):
+        tag, wl, phases = cc[name]; out, att, acc = pkg.run_coupled_workload(wl, phases=1); print(name, int(att.sum()))
+    wl = WC.swing_ring(NS=5); out, att, acc = pkg.run_coupled_workload(wl, phases=1) if False else (None, np.zeros(1), None)
+else:
+    c = make_cases(pkg.workloads)
+    for name in ("lorenz_rkck45_f64", "duffing_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64", "lorenz_rkck45_f32"):
+        wl, phases = c[name]
+        for refill in (0, 1, 8):
+            out, att, acc = pkg.run_workload(wl, phases=1, lane_refill=refill); print(name, refill, int(att.sum()))
+PY
+for tool in memcheck racecheck; do
+  for which in coupled perthread; do
+    timeout 600 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py $which > gpurun_out/sanitize_${tool}_${which}.txt 2>&1
+    echo "== $tool $which: rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_${tool}_${which}.txt | sort | uniq -c | head -5; grep -cE "^(bubble|ring|lorenz|duffing|impact|keller)" gpurun_out/sanitize_${tool}_${which}.txt
+  done
+done
