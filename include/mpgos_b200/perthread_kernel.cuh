@@ -101,7 +101,13 @@ static __constant__ float  kCashKarpF32[CK_COUNT] = MPGOS_B200_CK_TABLE(float);
 
 template <class P> __device__ __forceinline__ P ck(int i);
 template <> __device__ __forceinline__ double ck<double>(int i) { return kCashKarpF64[i]; }
+#ifdef MPGOS_B200_F32_TABLE_IN_CONSTANT_MEMORY
 template <> __device__ __forceinline__ float  ck<float>(int i)  { return kCashKarpF32[i]; }
+#else
+// FP32 instructions take 32-bit immediates: with a compile-time index the literal folds into the FFMA/FMUL itself and
+// needs neither a uniform register nor a load (the FP32 kernel is issue-bound: every instruction saved counts).
+template <> __device__ __forceinline__ float  ck<float>(int i)  { constexpr float t[CK_COUNT] = MPGOS_B200_CK_TABLE(float); return t[i]; }
+#endif
 
 // SFU approximations without the denormal / special-case wrappers of the CUDA math library
 // (operands are range-checked by the caller).
