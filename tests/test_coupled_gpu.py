@@ -88,6 +88,30 @@ def test_tensor_core_coupling_against_checker_and_scalar_path(ups, ns, pkg, orac
     assert not np.array_equal(tc.ActualState, sc.ActualState) or ups < 32    # the two paths really are different code
 
 
+@pytest.mark.parametrize("algorithm,ndo", [(1, 24), (0, 0)])
+def test_tensor_core_coupling_with_dense_output_and_rk4(algorithm, ndo, pkg, oracle):
+    """The lockstep (tensor-core) variant with dense output (stored points of every unit, per-system index and time) and
+    with the fixed-step scheme, 11 systems of 64 units (one full block + one with idle slots), against the checker."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=11, UPS=64, amplitude=(0.3, 1.0), algorithm=algorithm, ndo=ndo)
+    if algorithm == 0:
+        wl.buffers.TimeDomain[1][:] = 0.2
+        wl.options.InitialTimeStep = 1e-3
+    else:
+        wl.options.DenseOutputMinimumTimeStep = 0.02
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=1, host_threads=8)
+    for tc in (1, 0):
+        out, att, acc = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=tc)
+        assert np.array_equal(out.ActualTime, ref.ActualTime)
+        assert np.abs(att - ratt).max() <= 1
+        assert rel_err(out.ActualState, ref.ActualState).max() < 1e-9
+        if ndo:
+            assert np.array_equal(out.DenseIndex, ref.DenseIndex) and (ref.DenseIndex > 3).all()
+            n = int(ref.DenseIndex.min())
+            assert rel_err(out.DenseTime[:n], ref.DenseTime[:n]).max() < 1e-9
+            assert rel_err(out.DenseState[:n], ref.DenseState[:n]).max() < 1e-8
+
+
 @pytest.mark.parametrize("name,tag,tol", [("bubble_u16_rkck45", "bubble_ensemble_u16", 1e-11), ("ring_b1c1_rkck45", "duffing_ring_b1c1", 1e-9)])
 def test_against_reference_mpgos_coupled_kernels_on_the_same_gpu(name, tag, tol, ccases, pkg, oracle):
     """GPU vs GPU: the reference's own coupled kernels compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_coupled_*.so)."""
