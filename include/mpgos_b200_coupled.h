@@ -108,7 +108,7 @@ int   mpgos_coupled_save_state(mpgos_coupled_solver* s);
 int   mpgos_coupled_restore_state(mpgos_coupled_solver* s);
 void* mpgos_coupled_stream(mpgos_coupled_solver* s);
 
-/* systems compiled into the library: "bubble_ensemble" (UPS 8, 16, 32, 64, 128), "duffing_ring" (UPS 14; CBW/CCI 1/1, 1/0, 0/1, 0/0) */
+/* systems compiled into the library: "bubble_ensemble" (UPS 8, 16, 32, 64, 128), "duffing_ring" (UPS 14; CBW/CCI 1/1, 1/0, 0/1, 0/0; UPS 32 with full matrices) */
 int   mpgos_coupled_builtin_desc(const char* system, int ups, int cbw, int cci, mpgos_coupled_desc* desc);
 mpgos_coupled_launcher mpgos_coupled_builtin_launcher(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output);
 

@@ -25,6 +25,7 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 1, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 1, kAlgRK4, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 0, kAlgRKCK45, true),
+	COUPLED_ENTRY("duffing_ring", DuffingRing, 32, 0, 0, kAlgRKCK45, true),      // full matrices, 2 couplings, events: the tensor-core path with everything on
 };
 const CoupledBuiltinEntry* builtin_entries_coupled(int* n) { *n = (int)(sizeof(kEntries) / sizeof(kEntries[0])); return kEntries; }
 }

@@ -211,11 +211,10 @@ def bubble_ensemble(NS: int = 1 << 16, UPS: int = 64, algorithm: int = RKCK45, p
 
 
 def duffing_ring(NS: int = 9, CBW: int = 1, CCI: int = 1, algorithm: int = RKCK45, phases: int = 1, ndo: int = 100,
-                 TPB: int = 32, SPB: int = 3) -> CoupledWorkload:
+                 TPB: int = 32, SPB: int = 3, UPS: int = 14) -> CoupledWorkload:
     """Tutorials_CoupledSystems_PerBlock/T1_RingOfDuffingOscillators/RingOfDuffingOscillators.cu:79-106, 215-300 -- rings
     of 14 Duffing oscillators, two coupling terms through a banded / circulant matrix, one event per unit (second
     local maximum of any unit ends the phase), system accessories tracking min/max dt, dense output."""
-    UPS = 14
     sh = CoupledShape(UPS=UPS, UD=2, NC=2, CBW=CBW, CCI=CCI, NUP=3, NGP=1, NUA=3, NiUA=1, NSA=2, NiSA=1, NE=1, NDO=ndo,
                       Algorithm=algorithm, TPB=TPB, SPB=SPB)
     b = CoupledBuffers(sh, NS)

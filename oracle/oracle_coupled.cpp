@@ -134,6 +134,7 @@ int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo,
 		if (ups == 64) return dispatch<BubbleEnsemble<double, 64> >(algorithm, ndo, b, o, shape);
 		if (ups == 128) return dispatch<BubbleEnsemble<double, 128> >(algorithm, ndo, b, o, shape);
 	}
+	if (!std::strcmp(system, "duffing_ring") && ups == 32 && cbw == 0 && cci == 0) return dispatch<DuffingRing<double, 32, 0, 0> >(algorithm, ndo, b, o, shape);
 	if (!std::strcmp(system, "duffing_ring") && ups == 14)
 	{
 		if (cbw == 1 && cci == 1) return dispatch<DuffingRing<double, 14, 1, 1> >(algorithm, ndo, b, o, shape);

@@ -112,6 +112,34 @@ def test_tensor_core_coupling_with_dense_output_and_rk4(algorithm, ndo, pkg, ora
             assert rel_err(out.DenseState[:n], ref.DenseState[:n]).max() < 1e-8
 
 
+def test_tensor_core_coupling_with_two_couplings_events_and_accessories(pkg, oracle):
+    """Ring of 32 Duffing oscillators with FULL coupling matrices: two couplings (two matrix products per stage), one event
+    per unit with user-defined termination, system accessories written by unit 0, dense output -- the lockstep variant with
+    every feature on, 19 systems (blocks with idle slots, systems ending at different times), against the checker and
+    against the scalar variant."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.duffing_ring(NS=19, CBW=0, CCI=0, UPS=32, ndo=60, TPB=32, SPB=1)
+    rng = np.random.default_rng(7)
+    A = rng.uniform(0.0, 0.08, (2, 32, 32)) * (1.0 - np.eye(32))[None]
+    wl.buffers.CouplingMatrix[...] = A
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=2, host_threads=8)
+    outs = {}
+    for tc in (1, 0):
+        out, att, acc = outs[tc] = pkg.run_coupled_workload(wl, phases=2, tensor_core_coupling=tc)
+        assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)
+        assert np.abs(att - ratt).max() <= 2 and np.abs(out.IntegerSystemAccessories - ref.IntegerSystemAccessories).max() <= 2
+        assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6
+        assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
+        assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
+        same = out.DenseIndex == ref.DenseIndex
+        assert same.mean() >= 0.7
+        n = int(min(ref.DenseIndex.min(), out.DenseIndex.min())) - 1
+        cols = np.where(same)[0]
+        assert rel_err(out.DenseState[:n][:, :, cols], ref.DenseState[:n][:, :, cols]).max() < 1e-5
+    assert len(set(ref.ActualTime.tolist())) > 3          # event-terminated: the systems really end at different times
+    assert rel_err(outs[1][0].ActualState, outs[0][0].ActualState).max() < 1e-5
+
+
 @pytest.mark.parametrize("name,tag,tol", [("bubble_u16_rkck45", "bubble_ensemble_u16", 1e-11), ("ring_b1c1_rkck45", "duffing_ring_b1c1", 1e-9)])
 def test_against_reference_mpgos_coupled_kernels_on_the_same_gpu(name, tag, tol, ccases, pkg, oracle):
     """GPU vs GPU: the reference's own coupled kernels compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_coupled_*.so)."""
