@@ -16,8 +16,8 @@
 //    stage instead of two), the column sum runs in ascending order with a single accumulator exactly like
 //    ComputeCouplingValue_* (Steppers.cuh:2551-2713), so results track the reference to rounding;
 //  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid);
-//  * TENSOR-CORE COUPLING (MMA variant; dense matrices shared by all systems, FP64, UPS = 32 or 64): the column sums of the
-//    8 systems of a block are ONE matrix product  V[UPS x 8] = M[UPS x UPS] . CPT[UPS x 8]  per stage, issued as
+//  * TENSOR-CORE COUPLING (MMA variant; dense matrices shared by all systems, FP64, UPS = 32, 64 or 128): the column sums of the
+//    8 systems of a block (4 for UPS = 128) are ONE matrix product  V[UPS x 8] = M[UPS x UPS] . CPT[UPS x 8]  per stage, issued as
 //    mma.sync.m8n8k4.f64 (DMMA) by all warps of the block; the matrix sits in shared memory in fragment order.  The scalar
 //    form needs one 8-byte shared-memory operand per FMA and is bound by shared-memory bandwidth (ncu: 45 % of the LSU
 //    wavefront peak at 44 % FP64-pipe activity, profiles/); one DMMA performs 256 FMAs on two 8-byte operands per lane.
@@ -145,40 +145,48 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
 	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Geometry of the block-wide product for UPS units and 8 systems (= SLOTS warps-groups of UPS threads).
-template <int UPS>
+// Geometry of the block-wide product for UPS units and SLOTS <= 8 systems (warp-groups of UPS threads; the N extent of the
+// instruction is 8, columns SLOTS..7 stay zero).  The RT x KG work items (one row tile x one group of k tiles) are dealt
+// round-robin to the warps of the block.
+template <int UPS, int SLOTS_>
 struct MmaGeometry
 {
-	static constexpr int SLOTS = 8;                    // the N extent of the instruction
+	static constexpr int SLOTS = SLOTS_;
+	static constexpr int NCOL = 8;                     // the N extent of the instruction
 	static constexpr int RT = UPS / 8;                 // row tiles of the matrix
 	static constexpr int KT = UPS / 4;                 // column (k) tiles
 	static constexpr int WARPS = SLOTS * UPS / 32;
-	static constexpr int KG = WARPS / RT;              // a warp owns one row tile and 1/KG of the k tiles
+	static constexpr int KG = (WARPS >= RT) ? WARPS / RT : 1;      // a warp owns one row tile and 1/KG of the k tiles (or several row tiles)
+	static constexpr int ITEMS = RT * KG;
 	static constexpr int KPG = KT / KG;
 	static constexpr int CS = UPS + 4;                 // stride of a system's coupling terms  (conflict-free B fragment loads)
 	static constexpr int VS = UPS + 2;                 // stride of a system's partial sums    (conflict-free D fragment stores)
-	static_assert(UPS % 32 == 0 && WARPS % RT == 0 && KT % KG == 0 && KPG % 2 == 0, "unsupported shape for the tensor-core coupling");
+	static_assert(UPS % 32 == 0 && SLOTS >= 1 && SLOTS <= NCOL && ITEMS % WARPS == 0 && KT % KG == 0 && KPG % 2 == 0, "unsupported shape for the tensor-core coupling");
 };
 
-// One coupling term of all 8 systems.  frag: the matrix in fragment order [RT][KT][32]; cpt: [8][CS]; vpart: [KG][8][VS].
-template <int UPS>
+// One coupling term of all systems of the block.  frag: the matrix in fragment order [RT][KT][32]; cpt: [8][CS]; vpart: [KG][8][VS].
+template <int UPS, int SLOTS>
 __device__ __forceinline__ void mma_coupling_product(const double* __restrict__ frag, const double* cpt, double* vpart, int warp, int lane)
 {
-	using G = MmaGeometry<UPS>;
-	const int rt = warp % G::RT, kg = warp / G::RT;
-	const double* A = frag + (size_t)(rt * G::KT + kg * G::KPG) * 32 + lane;
-	const double* B = cpt + (lane >> 2) * G::CS + kg * G::KPG * 4 + (lane & 3);
-	double c0 = 0, c1 = 0, e0 = 0, e1 = 0;             // two independent accumulator pairs hide the DMMA latency
+	using G = MmaGeometry<UPS, SLOTS>;
 	#pragma unroll
-	for (int j = 0; j < G::KPG; j += 2)
+	for (int item = warp; item < G::ITEMS; item += G::WARPS)
 	{
-		const double a0 = A[j * 32], b0 = B[j * 4], a1 = A[(j + 1) * 32], b1 = B[(j + 1) * 4];
-		dmma_8x8x4(c0, c1, a0, b0);
-		dmma_8x8x4(e0, e1, a1, b1);
+		const int rt = item % G::RT, kg = item / G::RT;
+		const double* A = frag + (size_t)(rt * G::KT + kg * G::KPG) * 32 + lane;
+		const double* B = cpt + (lane >> 2) * G::CS + kg * G::KPG * 4 + (lane & 3);
+		double c0 = 0, c1 = 0, e0 = 0, e1 = 0;             // two independent accumulator pairs hide the DMMA latency
+		#pragma unroll
+		for (int j = 0; j < G::KPG; j += 2)
+		{
+			const double a0 = A[j * 32], b0 = B[j * 4], a1 = A[(j + 1) * 32], b1 = B[(j + 1) * 4];
+			dmma_8x8x4(c0, c1, a0, b0);
+			dmma_8x8x4(e0, e1, a1, b1);
+		}
+		double* V = vpart + (size_t)kg * G::NCOL * G::VS + rt * 8 + (lane >> 2);
+		V[(2 * (lane & 3)) * G::VS]     = c0 + e0;
+		V[(2 * (lane & 3) + 1) * G::VS] = c1 + e1;
 	}
-	double* V = vpart + (size_t)kg * G::SLOTS * G::VS + rt * 8 + (lane >> 2);
-	V[(2 * (lane & 3)) * G::VS]     = c0 + e0;
-	V[(2 * (lane & 3) + 1) * G::VS] = c1 + e1;
 }
 
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
@@ -191,10 +199,10 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	constexpr int MSIZE = packed_matrix_elements(UPS, NC, CBW, CCI);
 	constexpr int MSTRIDE = MSIZE / (NC > 0 ? NC : 1);
 	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA, MMA>;
-	using G = MmaGeometry<MMA ? UPS : 32>;
-	constexpr int CPT_ELEMS = MMA ? NC * G::SLOTS * G::CS : 0;             // coupling terms of the 8 systems (MMA variant)
-	constexpr int V_ELEMS   = MMA ? NC * G::KG * G::SLOTS * G::VS : 0;     // partial column sums per k group
-	static_assert(!MMA || (SPBK == G::SLOTS && CBW == 0 && CCI == 0 && NC > 0 && sizeof(P) == 8), "tensor-core coupling: dense FP64 matrices, 8 systems per block");
+	using G = MmaGeometry<MMA ? UPS : 32, MMA ? SPBK : 8>;
+	constexpr int CPT_ELEMS = MMA ? NC * G::NCOL * G::CS : 0;              // coupling terms of the systems of the block (MMA variant)
+	constexpr int V_ELEMS   = MMA ? NC * G::KG * G::NCOL * G::VS : 0;      // partial column sums per k group
+	static_assert(!MMA || (CBW == 0 && CCI == 0 && NC > 0 && sizeof(P) == 8), "tensor-core coupling: dense FP64 matrices");
 
 	extern __shared__ __align__(16) unsigned char dyn_smem[];
 	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE]  packed (scalar) or in fragment order (MMA)
@@ -214,6 +222,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			const int row = (tile / G::KT) * 8 + (l >> 2), col = (tile % G::KT) * 4 + (l & 3);
 			s_matrix[i] = a.CouplingMatrix[(size_t)k * UPS * UPS + row + col * UPS];
 		}
+		for (int i = threadIdx.x; i < CPT_ELEMS; i += blockDim.x) s_cptm[i] = P(0);    // columns without a slot stay zero
 	}
 	else
 		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
@@ -324,13 +333,13 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				{
 					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
 					#pragma unroll
-					for (int k = 0; k < NC; k++) s_cptm[(k * G::SLOTS + slot) * G::CS + unit] = cpt[k];
+					for (int k = 0; k < NC; k++) s_cptm[(k * G::NCOL + slot) * G::CS + unit] = cpt[k];
 				}
 				__syncthreads();
 				#pragma unroll
 				for (int k = 0; k < NC; k++)
-					mma_coupling_product<MMA ? UPS : 32>((const double*)s_matrix + (size_t)k * UPS * UPS, (const double*)s_cptm + k * G::SLOTS * G::CS,
-					                                     (double*)s_vpart + k * G::KG * G::SLOTS * G::VS, warp, threadIdx.x & 31);
+					mma_coupling_product<MMA ? UPS : 32, MMA ? SPBK : 8>((const double*)s_matrix + (size_t)k * UPS * UPS, (const double*)s_cptm + k * G::NCOL * G::CS,
+					                                                     (double*)s_vpart + k * G::KG * G::NCOL * G::VS, warp, lane);
 				__syncthreads();
 				if (live)
 				{
@@ -339,7 +348,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 					{
 						P v = 0;
 						#pragma unroll
-						for (int g = 0; g < G::KG; g++) v += s_vpart[((k * G::KG + g) * G::SLOTS + slot) * G::VS + unit];
+						for (int g = 0; g < G::KG; g++) v += s_vpart[((k * G::KG + g) * G::NCOL + slot) * G::VS + unit];
 						const P add = S.strength[k] * cpf[k] * v;
 						const int ci = s_cidx[k];
 						#pragma unroll
@@ -655,14 +664,15 @@ struct PerBlockLauncher
 	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
 
 	// tensor-core coupling: dense FP64 matrices shared by all systems, whole-warp systems, 8 systems x UPS threads <= 512
-	static constexpr bool kCanMMA = (sizeof(P) == 8) && CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64);
+	static constexpr bool kCanMMA = (sizeof(P) == 8) && CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64 || UPS == 128);
+	static constexpr int  kMmaSlots = (UPS == 128) ? 4 : 8;      // 512 threads; with 128 units half of the instruction's N extent is used
 
 	template <int SLOTS, bool MMA>
 	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
 	{
 		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA>;
-		using G = MmaGeometry<MMA ? UPS : 32>;
-		const size_t extra = MMA ? (size_t)NC * G::SLOTS * G::CS + (size_t)NC * G::KG * G::SLOTS * G::VS : 0;
+		using G = MmaGeometry<MMA ? UPS : 32, MMA ? SLOTS : 8>;
+		const size_t extra = MMA ? (size_t)NC * G::NCOL * G::CS + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
 		const size_t smem = sizeof(P) * (packed_matrix_elements(UPS, NC, CBW, CCI) + extra + NGP) + sizeof(int) * NiGP + 16;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return (int)e;
@@ -703,7 +713,7 @@ struct PerBlockLauncher
 		if (a.Active <= 0) return (int)cudaSuccess;
 		if constexpr (kCanMMA)
 		{
-			if (L->TensorCoreCoupling) return enqueue<8, true>(L, a, stream);
+			if (L->TensorCoreCoupling) return enqueue<kMmaSlots, true>(L, a, stream);
 		}
 		return enqueue<SPBK, false>(L, a, stream);
 	}

@@ -69,9 +69,9 @@ def test_bubble_ensemble_64_units_properties(pkg):
     assert np.array_equal(sout.ActualState, out.ActualState[:, idx, :]) and np.array_equal(satt, att[idx])
 
 
-@pytest.mark.parametrize("ups,ns", [(32, 21), (64, 13)])
+@pytest.mark.parametrize("ups,ns", [(32, 21), (64, 13), (128, 7)])
 def test_tensor_core_coupling_against_checker_and_scalar_path(ups, ns, pkg, oracle):
-    """Dense shared matrix, FP64, UPS 32/64: the column sums of the 8 systems of a block are one DMMA product
+    """Dense shared matrix, FP64, UPS 32/64/128: the column sums of the 8 (4 for UPS 128) systems of a block are one DMMA product
     (mma.sync.m8n8k4.f64).  Checked against the CPU checker (reference summation order) and against our scalar path;
     NS is not a multiple of 8, so blocks also run with idle slots.  The product sums in a different order than the
     reference's single accumulator: endpoints agree to rounding (stated tolerance 1e-9), step counts exactly."""

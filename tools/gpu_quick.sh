@@ -1,3 +1,3 @@
-python -m pytest tests/test_perthread_gpu.py tests/test_coupled_gpu.py -x -q -m gpu --tb=short 2>&1 | grep -E "^E   |passed|failed" | cut -c1-200 | head -5
-REFILLS=0 TPBS=128 python tools/time_perthread.py impact:8 kellermiksis:2 lorenz:1 lorenz_f32:1 2>&1 | grep -v Warning
-TC=1 python tools/time_coupled.py 8192 2>&1 | tail -1
+python -m pytest tests/test_coupled_gpu.py -x -q -m gpu --tb=short 2>&1 | grep -E "^E   |passed|failed" | cut -c1-300 | head -8
+UPS=128 TC=0 python tools/time_coupled.py 4096 2>&1 | tail -1
+UPS=128 TC=1 REFTAG=bubble_ensemble_u128 python tools/time_coupled.py 4096 2>&1 | grep -vE "^ |^$|memory|Object|THREAD|GLOBAL|SHARED|\-\-\-" | tail -4

@@ -6,8 +6,9 @@ sys.path[:0] = [ROOT]
 pkg = importlib.import_module("massively-parallel-gpu-ode-solver_b200")
 WC = pkg.workloads_coupled
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-wl = WC.bubble_ensemble(NS=NS, UPS=64)
-with pkg.CoupledProblemSolver("bubble_ensemble", NS, 64) as ps:
+UPS = int(os.environ.get('UPS', '64'))
+wl = WC.bubble_ensemble(NS=NS, UPS=UPS)
+with pkg.CoupledProblemSolver("bubble_ensemble", NS, UPS) as ps:
     pkg.apply_coupled_workload(ps, wl)
     ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, int(os.environ.get('TC', '1')))
     best = None
@@ -18,4 +19,11 @@ with pkg.CoupledProblemSolver("bubble_ensemble", NS, 64) as ps:
         best = ms if best is None else min(best, ms)
     att, acc = ps.StepCounters()
     out = pkg.read_back_coupled(ps, wl)
-print(f"TC={os.environ.get('TC','1')} lib={os.environ.get('MPGOS_B200_LIBRARY','(default)'):34s} NS={NS}: {best:.2f} ms  {int(att.sum())/best/1e3:.3f} M system-steps/s  checksum {out.ActualState.sum():.12e}")
+if os.environ.get('REFTAG'):
+    sys.path[:0] = [os.path.join(ROOT, 'oracle')]
+    import oracle_py
+    for shared in (0, 1):
+        ref, rms = oracle_py.run_coupled_ref_gpu(os.environ['REFTAG'], wl, phases=1, shared_matrices=shared, repeats=2)
+        rel = np.abs(out.ActualState - ref.ActualState) / np.maximum(np.abs(ref.ActualState), 1.0)
+        print(f'reference MPGOS {os.environ["REFTAG"]} SharedCouplingMatrices={shared}: {rms:.2f} ms; ours vs reference max rel {rel.max():.2e}')
+print(f"UPS={UPS} TC={os.environ.get('TC','1')} lib={os.environ.get('MPGOS_B200_LIBRARY','(default)'):34s} NS={NS}: {best:.2f} ms  {int(att.sum())/best/1e3:.3f} M system-steps/s  checksum {out.ActualState.sum():.12e}")
