@@ -162,10 +162,11 @@ def test_lane_refill_is_bit_identical_to_direct_mapping(cases, pkg):
     for name in ("lorenz_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64"):
         wl, phases = cases[name]
         a, aatt, aacc = pkg.run_workload(wl, phases=phases, lane_refill=0)
-        b, batt, bacc = pkg.run_workload(wl, phases=phases, lane_refill=1, threads_per_block=64)
-        for f in RESULT_FIELDS:
-            assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), (name, f)
-        assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc)
+        for threshold in (1, 5, 32):       # idle lanes per warp that trigger the ballot-batched refill
+            b, batt, bacc = pkg.run_workload(wl, phases=phases, lane_refill=threshold, threads_per_block=64)
+            for f in RESULT_FIELDS:
+                assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), (name, f, threshold)
+            assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc)
 
 
 def test_active_number_of_threads(cases, pkg):

@@ -1,0 +1,43 @@
+"""The drop-in claim as a test: every tutorial program of the reference compiles UNMODIFIED against include/ (same include
+order, same template arguments, same unscoped enums and method overloads).  Needs the reference checkout and nvcc, i.e. the
+development container; skipped elsewhere.  Compile only (-c): running them is the GPU tests' job."""
+import concurrent.futures
+import glob
+import os
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+def _tutorials():
+    out = []
+    for group in ("Tutorials_SingleSystem_PerThread", "Tutorials_CoupledSystems_PerBlock"):
+        for d in sorted(glob.glob(os.path.join(REF, group, "T*"))):
+            mains = [f for f in glob.glob(os.path.join(d, "*.cu"))]
+            out += [(os.path.basename(d), f) for f in mains]
+    return out
+
+
+def _compile(item):
+    name, src = item
+    with tempfile.TemporaryDirectory() as tmp:
+        cmd = ["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", os.path.join(ROOT, "include"),
+               "-I", os.path.dirname(src), "-c", src, "-o", os.path.join(tmp, "t.o")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return name, r.returncode, r.stderr[-1500:]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "SourceCodes")) or shutil.which("nvcc") is None,
+                    reason="needs /root/reference and nvcc (development container)")
+def test_every_reference_tutorial_compiles_unmodified_against_the_dropin_headers():
+    items = _tutorials()
+    assert len(items) >= 10          # T1..T8 per-thread, T1..T2 coupled
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(_compile, items))
+    failed = [(n, err) for n, rc, err in results if rc != 0]
+    assert not failed, failed
