@@ -39,6 +39,15 @@ constexpr int kMaxThreadsPerBlock = 256;
 #endif
 constexpr int kAlgRK4 = 0, kAlgRKCK45 = 1;
 
+// Compile-time choices of the RKCK45 arithmetic (see the comments at their use).  The parity build
+// (libmpgos_b200_strict.so) sets MPGOS_B200_STAGE_FORM=0: the reference's expression shapes.
+#ifndef MPGOS_B200_STAGE_FORM
+#define MPGOS_B200_STAGE_FORM 1
+#endif
+#ifndef MPGOS_B200_NEWTON_F64
+#define MPGOS_B200_NEWTON_F64 1
+#endif
+
 template <int N> struct AtLeastOne { static constexpr int value = (N > 0 ? N : 1); };
 
 // By-value kernel argument (constant bank).  Role of the reference's Struct_GlobalVariables +
@@ -129,7 +138,9 @@ template <> struct Num<double>
 	static __device__ __forceinline__ unsigned top(double x) { return (unsigned)__double2hiint(x); }
 	static constexpr unsigned kLow = (1023u - 100u) << 20, kSpan = 130u << 20;
 	static constexpr int kRatioLimit = 98 << 20;    // top(tol) - top(err) below this  =>  tol/err < 2^99 < 1e30
-	static constexpr int kNewton = 2;
+	static constexpr int kRatioFloor = 60 << 20;    // and above minus this  =>  tol/err > 2^-61: (tol/err)^(4/4) stays a normal float
+	static constexpr int kNewton = MPGOS_B200_NEWTON_F64;
+	static constexpr bool kNewtonSeed = (MPGOS_B200_NEWTON_F64 == 1);
 	static __device__ __forceinline__ float  narrow(double x) { return __double2float_rn(x); }
 };
 
@@ -139,7 +150,9 @@ template <> struct Num<float>
 	static __device__ __forceinline__ unsigned top(float x) { return (unsigned)__float_as_int(x); }
 	static constexpr unsigned kLow = (127u - 60u) << 23, kSpan = 90u << 23;
 	static constexpr int kRatioLimit = 98 << 23;
+	static constexpr int kRatioFloor = 60 << 23;
 	static constexpr int kNewton = 1;
+	static constexpr bool kNewtonSeed = false;
 	static __device__ __forceinline__ float  narrow(float x) { return x; }
 };
 
@@ -148,16 +161,29 @@ template <> struct Num<float>
 //     y <- y + y (1 - a y^n)/n  =  y + y (tol - err y^n) / (n tol).
 // The residual tol - err y^n is one FMA in working precision; the factor 1/(n tol) only scales a
 // correction of relative size <= 1e-5, so a single-precision reciprocal is exact enough.  The
-// seed comes from the SFU (lg2/ex2) with relative error <~ 4e-6; two steps in FP64 (one in FP32)
-// leave ~1 ulp.
+// seed comes from the SFU (lg2/ex2) with relative error <~ 4e-6.
+//   MPGOS_B200_NEWTON_F64 == 1 (default): one Newton step in FP32 (FP32 pipe, idle in this kernel) takes the seed to
+//     ~1e-7, one step in FP64 to ~3e-14.  The step-size factor then differs from the exact root by <~ 100 ulp, which
+//     moves the next step's error estimate by 5 x 3e-14 relative -- five orders below the rounding noise of the embedded
+//     error estimate itself (a difference of nearly cancelling stage terms: 1e-16 |k| dt against err ~ 1e-8 |x|).
+//   MPGOS_B200_NEWTON_F64 == 2: two steps in FP64 straight from the seed (~1 ulp), 6 more FP64-pipe instructions per step.
 template <class P>
 __device__ __forceinline__ P ratio_root_fast(P tol, P err, bool accept)
 {
 	const float tf  = Num<P>::narrow(tol);
 	const float ef  = Num<P>::narrow(err);
 	const float inv = accept ? 0.2f : 0.25f;
-	P y = (P)sfu_ex2((sfu_lg2(tf) - sfu_lg2(ef)) * inv);
-	const P rn = (P)(sfu_rcp(tf) * inv);
+	float yf = sfu_ex2((sfu_lg2(tf) - sfu_lg2(ef)) * inv);
+	const float rnf = sfu_rcp(tf) * inv;
+	if (Num<P>::kNewtonSeed)
+	{
+		const float y2 = yf * yf;
+		const float y4 = y2 * y2;
+		const float yn = accept ? y4 * yf : y4;
+		yf = fmaf(yf * fmaf(-ef, yn, tf), rnf, yf);
+	}
+	P y = (P)yf;
+	const P rn = (P)rnf;
 	#pragma unroll
 	for (int it = 0; it < Num<P>::kNewton; it++)
 	{
@@ -342,8 +368,62 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 		}
 		else
 		{
-			// Steppers.cuh:122-290 -- Cash-Karp 4(5); expression shapes as in the reference
+			// Steppers.cuh:122-290 -- Cash-Karp 4(5)
 			P X[SD], T, k1[SD], k2[SD], k3[SD], k4[SD], k5[SD], k6[SD], err[SD];
+#if MPGOS_B200_STAGE_FORM == 1
+			// Increment form: each slope is scaled by dt once (h_j = dt k_j), every stage is then a chain of FMAs with one
+			// tableau constant as operand.  Same instruction count as the reference's shape x + dt (a1 k1 + a2 k2 + ...), but
+			// no FMA reads three register pairs: on sm_100a such a DFMA occupies the FP64 pipe for 3 cycles instead of 2
+			// (register-file read bandwidth; tools/microbench_fp64.cu).  Rounding differs from the reference's shape by
+			// O(1 ulp) per stage, as FMA contraction already does; the parity build keeps the reference's shape (#else).
+			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k1[i] *= dt;
+
+			T = s.t + dt * ck<P>(CK_C2);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A21), k1[i], s.x[i]);
+			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k2[i] *= dt;
+
+			T = s.t + dt * ck<P>(CK_C3);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A32), k2[i], fma(ck<P>(CK_A31), k1[i], s.x[i]));
+			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k3[i] *= dt;
+
+			T = s.t + dt * ck<P>(CK_C4);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A43), k3[i], fma(ck<P>(CK_A42), k2[i], fma(ck<P>(CK_A41), k1[i], s.x[i])));
+			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k4[i] *= dt;
+
+			T = s.t + dt;
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A54), k4[i], fma(ck<P>(CK_A53), k3[i], fma(ck<P>(CK_A52), k2[i], fma(ck<P>(CK_A51), k1[i], s.x[i]))));
+			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k5[i] *= dt;
+
+			T = s.t + dt * ck<P>(CK_C6);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A65), k5[i], fma(ck<P>(CK_A64), k4[i], fma(ck<P>(CK_A63), k3[i], fma(ck<P>(CK_A62), k2[i], fma(ck<P>(CK_A61), k1[i], s.x[i])))));
+			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) k6[i] *= dt;
+
+			#pragma unroll
+			for (int i = 0; i < SD; i++)
+			{
+				xn[i] = fma(ck<P>(CK_B6), k6[i], fma(ck<P>(CK_B4), k4[i], fma(ck<P>(CK_B3), k3[i], fma(ck<P>(CK_B1), k1[i], s.x[i]))));
+				const P e = fma(ck<P>(CK_E6), k6[i], fma(ck<P>(CK_E5), k5[i], fma(ck<P>(CK_E4), k4[i], fma(ck<P>(CK_E3), k3[i], ck<P>(CK_E1) * k1[i]))));
+				err[i] = fabs(e) + ck<P>(CK_ERRFLOOR);
+			}
+#else
+			// expression shapes as in the reference
 			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
 
 			T = s.t + dt * ck<P>(CK_C2);
@@ -378,6 +458,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				const P e = ck<P>(CK_E1) * k1[i] + ck<P>(CK_E3) * k3[i] + ck<P>(CK_E4) * k4[i] + ck<P>(CK_E5) * k5[i] + ck<P>(CK_E6) * k6[i];
 				err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
 			}
+#endif
 
 			// ErrorControllers.cuh:24-86 -- accept test, limiting component, new step size.
 			// The selects are ordered so that a NaN/Inf in xn or err reaches tol/err unchanged; the
@@ -387,9 +468,10 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
-				const P ax = fabs(s.x[i]), an = fabs(xn[i]);
-				const P m  = (ax > an) ? ax : an;
-				const P t  = a.RelativeTolerance[i] * m;
+				// max(|x|, |xn|): select the signed value, take |.| as an operand modifier of the product (a materialised
+				// fabs() is a DADD on the FP64 pipe)
+				const P m  = (fabs(s.x[i]) > fabs(xn[i])) ? s.x[i] : xn[i];
+				const P t  = a.RelativeTolerance[i] * fabs(m);
 				tol[i] = (a.AbsoluteTolerance[i] > t) ? a.AbsoluteTolerance[i] : t;
 				update = update && (err[i] < tol[i]);
 				outside = max(outside, max(Num<P>::top(tol[i]) - Num<P>::kLow, Num<P>::top(err[i]) - Num<P>::kLow));
@@ -403,7 +485,8 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				tsel = less ? tol[i] : tsel;
 				esel = less ? err[i] : esel;
 			}
-			const bool fast = (outside < Num<P>::kSpan) && ((int)(Num<P>::top(tsel) - Num<P>::top(esel)) < Num<P>::kRatioLimit);
+			const bool fast = (outside < Num<P>::kSpan) &&
+			                  ((unsigned)((int)(Num<P>::top(tsel) - Num<P>::top(esel)) + Num<P>::kRatioFloor) < (unsigned)(Num<P>::kRatioLimit + Num<P>::kRatioFloor));
 			const bool at_minimum = dt < a.MinimumTimeStepGuard;
 			P mult;
 			if (fast)
