@@ -34,6 +34,9 @@
 namespace mpgos_b200 {
 
 constexpr int kMaxThreadsPerBlock = 256;
+// MINB (resident blocks per SM the kernel is compiled for) sets the register cap: 1..4 with 256-thread blocks
+// (255 / 128 / 80 / 64 registers), 5..8 with blocks of at most 128 threads (96 / 80 / 72 / 64 registers).
+__host__ __device__ constexpr int launch_bound_threads(int minb) { return minb >= 5 ? 128 : kMaxThreadsPerBlock; }
 #ifndef MPGOS_B200_MIN_BLOCKS_PER_SM
 #define MPGOS_B200_MIN_BLOCKS_PER_SM 2
 #endif
@@ -84,29 +87,35 @@ struct PerThreadArgs
 // instructions with constants from uniform registers; literals are rebuilt with two UMOVs per
 // use once the 63 uniform registers run out (66 UMOVs per step for Lorenz), whereas constant
 // memory is fetched two doubles at a time (LDCU.128).  Same values as the reference's literals.
+// Rows start on even indices so that a row is fetched with 16-byte loads (LDCU.128).
 enum CashKarp
 {
 	CK_C2, CK_C3, CK_C4, CK_C6,
-	CK_A21, CK_A31, CK_A32, CK_A41, CK_A42, CK_A43, CK_A51, CK_A52, CK_A53, CK_A54,
-	CK_A61, CK_A62, CK_A63, CK_A64, CK_A65,
+	CK_A21, CK_PAD0,
+	CK_A31, CK_A32,
+	CK_A41, CK_A42, CK_A43, CK_PAD1,
+	CK_A51, CK_A52, CK_A53, CK_A54,
+	CK_A61, CK_A62, CK_A63, CK_A64, CK_A65, CK_PAD2,
 	CK_B1, CK_B3, CK_B4, CK_B6,
-	CK_E1, CK_E3, CK_E4, CK_E5, CK_E6,
-	CK_ERRFLOOR, CK_SAFETY,
+	CK_E1, CK_E3, CK_E4, CK_E5, CK_E6, CK_ERRFLOOR,
+	CK_SAFETY, CK_PAD3,
 	CK_COUNT
 };
 
 #define MPGOS_B200_CK_TABLE(T)                                                                                     \
 	{ (T)(1.0 / 5.0), (T)(3.0 / 10.0), (T)(3.0 / 5.0), (T)(7.0 / 8.0),                                              \
-	  (T)(1.0 / 5.0), (T)(3.0 / 40.0), (T)(9.0 / 40.0), (T)(3.0 / 10.0), (T)(-9.0 / 10.0), (T)(6.0 / 5.0),          \
+	  (T)(1.0 / 5.0), (T)0,                                                                                         \
+	  (T)(3.0 / 40.0), (T)(9.0 / 40.0),                                                                             \
+	  (T)(3.0 / 10.0), (T)(-9.0 / 10.0), (T)(6.0 / 5.0), (T)0,                                                      \
 	  (T)(-11.0 / 54.0), (T)(5.0 / 2.0), (T)(-70.0 / 27.0), (T)(35.0 / 27.0),                                       \
-	  (T)(1631.0 / 55296.0), (T)(175.0 / 512.0), (T)(575.0 / 13824.0), (T)(44275.0 / 110592.0), (T)(253.0 / 4096.0), \
+	  (T)(1631.0 / 55296.0), (T)(175.0 / 512.0), (T)(575.0 / 13824.0), (T)(44275.0 / 110592.0), (T)(253.0 / 4096.0), (T)0, \
 	  (T)(37.0 / 378.0), (T)(250.0 / 621.0), (T)(125.0 / 594.0), (T)(512.0 / 1771.0),                               \
 	  (T)(37.0 / 378.0 - 2825.0 / 27648.0), (T)(250.0 / 621.0 - 18575.0 / 48384.0),                                 \
-	  (T)(125.0 / 594.0 - 13525.0 / 55296.0), (T)(0.0 - 277.0 / 14336.0), (T)(512.0 / 1771.0 - 1.0 / 4.0),          \
-	  (T)(1e-18), (T)(0.9) }
+	  (T)(125.0 / 594.0 - 13525.0 / 55296.0), (T)(0.0 - 277.0 / 14336.0), (T)(512.0 / 1771.0 - 1.0 / 4.0), (T)(1e-18), \
+	  (T)(0.9), (T)0 }
 
-static __constant__ double kCashKarpF64[CK_COUNT] = MPGOS_B200_CK_TABLE(double);
-static __constant__ float  kCashKarpF32[CK_COUNT] = MPGOS_B200_CK_TABLE(float);
+static __constant__ __align__(16) double kCashKarpF64[CK_COUNT] = MPGOS_B200_CK_TABLE(double);
+static __constant__ __align__(16) float  kCashKarpF32[CK_COUNT] = MPGOS_B200_CK_TABLE(float);
 
 template <class P> __device__ __forceinline__ P ck(int i);
 template <> __device__ __forceinline__ double ck<double>(int i) { return kCashKarpF64[i]; }
@@ -116,6 +125,49 @@ template <> __device__ __forceinline__ float  ck<float>(int i)  { return kCashKa
 // FP32 instructions take 32-bit immediates: with a compile-time index the literal folds into the FFMA/FMUL itself and
 // needs neither a uniform register nor a load (the FP32 kernel is issue-bound: every instruction saved counts).
 template <> __device__ __forceinline__ float  ck<float>(int i)  { constexpr float t[CK_COUNT] = MPGOS_B200_CK_TABLE(float); return t[i]; }
+#endif
+
+// One tableau row, fetched where it is used.  Left to itself the compiler hoists all 28 constant loads out of the
+// step loop, runs out of uniform registers, parks the rest in vector registers (some even on the stack) and moves
+// them back with two R2UR per constant and step.  A volatile load cannot be hoisted: a row costs one LDCU.128 per two
+// constants and lives in uniform registers only while its stage is formed.
+#ifndef MPGOS_B200_TABLEAU_ROW_LOADS
+#define MPGOS_B200_TABLEAU_ROW_LOADS 1
+#endif
+#ifndef MPGOS_B200_TABLEAU_IMMEDIATES
+#define MPGOS_B200_TABLEAU_IMMEDIATES 1
+#endif
+template <class P, int FIRST, int N> struct CkRow
+{
+	static __device__ __forceinline__ void load(P* c)
+	{
+		#pragma unroll
+		for (int j = 0; j < N; j++) c[j] = ck<P>(FIRST + j);
+	}
+};
+#if MPGOS_B200_TABLEAU_ROW_LOADS
+template <int FIRST, int N> struct CkRow<double, FIRST, N>
+{
+	static_assert(FIRST % 2 == 0, "rows start on 16-byte boundaries");
+	static __device__ __forceinline__ void load(double* c)
+	{
+		#pragma unroll
+		for (int j = 0; j + 1 < N; j += 2)
+			asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(c[j]), "=d"(c[j + 1]) : "l"(__cvta_generic_to_constant(&kCashKarpF64[FIRST + j])));
+		if (N % 2 == 1)
+			asm volatile("ld.const.f64 %0, [%1];" : "=d"(c[N - 1]) : "l"(__cvta_generic_to_constant(&kCashKarpF64[FIRST + N - 1])));
+#if MPGOS_B200_TABLEAU_IMMEDIATES
+		// dyadic entries whose low mantissa word is zero fold into the instruction as 32-bit immediates: no uniform register
+		#pragma unroll
+		for (int j = 0; j < N; j++)
+		{
+			if (FIRST + j == CK_A52) c[j] = 5.0 / 2.0;
+			if (FIRST + j == CK_A62) c[j] = 175.0 / 512.0;
+			if (FIRST + j == CK_A65) c[j] = 253.0 / 4096.0;
+		}
+#endif
+	}
+};
 #endif
 
 // SFU approximations without the denormal / special-case wrappers of the CUDA math library
@@ -222,7 +274,7 @@ struct LaneState
 // user's PerThread_* functions).
 
 template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL, int MINB>
-__global__ void __launch_bounds__(kMaxThreadsPerBlock, MINB)
+__global__ void __launch_bounds__(launch_bound_threads(MINB), MINB)
 perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 {
 	// shared parameters: staged once per block (Solver.cuh:66-88); unlike the reference we
@@ -236,97 +288,74 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 		__syncthreads();
 	}
 
+	// A handful of shared parameters is copied on into registers: the volatile tableau loads of the step loop keep the
+	// compiler from hoisting shared-memory reads out of it (13 LDS + address arithmetic per step for the impact system).
+	constexpr bool kSharedInRegisters = (NSP <= 8 && NISP <= 8);
+	P   r_par[kSharedInRegisters ? AtLeastOne<NSP>::value : 1];
+	int r_pari[kSharedInRegisters ? AtLeastOne<NISP>::value : 1];
+	if (kSharedInRegisters)
+	{
+		#pragma unroll
+		for (int i = 0; i < NSP; i++)  r_par[i]  = s_par[i];
+		#pragma unroll
+		for (int i = 0; i < NISP; i++) r_pari[i] = s_pari[i];
+	}
+	P*   const p_par  = kSharedInRegisters ? r_par  : s_par;
+	int* const p_pari = kSharedInRegisters ? r_pari : s_pari;
+
 	const int NTG    = a.GlobalInstances;
 	const int stride = a.Stride;
 
 	LaneState<P, SD, NCP, NE, NA, NIA> s;
-	int  inst  = blockIdx.x * blockDim.x + threadIdx.x;
-	bool alive = false;
-	bool first = true;
-	bool queue_empty = false;       // REFILL: warp-uniform
 
-	for (;;)
+	// ---- load one instance into the lane's registers (Solver.cuh:117-193) --------------------------
+	auto load = [&](const int inst)
 	{
-		bool take = false;
-		if (REFILL)
-		{
-			// ---- warp ballot: refill the idle lanes together once there are enough of them -------
-			const unsigned idle = __ballot_sync(0xffffffffu, !alive);
-			if (idle != 0u)
-			{
-				const int n = __popc(idle);
-				if (!queue_empty && (n >= a.RefillThreshold || n == 32))
-				{
-					const int lane = threadIdx.x & 31;
-					const int leader = __ffs(idle) - 1;
-					unsigned base = 0;
-					if (lane == leader) base = atomicAdd(a.WorkQueue, (unsigned)n);
-					base = __shfl_sync(0xffffffffu, base, leader);
-					if (!alive)
-					{
-						inst = (int)(base + (unsigned)__popc(idle & ((1u << lane) - 1u)));
-						take = inst < a.Active;
-					}
-					queue_empty = (base + (unsigned)n) >= (unsigned)a.Active;
-				}
-				if (idle == 0xffffffffu && !__any_sync(0xffffffffu, take)) break;
-			}
-		}
-		else if (!alive)
-		{
-			if (!first) break;
-			first = false;
-			if (inst >= a.Active) break;
-			take = true;
-		}
+		// ---- load (coalesced on the first fill), Solver.cuh:117-142 ----------------------
+		#pragma unroll
+		for (int i = 0; i < 2; i++)   s.td[i]   = a.TimeDomain[inst + i * stride];
+		#pragma unroll
+		for (int i = 0; i < SD; i++)  s.x[i]    = a.ActualState[inst + i * stride];
+		#pragma unroll
+		for (int i = 0; i < NCP; i++) s.cpar[i] = a.ControlParameters[inst + i * stride];
+		#pragma unroll
+		for (int i = 0; i < NA; i++)  s.acc[i]  = a.Accessories[inst + i * stride];
+		#pragma unroll
+		for (int i = 0; i < NIA; i++) s.acci[i] = a.IntegerAccessories[inst + i * stride];
+		s.t = a.ActualTime[inst];
+		s.dense_index = DENSE ? a.DenseOutputIndex[inst] : 0;
+		s.dense_skipped = 0;
+		s.dense_next_time = P(0);
+		s.dt_new = a.InitialTimeStep;
+		s.attempted = 0;  s.accepted = 0;
 
-		if (take)
+		P dt0 = a.InitialTimeStep;
+		const int gid = inst + a.InstanceOffset;
+		Sys::Initialization(gid, NTG, s.dense_index, s.t, dt0, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
+		if (NE > 0)
+			Sys::EventFunction(gid, NTG, s.ev, s.t, dt0, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
+		if (DENSE)   // first point of the phase, stored without looking at the index (Solver.cuh:179-193)
 		{
-			// ---- load (coalesced on the first fill), Solver.cuh:117-142 ----------------------
-			#pragma unroll
-			for (int i = 0; i < 2; i++)   s.td[i]   = a.TimeDomain[inst + i * stride];
-			#pragma unroll
-			for (int i = 0; i < SD; i++)  s.x[i]    = a.ActualState[inst + i * stride];
-			#pragma unroll
-			for (int i = 0; i < NCP; i++) s.cpar[i] = a.ControlParameters[inst + i * stride];
-			#pragma unroll
-			for (int i = 0; i < NA; i++)  s.acc[i]  = a.Accessories[inst + i * stride];
-			#pragma unroll
-			for (int i = 0; i < NIA; i++) s.acci[i] = a.IntegerAccessories[inst + i * stride];
-			s.t = a.ActualTime[inst];
-			s.dense_index = DENSE ? a.DenseOutputIndex[inst] : 0;
+			if (s.dense_index < a.DenseCapacity)
+			{
+				a.DenseOutputTimeInstances[inst + (size_t)s.dense_index * stride] = s.t;
+				#pragma unroll
+				for (int i = 0; i < SD; i++)
+					a.DenseOutputStates[inst + (size_t)i * stride + (size_t)s.dense_index * stride * SD] = s.x[i];
+			}
+			s.dense_index++;
 			s.dense_skipped = 0;
-			s.dense_next_time = P(0);
-			s.dt_new = a.InitialTimeStep;
-			s.attempted = 0;  s.accepted = 0;
-			alive = true;
-
-			P dt0 = a.InitialTimeStep;
-			const int gid = inst + a.InstanceOffset;
-			Sys::Initialization(gid, NTG, s.dense_index, s.t, dt0, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
-			if (NE > 0)
-				Sys::EventFunction(gid, NTG, s.ev, s.t, dt0, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
-			if (DENSE)   // first point of the phase, stored without looking at the index (Solver.cuh:179-193)
-			{
-				if (s.dense_index < a.DenseCapacity)
-				{
-					a.DenseOutputTimeInstances[inst + (size_t)s.dense_index * stride] = s.t;
-					#pragma unroll
-					for (int i = 0; i < SD; i++)
-						a.DenseOutputStates[inst + (size_t)i * stride + (size_t)s.dense_index * stride * SD] = s.x[i];
-				}
-				s.dense_index++;
-				s.dense_skipped = 0;
-				s.dense_next_time = fmin(s.t + a.DenseOutputMinimumTimeStep, s.td[1]);
-			}
+			s.dense_next_time = fmin(s.t + a.DenseOutputMinimumTimeStep, s.td[1]);
 		}
+	};
 
-		if (REFILL && !alive) continue;
-
+	// ---- one attempted step (Solver.cuh:197-394); returns true when the phase of this instance ends ----
+	auto step = [&](const int inst, P& dt) -> bool
+	{
 		// ======================== one attempted step (Solver.cuh:197-394) =====================
 		const int gid = inst + a.InstanceOffset;
 		bool update = true, finite = true, terminate = false, end_reached = false;
-		P dt = s.dt_new;
+		dt = s.dt_new;
 		{
 			const P remaining = s.td[1] - s.t;
 			if (dt > remaining) { dt = remaining; end_reached = true; }
@@ -340,18 +369,18 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			P X[SD], k[SD], T;
 			const P half = P(0.5) * dt;
 			const P sixth = P(1.0 / 6.0) * dt;
-			Sys::OdeFunction(gid, NTG, xn, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, xn, s.x, s.t, s.cpar, p_par, p_pari, s.acc, s.acci);
 			T = s.t + half;
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + xn[i] * half;
-			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) { xn[i] = xn[i] + P(2.0) * k[i]; X[i] = s.x[i] + k[i] * half; }
-			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			T = s.t + dt;
 			#pragma unroll
 			for (int i = 0; i < SD; i++) { xn[i] = xn[i] + P(2.0) * k[i]; X[i] = s.x[i] + k[i] * dt; }
-			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
@@ -376,80 +405,89 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			// no FMA reads three register pairs: on sm_100a such a DFMA occupies the FP64 pipe for 3 cycles instead of 2
 			// (register-file read bandwidth; tools/microbench_fp64.cu).  Rounding differs from the reference's shape by
 			// O(1 ulp) per stage, as FMA contraction already does; the parity build keeps the reference's shape (#else).
-			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+			P c[6];
+			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k1[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C2);
+			CkRow<P, CK_A21, 1>::load(c);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A21), k1[i], s.x[i]);
-			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			for (int i = 0; i < SD; i++) X[i] = fma(c[0], k1[i], s.x[i]);
+			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k2[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C3);
+			CkRow<P, CK_A31, 2>::load(c);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A32), k2[i], fma(ck<P>(CK_A31), k1[i], s.x[i]));
-			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			for (int i = 0; i < SD; i++) X[i] = fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]));
+			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k3[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C4);
+			CkRow<P, CK_A41, 3>::load(c);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A43), k3[i], fma(ck<P>(CK_A42), k2[i], fma(ck<P>(CK_A41), k1[i], s.x[i])));
-			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			for (int i = 0; i < SD; i++) X[i] = fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])));
+			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k4[i] *= dt;
 
 			T = s.t + dt;
+			CkRow<P, CK_A51, 4>::load(c);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A54), k4[i], fma(ck<P>(CK_A53), k3[i], fma(ck<P>(CK_A52), k2[i], fma(ck<P>(CK_A51), k1[i], s.x[i]))));
-			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			for (int i = 0; i < SD; i++) X[i] = fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]))));
+			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k5[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C6);
+			CkRow<P, CK_A61, 5>::load(c);
 			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(ck<P>(CK_A65), k5[i], fma(ck<P>(CK_A64), k4[i], fma(ck<P>(CK_A63), k3[i], fma(ck<P>(CK_A62), k2[i], fma(ck<P>(CK_A61), k1[i], s.x[i])))));
-			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			for (int i = 0; i < SD; i++) X[i] = fma(c[4], k5[i], fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])))));
+			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k6[i] *= dt;
 
+			CkRow<P, CK_B1, 4>::load(c);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) xn[i] = fma(c[3], k6[i], fma(c[2], k4[i], fma(c[1], k3[i], fma(c[0], k1[i], s.x[i]))));
+			CkRow<P, CK_E1, 6>::load(c);
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
-				xn[i] = fma(ck<P>(CK_B6), k6[i], fma(ck<P>(CK_B4), k4[i], fma(ck<P>(CK_B3), k3[i], fma(ck<P>(CK_B1), k1[i], s.x[i]))));
-				const P e = fma(ck<P>(CK_E6), k6[i], fma(ck<P>(CK_E5), k5[i], fma(ck<P>(CK_E4), k4[i], fma(ck<P>(CK_E3), k3[i], ck<P>(CK_E1) * k1[i]))));
-				err[i] = fabs(e) + ck<P>(CK_ERRFLOOR);
+				const P e = fma(c[4], k6[i], fma(c[3], k5[i], fma(c[2], k4[i], fma(c[1], k3[i], c[0] * k1[i]))));
+				err[i] = fabs(e) + c[5];
 			}
 #else
 			// expression shapes as in the reference
-			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			T = s.t + dt * ck<P>(CK_C2);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A21) * k1[i]);
-			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			T = s.t + dt * ck<P>(CK_C3);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A31) * k1[i] + ck<P>(CK_A32) * k2[i]);
-			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			T = s.t + dt * ck<P>(CK_C4);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A41) * k1[i] + ck<P>(CK_A42) * k2[i] + ck<P>(CK_A43) * k3[i]);
-			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			T = s.t + dt;
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A51) * k1[i] + ck<P>(CK_A52) * k2[i] + ck<P>(CK_A53) * k3[i] + ck<P>(CK_A54) * k4[i]);
-			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			T = s.t + dt * ck<P>(CK_C6);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = s.x[i] + dt * (ck<P>(CK_A61) * k1[i] + ck<P>(CK_A62) * k2[i] + ck<P>(CK_A63) * k3[i] + ck<P>(CK_A64) * k4[i] + ck<P>(CK_A65) * k5[i]);
-			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
@@ -539,7 +577,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 		P evn[AtLeastOne<NE>::value];
 		if (NE > 0)
 		{
-			Sys::EventFunction(gid, NTG, evn, s.t + dt, dt, s.td, xn, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::EventFunction(gid, NTG, evn, s.t + dt, dt, s.td, xn, s.cpar, p_par, p_pari, s.acc, s.acci);
 			if (update && !terminate)
 			{
 				P dt_event = dt;
@@ -575,7 +613,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			#pragma unroll
 			for (int i = 0; i < SD; i++) s.x[i] = xn[i];
 
-			Sys::ActionAfterSuccessfulTimeStep(gid, NTG, user_terminate, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+			Sys::ActionAfterSuccessfulTimeStep(gid, NTG, user_terminate, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 
 			if (NE > 0)
 			{
@@ -585,9 +623,9 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 					const P et = a.EventTolerance[i];
 					if (((s.ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) ||
 					    ((s.ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
-						Sys::ActionAfterEventDetection(gid, NTG, i, user_terminate, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+						Sys::ActionAfterEventDetection(gid, NTG, i, user_terminate, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 				}
-				Sys::EventFunction(gid, NTG, s.ev, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
+				Sys::EventFunction(gid, NTG, s.ev, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 			}
 
 			if (DENSE)   // DenseOutput.cuh:41-58 then :6-37
@@ -610,27 +648,74 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 
 			if (end_reached || user_terminate == 1) terminate = true;
 		}
+		return terminate;
+	};
 
-		// ---- end of the phase for this instance (Solver.cuh:398-435) ---------------------------
-		if (terminate)
+	// ---- end of the phase for this instance (Solver.cuh:398-435) ------------------------------------
+	auto store = [&](const int inst, P& dt)
+	{
+		const int gid = inst + a.InstanceOffset;
+		Sys::Finalization(gid, NTG, s.dense_index, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
+		#pragma unroll
+		for (int i = 0; i < 2; i++)   a.TimeDomain[inst + i * stride] = s.td[i];
+		#pragma unroll
+		for (int i = 0; i < SD; i++)  a.ActualState[inst + i * stride] = s.x[i];
+		#pragma unroll
+		for (int i = 0; i < NCP; i++) a.ControlParameters[inst + i * stride] = s.cpar[i];
+		#pragma unroll
+		for (int i = 0; i < NA; i++)  a.Accessories[inst + i * stride] = s.acc[i];
+		#pragma unroll
+		for (int i = 0; i < NIA; i++) a.IntegerAccessories[inst + i * stride] = s.acci[i];
+		a.ActualTime[inst] = s.t;
+		if (DENSE) a.DenseOutputIndex[inst] = s.dense_index;
+		a.StepsAttempted[inst] += s.attempted;
+		a.StepsAccepted[inst]  += s.accepted;
+	};
+
+	if (!REFILL)
+	{
+		// direct mapping: thread i integrates instance i; the step loop is the whole kernel
+		const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+		if (inst >= a.Active) return;
+		load(inst);
+		P dt;
+		while (!step(inst, dt)) { }
+		store(inst, dt);
+		return;
+	}
+
+	// persistent warps
+	int  inst  = 0;
+	bool alive = false;
+	bool queue_empty = false;       // warp-uniform
+	for (;;)
+	{
+		bool take = false;
+		// ---- warp ballot: refill the idle lanes together once there are enough of them -------
+		const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+		if (idle != 0u)
 		{
-			Sys::Finalization(gid, NTG, s.dense_index, s.t, dt, s.td, s.x, s.cpar, s_par, s_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < 2; i++)   a.TimeDomain[inst + i * stride] = s.td[i];
-			#pragma unroll
-			for (int i = 0; i < SD; i++)  a.ActualState[inst + i * stride] = s.x[i];
-			#pragma unroll
-			for (int i = 0; i < NCP; i++) a.ControlParameters[inst + i * stride] = s.cpar[i];
-			#pragma unroll
-			for (int i = 0; i < NA; i++)  a.Accessories[inst + i * stride] = s.acc[i];
-			#pragma unroll
-			for (int i = 0; i < NIA; i++) a.IntegerAccessories[inst + i * stride] = s.acci[i];
-			a.ActualTime[inst] = s.t;
-			if (DENSE) a.DenseOutputIndex[inst] = s.dense_index;
-			a.StepsAttempted[inst] += s.attempted;
-			a.StepsAccepted[inst]  += s.accepted;
-			alive = false;
+			const int n = __popc(idle);
+			if (!queue_empty && (n >= a.RefillThreshold || n == 32))
+			{
+				const int lane = threadIdx.x & 31;
+				const int leader = __ffs(idle) - 1;
+				unsigned base = 0;
+				if (lane == leader) base = atomicAdd(a.WorkQueue, (unsigned)n);
+				base = __shfl_sync(0xffffffffu, base, leader);
+				if (!alive)
+				{
+					inst = (int)(base + (unsigned)__popc(idle & ((1u << lane) - 1u)));
+					take = inst < a.Active;
+				}
+				queue_empty = (base + (unsigned)n) >= (unsigned)a.Active;
+			}
+			if (idle == 0xffffffffu && !__any_sync(0xffffffffu, take)) break;
 		}
+		if (take) { load(inst); alive = true; }
+		if (!alive) continue;
+		P dt;
+		if (step(inst, dt)) { store(inst, dt); alive = false; }
 	}
 }
 
@@ -651,7 +736,7 @@ struct PerThreadLauncher
 		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL, MINB>;
 		int block = L->ThreadsPerBlock;
 		if (block < 32) block = 32;
-		if (block > kMaxThreadsPerBlock) block = kMaxThreadsPerBlock;
+		if (block > launch_bound_threads(MINB)) block = launch_bound_threads(MINB);
 		block = (block / 32) * 32;
 		const int active = args.Active;
 		if (active <= 0) return cudaSuccess;
