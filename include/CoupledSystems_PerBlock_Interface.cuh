@@ -19,7 +19,8 @@
 //   * SharedGlobalVariables / SharedCouplingMatrices are accepted and ignored: both always live in shared memory;
 //   * device-side warnings are printed only after SolverOption(DeviceMessages, 1);
 //   * extra options DeviceMessages / TensorCoreCoupling and the StepCounters() accessor;
-//   * double precision only (the reference's tutorials use double; a float instantiation is rejected at compile time).
+//   * Precision = double or float; the tensor-core coupling exists in double only (a float instantiation sums the coupling
+//     in FP32 on the scalar path).
 #ifndef COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
 #define COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
 
@@ -130,7 +131,7 @@ template <int NS, int UPS, int UD, int TPB, int SPB, int NC, int CBW, int CCI, i
           int NE, int NDO, Algorithms Algorithm, class Precision>
 class ProblemSolver
 {
-	static_assert(std::is_same<Precision, double>::value, "the coupled module is built for double precision");
+	static_assert(std::is_same<Precision, double>::value || std::is_same<Precision, float>::value, "Precision is double or float");
 
 	mpgos_coupled_solver* Handle;
 	// pinned host mirrors owned by the runtime (reference: h_* members, CP/Interface.cuh:177-194); unit scope is stored
@@ -261,7 +262,7 @@ public:
 		h_CouplingStrength = Mirror<Precision>(CouplingStrength);  h_CouplingIndex = Mirror<int>(CouplingIndex);
 		h_DenseOutputIndex = Mirror<int>(DenseIndex);  h_DenseOutputTimeInstances = Mirror<Precision>(DenseTime);  h_DenseOutputStates = Mirror<Precision>(DenseState);
 		std::cout << "Object for Parameters scan is successfully created on device " << Device << " (B200-native coupled solver, " << NS << " systems x "
-		          << UPS << " units, " << (Algorithm == RK4 ? "RK4" : "RKCK45") << ", double)" << std::endl << std::endl;
+		          << UPS << " units, " << (Algorithm == RK4 ? "RK4" : "RKCK45") << (sizeof(Precision) == 8 ? ", double)" : ", float)") << std::endl << std::endl;
 	}
 
 	~ProblemSolver() { mpgos_coupled_destroy(Handle); std::cout << "Object for Parameters scan is deleted! Every memory have been deallocated!" << std::endl << std::endl; }

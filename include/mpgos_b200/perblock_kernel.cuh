@@ -62,17 +62,18 @@ __host__ __device__ constexpr int packed_matrix_elements(int UPS, int NC, int CB
 
 // y = a^(-1/n), n = 5 (accept) or 4, for a = max_i err_i/tol_i of a whole system: the same division-free Newton map
 // as ratio_root_fast with tol = 1, err = a.
-__device__ __forceinline__ double inverse_root_fast(double a, bool accept)
+template <class P>
+__device__ __forceinline__ P inverse_root_fast(P a, bool accept)
 {
 	const float inv = accept ? 0.2f : 0.25f;
-	double y = (double)sfu_ex2(-sfu_lg2(__double2float_rn(a)) * inv);
-	const double rn = accept ? 0.2 : 0.25;
+	P y = (P)sfu_ex2(-sfu_lg2(Num<P>::narrow(a)) * inv);
+	const P rn = accept ? P(0.2) : P(0.25);
 	#pragma unroll
-	for (int it = 0; it < 2; it++)
+	for (int it = 0; it < (sizeof(P) == 8 ? 2 : 1); it++)
 	{
-		const double y2 = y * y, y4 = y2 * y2;
-		const double yn = accept ? y4 * y : y4;
-		y = fma(y * fma(-a, yn, 1.0), rn, y);
+		const P y2 = y * y, y4 = y2 * y2;
+		const P yn = accept ? y4 * y : y4;
+		y = fma(y * fma(-a, yn, P(1.0)), rn, y);
 	}
 	return y;
 }
@@ -489,7 +490,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			P mult;
 			const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 <= q < 2^30 (and q > 1e-30: the reference's initial 1e30)
 			if (finite && qt < Num<P>::kSpan)
-				mult = P(0.8) * inverse_root_fast(q, update);
+				mult = P(0.8) * inverse_root_fast<P>(q, update);
 			else if (MMA && !have)
 				mult = P(1.0);                                      // a slot without a system: nothing to control
 			else

@@ -6,11 +6,12 @@
 namespace mpgos_b200 {
 using namespace builtin;
 
-#define COUPLED_ENTRY(NAME, S, UPS, CBW, CCI, ALG, D)                                                                                      \
-	{ NAME, UPS, CBW, CCI, S<double>::UD, S<double>::NC, S<double>::NUP, S<double>::NSP, S<double>::NGP, S<double>::NiGP, S<double>::NUA,     \
-	  S<double>::NiUA, S<double>::NSA, S<double>::NiSA, S<double>::NE, ALG, D,                                                             \
-	  &PerBlockLauncher<S<double>, double, UPS, S<double>::UD, S<double>::NC, CBW, CCI, S<double>::NUP, S<double>::NSP, S<double>::NGP,    \
-	                    S<double>::NiGP, S<double>::NUA, S<double>::NiUA, S<double>::NSA, S<double>::NiSA, S<double>::NE, D, ALG>::launch }
+#define COUPLED_ENTRY_P(NAME, S, P, UPS, CBW, CCI, ALG, D)                                                                    \
+	{ NAME, UPS, CBW, CCI, S<P>::UD, S<P>::NC, S<P>::NUP, S<P>::NSP, S<P>::NGP, S<P>::NiGP, S<P>::NUA,                         \
+	  S<P>::NiUA, S<P>::NSA, S<P>::NiSA, S<P>::NE, ALG, (int)sizeof(P), D,                                                     \
+	  &PerBlockLauncher<S<P>, P, UPS, S<P>::UD, S<P>::NC, CBW, CCI, S<P>::NUP, S<P>::NSP, S<P>::NGP,                           \
+	                    S<P>::NiGP, S<P>::NUA, S<P>::NiUA, S<P>::NSA, S<P>::NiSA, S<P>::NE, D, ALG>::launch }
+#define COUPLED_ENTRY(NAME, S, UPS, CBW, CCI, ALG, D) COUPLED_ENTRY_P(NAME, S, double, UPS, CBW, CCI, ALG, D)
 
 static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 8, 0, 0, kAlgRKCK45, false),
@@ -26,6 +27,12 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 1, kAlgRK4, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 32, 0, 0, kAlgRKCK45, true),      // full matrices, 2 couplings, events: the tensor-core path with everything on
+	// FP32 instantiations (scalar coupling; the tensor-core product exists in FP64 only)
+	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 16, 0, 0, kAlgRKCK45, false),
+	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 64, 0, 0, kAlgRKCK45, false),
+	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 64, 0, 0, kAlgRK4, false),
+	COUPLED_ENTRY_P("duffing_ring", DuffingRing, float, 14, 1, 1, kAlgRKCK45, true),
+	COUPLED_ENTRY_P("duffing_ring", DuffingRing, float, 14, 0, 0, kAlgRKCK45, true),
 };
 const CoupledBuiltinEntry* builtin_entries_coupled(int* n) { *n = (int)(sizeof(kEntries) / sizeof(kEntries[0])); return kEntries; }
 }

@@ -26,7 +26,7 @@ struct CoupledBuiltinEntry
 {
 	const char* name;
 	int UPS, CBW, CCI, UD, NC, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE;
-	int Algorithm;
+	int Algorithm, PrecisionBytes;
 	bool Dense;
 	mpgos_coupled_launcher launcher;
 };

@@ -69,14 +69,14 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 	    d.NUA < 0 || d.NiUA < 0 || d.NSA < 0 || d.NiSA < 0 || d.NE < 0 || d.NDO < 0)
 		return CFAIL(MPGOS_ERR_ARGUMENT, "invalid sizes in coupled descriptor");
 	if (d.Algorithm != MPGOS_RK4 && d.Algorithm != MPGOS_RKCK45) return CFAIL(MPGOS_ERR_ARGUMENT, "unknown algorithm %d", d.Algorithm);
-	if (d.PrecisionBytes != 8) return CFAIL(MPGOS_ERR_ARGUMENT, "the coupled module is built for double precision only");
+	if (d.PrecisionBytes != 8 && d.PrecisionBytes != 4) return CFAIL(MPGOS_ERR_ARGUMENT, "PrecisionBytes must be 8 (double) or 4 (float), got %d", d.PrecisionBytes);
 	if (2 * d.CBW + 1 > d.UPS) return CFAIL(MPGOS_ERR_ARGUMENT, "coupling bandwidth %d too wide for %d units", d.CBW, d.UPS);
 	int ndev = 0;
 	CUDA_TRY(cudaGetDeviceCount(&ndev));
 	if (d.Device < 0 || d.Device >= ndev) return CFAIL(MPGOS_ERR_ARGUMENT, "device %d not present (%d devices)", d.Device, ndev);
 	CUDA_TRY(cudaSetDevice(d.Device));
 
-	const size_t P = 8, NS = d.NS, NU = NS * d.UPS;
+	const size_t P = (size_t)d.PrecisionBytes, NS = d.NS, NU = NS * d.UPS;
 	size_t elems[MPGOS_CVAR_COUNT] = {0};
 	elems[MPGOS_CVAR_TimeDomain] = 2 * NS;  elems[MPGOS_CVAR_ActualTime] = NS;  elems[MPGOS_CVAR_ActualState] = NU * d.UD;
 	elems[MPGOS_CVAR_UnitParameters] = NU * d.NUP;  elems[MPGOS_CVAR_SystemParameters] = NS * d.NSP;  elems[MPGOS_CVAR_GlobalParameters] = d.NGP;
@@ -169,7 +169,8 @@ int mpgos_coupled_set_matrix_entry(mpgos_coupled_solver* s, int k, int row, int 
 	const long idx = packed_index(d, k, row, col);
 	if (idx < 0) return CFAIL(MPGOS_ERR_BOUNDS, "Coupling Matrix Shifted Diagonal of (%d,%d) outside 0-%d", row, col, (d.CBW > 0 ? 2 * d.CBW + 1 : d.UPS) - 1);
 	s->original_matrix[(size_t)row + (size_t)col * d.UPS + (size_t)k * d.UPS * d.UPS] = value;
-	static_cast<double*>(s->var[MPGOS_CVAR_CouplingMatrix].host)[idx] = value;
+	if (d.PrecisionBytes == 8) static_cast<double*>(s->var[MPGOS_CVAR_CouplingMatrix].host)[idx] = value;
+	else                       static_cast<float*>(s->var[MPGOS_CVAR_CouplingMatrix].host)[idx] = (float)value;
 	return MPGOS_OK;
 }
 
@@ -361,16 +362,22 @@ int mpgos_coupled_builtin_desc(const char* system, int ups, int cbw, int cci, mp
 	return CFAIL(MPGOS_ERR_UNKNOWN_SYSTEM, "no built-in coupled system '%s' with UPS=%d CBW=%d CCI=%d", system, ups, cbw, cci);
 }
 
-mpgos_coupled_launcher mpgos_coupled_builtin_launcher(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output)
+mpgos_coupled_launcher mpgos_coupled_builtin_launcher_p(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output, int precision_bytes)
 {
 	if (!system) return nullptr;
 	int n = 0;
 	const mpgos_b200::CoupledBuiltinEntry* e = mpgos_b200::builtin_entries_coupled(&n);
 	for (int i = 0; i < n; i++)
-		if (!std::strcmp(e[i].name, system) && e[i].UPS == ups && e[i].CBW == cbw && e[i].CCI == cci && e[i].Algorithm == algorithm && e[i].Dense == (dense_output != 0))
+		if (!std::strcmp(e[i].name, system) && e[i].UPS == ups && e[i].CBW == cbw && e[i].CCI == cci && e[i].Algorithm == algorithm && e[i].Dense == (dense_output != 0) &&
+		    e[i].PrecisionBytes == precision_bytes)
 			return e[i].launcher;
-	CFAIL(MPGOS_ERR_UNKNOWN_SYSTEM, "no built-in coupled launcher for '%s' UPS=%d CBW=%d CCI=%d algorithm %d dense %d", system, ups, cbw, cci, algorithm, dense_output);
+	CFAIL(MPGOS_ERR_UNKNOWN_SYSTEM, "no built-in coupled launcher for '%s' UPS=%d CBW=%d CCI=%d algorithm %d dense %d precision %d bytes", system, ups, cbw, cci, algorithm, dense_output, precision_bytes);
 	return nullptr;
+}
+
+mpgos_coupled_launcher mpgos_coupled_builtin_launcher(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output)
+{
+	return mpgos_coupled_builtin_launcher_p(system, ups, cbw, cci, algorithm, dense_output, 8);
 }
 
 } // extern "C"

@@ -58,7 +58,7 @@ COUPLED_ABI_SYMBOLS = (
     "mpgos_coupled_set_option", "mpgos_coupled_set_option_indexed", "mpgos_coupled_sync_h2d", "mpgos_coupled_sync_d2h", "mpgos_coupled_solve",
     "mpgos_coupled_solve_timed", "mpgos_coupled_insert_sync_point", "mpgos_coupled_sync_solver", "mpgos_coupled_sync_device",
     "mpgos_coupled_read_step_counters", "mpgos_coupled_reset_step_counters", "mpgos_coupled_save_state", "mpgos_coupled_restore_state",
-    "mpgos_coupled_stream", "mpgos_coupled_builtin_desc", "mpgos_coupled_builtin_launcher",
+    "mpgos_coupled_stream", "mpgos_coupled_builtin_desc", "mpgos_coupled_builtin_launcher", "mpgos_coupled_builtin_launcher_p",
 )
 
 
@@ -95,22 +95,25 @@ def _bind(lib):
     lib.mpgos_coupled_builtin_desc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_CDesc)]
     lib.mpgos_coupled_builtin_launcher.restype = v
     lib.mpgos_coupled_builtin_launcher.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.mpgos_coupled_builtin_launcher_p.restype = v
+    lib.mpgos_coupled_builtin_launcher_p.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     _BOUND = True
 
 
 class CoupledProblemSolver:
-    """``ProblemSolver<NS,UPS,UD,TPB,SPB,NC,CBW,CCI,NUP,...,Algorithm,double>`` for a built-in coupled system."""
+    """``ProblemSolver<NS,UPS,UD,TPB,SPB,NC,CBW,CCI,NUP,...,Algorithm,Precision>`` for a built-in coupled system."""
 
     def __init__(self, system: str, NS: int, UPS: int, CBW: int = 0, CCI: int = 0, NDO: int = 0, Algorithm: int = 1,
-                 Device: int = 0, TPB: int = 64, SPB: int = 1, SystemOffset: int = 0):
+                 Device: int = 0, TPB: int = 64, SPB: int = 1, SystemOffset: int = 0, Precision=np.float64):
         self._lib = lib = load_library()
         _bind(lib)
         self._h = None
         d = _CDesc()
         _check(lib, lib.mpgos_coupled_builtin_desc(system.encode(), UPS, CBW, CCI, C.byref(d)))
-        d.NS, d.NDO, d.Algorithm, d.PrecisionBytes, d.Device, d.TPB, d.SPB, d.SystemOffset = NS, NDO, int(Algorithm), 8, Device, TPB, SPB, SystemOffset
+        self.dtype = np.dtype(Precision)
+        d.NS, d.NDO, d.Algorithm, d.PrecisionBytes, d.Device, d.TPB, d.SPB, d.SystemOffset = NS, NDO, int(Algorithm), self.dtype.itemsize, Device, TPB, SPB, SystemOffset
         self.desc = d
-        self._launcher = lib.mpgos_coupled_builtin_launcher(system.encode(), UPS, CBW, CCI, int(Algorithm), int(NDO > 0))
+        self._launcher = lib.mpgos_coupled_builtin_launcher_p(system.encode(), UPS, CBW, CCI, int(Algorithm), int(NDO > 0), self.dtype.itemsize)
         if not self._launcher:
             raise MpgosError(lib.mpgos_last_error().decode())
         h = C.c_void_p()
@@ -146,7 +149,7 @@ class CoupledProblemSolver:
         p = self._lib.mpgos_coupled_host_ptr(self._h, variable, C.byref(n))
         V = CoupledVariables
         ints = variable in (V.IntegerGlobalParameters, V.IntegerUnitAccessories, V.IntegerSystemAccessories, V.CouplingIndex, V.DenseIndex)
-        dt = np.dtype(np.int32 if ints else np.float64)
+        dt = np.dtype(np.int32) if ints else self.dtype
         if n.value == 0:
             arr = np.zeros(0, dt)
         else:
@@ -278,7 +281,7 @@ def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device:
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
     with CoupledProblemSolver(wl.name, b.NS, sh.UPS, CBW=sh.CBW, CCI=sh.CCI, NDO=sh.NDO, Algorithm=sh.Algorithm, Device=device,
-                              TPB=sh.TPB, SPB=sh.SPB) as ps:
+                              TPB=sh.TPB, SPB=sh.SPB, Precision=sh.dtype) as ps:
         apply_coupled_workload(ps, wl, b)
         if tensor_core_coupling is not None:
             ps.SolverOption(CoupledOptions.TensorCoreCoupling, tensor_core_coupling)

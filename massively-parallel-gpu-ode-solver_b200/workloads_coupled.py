@@ -37,6 +37,7 @@ class CoupledShape:
     Algorithm: int = RKCK45
     TPB: int = 64       # the reference's launch hints (ours chooses its own block shape)
     SPB: int = 1
+    dtype: type = np.float64
 
 
 @dataclasses.dataclass
@@ -76,7 +77,7 @@ class CoupledBuffers:
                   "DenseIndex", "DenseTime", "DenseState")
 
     def __init__(self, sh: CoupledShape, NS: int):
-        f, i = np.float64, np.int32
+        f, i = np.dtype(sh.dtype), np.int32
         self.NS = NS
         self.TimeDomain = np.zeros((2, NS), f)
         self.ActualState = np.zeros((sh.UD, NS, sh.UPS), f)
@@ -159,11 +160,11 @@ def bubble_geometry(UPS: int, seed: int = 20200818):
 
 
 def bubble_ensemble(NS: int = 1 << 16, UPS: int = 64, algorithm: int = RKCK45, phases: int = 1, ndo: int = 0,
-                    amplitude=(0.0, 5.0), frequency_khz: float = 1000.0) -> CoupledWorkload:
+                    amplitude=(0.0, 5.0), frequency_khz: float = 1000.0, dtype=np.float64) -> CoupledWorkload:
     """C5: Tutorials_CoupledSystems_PerBlock/T2_BubbleEnsemble/BubbleEnsemble.cu:88-97, 225-353 -- NS systems of UPS
     coupled Keller-Miksis bubbles, pressure amplitude = Linspace(0, 5, NS) bar, full dense coupling matrix
     A[r][c] = RE_c^3 / RE_r^2 / dist_um shared by all systems, coupling strength 1 into component 1."""
-    sh = CoupledShape(UPS=UPS, UD=2, NC=1, NUP=21, NDO=ndo, Algorithm=algorithm, TPB=UPS, SPB=1)
+    sh = CoupledShape(UPS=UPS, UD=2, NC=1, NUP=21, NDO=ndo, Algorithm=algorithm, TPB=UPS, SPB=1, dtype=dtype)
     b = CoupledBuffers(sh, NS)
     radii, pos, dist = bubble_geometry(UPS)
     PI = 3.14159265358979323846
@@ -206,17 +207,20 @@ def bubble_ensemble(NS: int = 1 << 16, UPS: int = 64, algorithm: int = RKCK45, p
     b.CouplingMatrix[0] = A.T                                                    # stored [col, row]
     opt = CoupledOptions(InitialTimeStep=1e-3, MinimumTimeStep=1e-13,
                          RelativeTolerance=np.array([1e-10, 1e-8]), AbsoluteTolerance=np.array([1e-10, 1e-8]))
+    if np.dtype(dtype) == np.float32:      # the reference ships no single-precision settings: tolerances a float can resolve (our choice)
+        opt = CoupledOptions(InitialTimeStep=1e-3, MinimumTimeStep=1e-7,
+                             RelativeTolerance=np.array([1e-5, 1e-5]), AbsoluteTolerance=np.array([1e-5, 1e-5]))
     flops = 6 * UPS * (48 + 7 + 2 * UPS + 3) + UPS * 110 + 9 + UPS * 6
     return CoupledWorkload("bubble_ensemble", sh, opt, b, phases, flops, "T2_BubbleEnsemble amplitude sweep")
 
 
 def duffing_ring(NS: int = 9, CBW: int = 1, CCI: int = 1, algorithm: int = RKCK45, phases: int = 1, ndo: int = 100,
-                 TPB: int = 32, SPB: int = 3, UPS: int = 14) -> CoupledWorkload:
+                 TPB: int = 32, SPB: int = 3, UPS: int = 14, dtype=np.float64) -> CoupledWorkload:
     """Tutorials_CoupledSystems_PerBlock/T1_RingOfDuffingOscillators/RingOfDuffingOscillators.cu:79-106, 215-300 -- rings
     of 14 Duffing oscillators, two coupling terms through a banded / circulant matrix, one event per unit (second
     local maximum of any unit ends the phase), system accessories tracking min/max dt, dense output."""
     sh = CoupledShape(UPS=UPS, UD=2, NC=2, CBW=CBW, CCI=CCI, NUP=3, NGP=1, NUA=3, NiUA=1, NSA=2, NiSA=1, NE=1, NDO=ndo,
-                      Algorithm=algorithm, TPB=TPB, SPB=SPB)
+                      Algorithm=algorithm, TPB=TPB, SPB=SPB, dtype=dtype)
     b = CoupledBuffers(sh, NS)
     n = int(math.ceil(math.sqrt(NS)))
     icx, icy = _linspace(-8.0, 8.0, n), _linspace(-20.0, 40.0, n)
@@ -245,6 +249,9 @@ def duffing_ring(NS: int = 9, CBW: int = 1, CCI: int = 1, algorithm: int = RKCK4
     b.CouplingMatrix[1] = A.T
     opt = CoupledOptions(InitialTimeStep=1e-2, RelativeTolerance=np.array([1e-8, 1e-8]), AbsoluteTolerance=np.array([1e-8, 1e-8]),
                          EventDirection=np.array([-1], np.int32), DenseOutputMinimumTimeStep=1e-6)
+    if np.dtype(dtype) == np.float32:
+        opt = dataclasses.replace(opt, RelativeTolerance=np.array([1e-5, 1e-5]), AbsoluteTolerance=np.array([1e-5, 1e-5]), MinimumTimeStep=1e-6,
+                                  EventTolerance=np.array([1e-4]), DenseOutputMinimumTimeStep=1e-4)
     return CoupledWorkload("duffing_ring", sh, opt, b, phases, 0, "T1_RingOfDuffingOscillators")
 
 

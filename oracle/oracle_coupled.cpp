@@ -111,44 +111,56 @@ int run_all(const oracle_coupled_buffers* b, const oracle_coupled_options* o, in
 	return 0;
 }
 
-template <class Sys>
+template <class Sys, class P>
 int dispatch(int algorithm, int ndo, const oracle_coupled_buffers* b, const oracle_coupled_options* o, oracle_coupled_shape* shape)
 {
 	if (shape)
 	{
 		shape->UPS = Sys::UPS; shape->UD = Sys::UD; shape->NC = Sys::NC; shape->CBW = Sys::CBW; shape->CCI = Sys::CCI; shape->NUP = Sys::NUP; shape->NSP = Sys::NSP;
 		shape->NGP = Sys::NGP; shape->NiGP = Sys::NiGP; shape->NUA = Sys::NUA; shape->NiUA = Sys::NiUA; shape->NSA = Sys::NSA; shape->NiSA = Sys::NiSA; shape->NE = Sys::NE;
-		shape->NDO = ndo; shape->Algorithm = algorithm; shape->Precision = 8;
+		shape->NDO = ndo; shape->Algorithm = algorithm; shape->Precision = (int)sizeof(P);
 		return 0;
 	}
-	return algorithm == ALG_RK4 ? run_all<Sys, double, ALG_RK4>(b, o, ndo) : run_all<Sys, double, ALG_RKCK45>(b, o, ndo);
+	return algorithm == ALG_RK4 ? run_all<Sys, P, ALG_RK4>(b, o, ndo) : run_all<Sys, P, ALG_RKCK45>(b, o, ndo);
 }
 
+// P = float instantiates the same restatement in single precision, with the system definitions' double literals
+// promoting as they do in the reference's own float instantiation (pinned against the reference's ring kernel in float,
+// tests/test_oracle_coupled.py; the reference's bubble tutorial does not compile with Precision = float).
+template <class P>
 int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo, const oracle_coupled_buffers* b, const oracle_coupled_options* o, oracle_coupled_shape* shape)
 {
 	if (!std::strcmp(system, "bubble_ensemble"))
 	{
-		if (ups == 8)  return dispatch<BubbleEnsemble<double, 8> >(algorithm, ndo, b, o, shape);
-		if (ups == 16) return dispatch<BubbleEnsemble<double, 16> >(algorithm, ndo, b, o, shape);
-		if (ups == 32) return dispatch<BubbleEnsemble<double, 32> >(algorithm, ndo, b, o, shape);
-		if (ups == 64) return dispatch<BubbleEnsemble<double, 64> >(algorithm, ndo, b, o, shape);
-		if (ups == 128) return dispatch<BubbleEnsemble<double, 128> >(algorithm, ndo, b, o, shape);
+		if (ups == 8)  return dispatch<BubbleEnsemble<P, 8>, P>(algorithm, ndo, b, o, shape);
+		if (ups == 16) return dispatch<BubbleEnsemble<P, 16>, P>(algorithm, ndo, b, o, shape);
+		if (ups == 32) return dispatch<BubbleEnsemble<P, 32>, P>(algorithm, ndo, b, o, shape);
+		if (ups == 64) return dispatch<BubbleEnsemble<P, 64>, P>(algorithm, ndo, b, o, shape);
+		if (ups == 128) return dispatch<BubbleEnsemble<P, 128>, P>(algorithm, ndo, b, o, shape);
 	}
-	if (!std::strcmp(system, "duffing_ring") && ups == 32 && cbw == 0 && cci == 0) return dispatch<DuffingRing<double, 32, 0, 0> >(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 32 && cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 32, 0, 0>, P>(algorithm, ndo, b, o, shape);
 	if (!std::strcmp(system, "duffing_ring") && ups == 14)
 	{
-		if (cbw == 1 && cci == 1) return dispatch<DuffingRing<double, 14, 1, 1> >(algorithm, ndo, b, o, shape);
-		if (cbw == 1 && cci == 0) return dispatch<DuffingRing<double, 14, 1, 0> >(algorithm, ndo, b, o, shape);
-		if (cbw == 0 && cci == 1) return dispatch<DuffingRing<double, 14, 0, 1> >(algorithm, ndo, b, o, shape);
-		if (cbw == 0 && cci == 0) return dispatch<DuffingRing<double, 14, 0, 0> >(algorithm, ndo, b, o, shape);
+		if (cbw == 1 && cci == 1) return dispatch<DuffingRing<P, 14, 1, 1>, P>(algorithm, ndo, b, o, shape);
+		if (cbw == 1 && cci == 0) return dispatch<DuffingRing<P, 14, 1, 0>, P>(algorithm, ndo, b, o, shape);
+		if (cbw == 0 && cci == 1) return dispatch<DuffingRing<P, 14, 0, 1>, P>(algorithm, ndo, b, o, shape);
+		if (cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 14, 0, 0>, P>(algorithm, ndo, b, o, shape);
 	}
-	if (!std::strcmp(system, "swing_ring") && ups == 40 && cbw == 2 && cci == 0) return dispatch<SwingRing<double, 40, 2, 0> >(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "swing_ring") && ups == 40 && cbw == 2 && cci == 0) return dispatch<SwingRing<P, 40, 2, 0>, P>(algorithm, ndo, b, o, shape);
 	return 1;
 }
 } // namespace
 
 extern "C" int oracle_coupled_query_shape(const char* system, int ups, int cbw, int cci, int algorithm, int ndo, oracle_coupled_shape* shape)
-{ return route(system, ups, cbw, cci, algorithm, ndo, nullptr, nullptr, shape); }
+{ return route<double>(system, ups, cbw, cci, algorithm, ndo, nullptr, nullptr, shape); }
 
 extern "C" int oracle_coupled_run(const char* system, int ups, int cbw, int cci, int algorithm, int ndo, const oracle_coupled_buffers* b, const oracle_coupled_options* o)
-{ return route(system, ups, cbw, cci, algorithm, ndo, b, o, nullptr); }
+{ return route<double>(system, ups, cbw, cci, algorithm, ndo, b, o, nullptr); }
+
+// the same with the precision stated in bytes (8 or 4)
+extern "C" int oracle_coupled_run_p(const char* system, int ups, int cbw, int cci, int algorithm, int ndo, int precision, const oracle_coupled_buffers* b, const oracle_coupled_options* o)
+{
+	if (precision == 8) return route<double>(system, ups, cbw, cci, algorithm, ndo, b, o, nullptr);
+	if (precision == 4) return route<float>(system, ups, cbw, cci, algorithm, ndo, b, o, nullptr);
+	return 2;
+}

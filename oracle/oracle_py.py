@@ -195,6 +195,8 @@ class _CBuffers(C.Structure):
 
 def _cpack(wl, b, phases, host_threads):
     o = wl.options.resolved(wl.shape, b.NS)
+    dt = np.dtype(getattr(wl.shape, "dtype", np.float64))
+    o.RelativeTolerance, o.AbsoluteTolerance, o.EventTolerance = (np.ascontiguousarray(a, dt) for a in (o.RelativeTolerance, o.AbsoluteTolerance, o.EventTolerance))
     att, acc = np.zeros(b.NS, np.int64), np.zeros(b.NS, np.int64)
     keep = [o.RelativeTolerance, o.AbsoluteTolerance, o.EventTolerance, o.EventDirection]
     cb = _CBuffers(b.NS, _ptr(b.TimeDomain), _ptr(b.ActualState), _ptr(b.ActualTime), _ptr(b.UnitParameters), _ptr(b.SystemParameters),
@@ -207,10 +209,12 @@ def _cpack(wl, b, phases, host_threads):
     return cb, co, att, acc, keep
 
 
-def _ccheck(s, wl):
+def _ccheck(s, wl, check_precision=True):
     sh = wl.shape
     got = (s.UPS, s.UD, s.NC, s.CBW, s.CCI, s.NUP, s.NSP, s.NGP, s.NiGP, s.NUA, s.NiUA, s.NSA, s.NiSA, s.NE, s.NDO, s.Algorithm)
     want = (sh.UPS, sh.UD, sh.NC, sh.CBW, sh.CCI, sh.NUP, sh.NSP, sh.NGP, sh.NiGP, sh.NUA, sh.NiUA, sh.NSA, sh.NiSA, sh.NE, sh.NDO, sh.Algorithm)
+    if check_precision and s.Precision != np.dtype(getattr(sh, "dtype", np.float64)).itemsize:
+        raise ValueError(f"coupled checker library precision {s.Precision} bytes does not match the workload's")
     if got != want:
         raise ValueError(f"coupled checker library shape {got} does not match workload shape {want}")
 
@@ -229,10 +233,11 @@ def run_coupled_oracle(wl, buffers=None, phases=None, host_threads: int = 1, fas
     rc = lib.oracle_coupled_query_shape(wl.name.encode(), sh.UPS, sh.CBW, sh.CCI, sh.Algorithm, sh.NDO, C.byref(s))
     if rc != 0:
         raise KeyError(f"coupled oracle has no system {wl.name!r} with UPS={sh.UPS} CBW={sh.CBW} CCI={sh.CCI}")
-    _ccheck(s, wl)
+    _ccheck(s, wl, check_precision=False)         # the shape query answers for double; the run call states the precision
     out = (buffers if buffers is not None else wl.buffers).copy()
     cb, co, att, acc, _keep = _cpack(wl, out, wl.phases if phases is None else phases, host_threads)
-    rc = lib.oracle_coupled_run(wl.name.encode(), sh.UPS, sh.CBW, sh.CCI, sh.Algorithm, sh.NDO, C.byref(cb), C.byref(co))
+    rc = lib.oracle_coupled_run_p(wl.name.encode(), sh.UPS, sh.CBW, sh.CCI, sh.Algorithm, sh.NDO, np.dtype(getattr(sh, "dtype", np.float64)).itemsize,
+                                  C.byref(cb), C.byref(co))
     if rc != 0:
         raise RuntimeError(f"oracle_coupled_run failed: {rc}")
     return out, att, acc

@@ -16,7 +16,10 @@
 #include REF_SYSDEF
 #include "CoupledSolver.patched.cuh"          // the reference kernels (sed-patched copy in oracle/_ref, see Makefile)
 
-typedef double P;
+#ifndef REF_PRECISION
+#define REF_PRECISION double
+#endif
+typedef REF_PRECISION P;
 #define TARGS REF_NS, REF_UPS, REF_UD, REF_TPB, REF_SPB, REF_NC, REF_CBW, REF_CCI, REF_NUP, REF_NSP, REF_NGP, REF_NiGP, REF_NUA, REF_NiUA, REF_NSA, REF_NiSA, REF_NE, REF_NDO, REF_ALGO, P
 
 static void launch(Struct_ThreadConfiguration tc, Struct_GlobalVariables<P> g, Struct_SharedMemoryUsage sm, Struct_SolverOptions<P> so)
@@ -40,7 +43,7 @@ static void launch(Struct_ThreadConfiguration tc, Struct_GlobalVariables<P> g, S
 extern "C" void ref_coupled_shape(oracle_coupled_shape* s)
 {
 	s->UPS = REF_UPS; s->UD = REF_UD; s->NC = REF_NC; s->CBW = REF_CBW; s->CCI = REF_CCI; s->NUP = REF_NUP; s->NSP = REF_NSP; s->NGP = REF_NGP; s->NiGP = REF_NiGP;
-	s->NUA = REF_NUA; s->NiUA = REF_NiUA; s->NSA = REF_NSA; s->NiSA = REF_NiSA; s->NE = REF_NE; s->NDO = REF_NDO; s->Algorithm = (REF_ALGO == RK4 ? 0 : 1); s->Precision = 8;
+	s->NUA = REF_NUA; s->NiUA = REF_NiUA; s->NSA = REF_NSA; s->NiSA = REF_NiSA; s->NE = REF_NE; s->NDO = REF_NDO; s->Algorithm = (REF_ALGO == RK4 ? 0 : 1); s->Precision = (int)sizeof(P);
 }
 extern "C" int ref_coupled_capacity() { return REF_NS; }
 

@@ -46,6 +46,8 @@ def make_coupled_cases(WC):
     c["ring_b1c0_rkck45"] = ("duffing_ring_u14_b1c0_rkck45", WC.duffing_ring(NS=5, CBW=1, CCI=0), 1)
     c["ring_b0c1_rk4"] = ("duffing_ring_u14_b0c1_rk4", WC.duffing_ring(NS=3, CBW=0, CCI=1, algorithm=WC.RK4), 1)
     c["ring_b0c0_rkck45"] = ("duffing_ring_u14_b0c0_rkck45", WC.duffing_ring(NS=4, CBW=0, CCI=0), 2)
+    # single precision: the reference's own float instantiation of the ring tutorial (its bubble tutorial does not compile in float)
+    c["ring_b1c1_rkck45_f32"] = ("duffing_ring_u14_b1c1_rkck45_f32", WC.duffing_ring(NS=7, CBW=1, CCI=1, dtype=np.float32), 2)
     return c
 
 

@@ -56,8 +56,13 @@ def test_coupled_builtins_and_descriptor_checks(pkg):
     h = C.c_void_p()
     bad = sc._CDesc(NS=4, UPS=14, UD=2, NC=2, CBW=9, CCI=0, PrecisionBytes=8, Algorithm=1)
     assert lib.mpgos_coupled_create(C.byref(bad), C.byref(h)) == -1            # band wider than the ring
-    bad = sc._CDesc(NS=4, UPS=14, UD=2, NC=2, PrecisionBytes=4, Algorithm=1)
-    assert lib.mpgos_coupled_create(C.byref(bad), C.byref(h)) == -1            # FP32 coupled not built
+    bad = sc._CDesc(NS=4, UPS=14, UD=2, NC=2, PrecisionBytes=2, Algorithm=1)
+    assert lib.mpgos_coupled_create(C.byref(bad), C.byref(h)) == -1            # double or float only
+    # FP32 instantiations of the coupled module are looked up with the precision stated
+    assert lib.mpgos_coupled_builtin_launcher_p(b"bubble_ensemble", 64, 0, 0, 1, 0, 4)
+    assert lib.mpgos_coupled_builtin_launcher_p(b"duffing_ring", 14, 1, 1, 1, 1, 4)
+    assert lib.mpgos_coupled_builtin_launcher_p(b"bubble_ensemble", 64, 0, 0, 1, 0, 8) == lib.mpgos_coupled_builtin_launcher(b"bubble_ensemble", 64, 0, 0, 1, 0)
+    assert not lib.mpgos_coupled_builtin_launcher_p(b"bubble_ensemble", 128, 0, 0, 1, 0, 4)
 
 
 def test_builtin_systems_and_shapes(pkg):

@@ -164,3 +164,48 @@ def test_matrix_entry_outside_band_is_rejected(pkg):
     with pytest.raises(pkg.MpgosError):
         ps.SetCouplingMatrix(2, 0, 0, 1.0)
     ps.close()
+
+
+def test_fp32_ring_against_checker_and_reference_float_kernel(ccases, pkg, oracle):
+    """FP32 instantiation of the block-per-system kernel (banded circulant matrix, events, accessories, dense output) against
+    the single-precision checker, which is bit-identical to the reference's own kernel instantiated with Precision = float
+    (tests/test_oracle_coupled.py).  Single-precision arithmetic with 1e-5 tolerances leaves ~1e-3 on the end state."""
+    tag, wl, phases = ccases["ring_b1c1_rkck45_f32"]
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=phases)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=phases)
+    assert out.ActualState.dtype == np.float32 and out.DenseState.dtype == np.float32
+    # A phase ends when ANY unit reaches its second local maximum: which unit wins is decided by single-precision event values,
+    # so a system may end a phase on another event than the checker's (FMA contraction, float vs double literals).  Systems whose
+    # event counters agree (most of them) are then compared value by value.
+    same = (out.IntegerUnitAccessories == ref.IntegerUnitAccessories).all(axis=(0, 2))
+    assert same.mean() >= 0.7
+    assert (out.IntegerUnitAccessories.max(axis=2) == 2).all()                       # every system stopped on a second maximum
+    assert np.abs(att - ratt)[same].max() <= 0.1 * ratt.max()
+    assert rel_err(out.ActualTime, ref.ActualTime)[same].max() < 1e-3
+    assert rel_err(out.ActualState, ref.ActualState)[:, same].max() < 5e-3
+    assert np.median(rel_err(out.ActualState, ref.ActualState)[:, same]) < 5e-4
+    assert rel_err(out.UnitAccessories, ref.UnitAccessories)[:, same].max() < 5e-3
+    # dense output: one point per accepted step (the step sequences differ in single precision); the first point of the last
+    # phase is the state the previous phase ended on
+    assert rel_err(out.DenseState[0], ref.DenseState[0])[:, same].max() < 5e-3
+    assert rel_err(out.DenseTime[0], ref.DenseTime[0])[same].max() < 1e-3
+    assert (out.DenseIndex > 10).all() and (out.DenseIndex <= wl.shape.NDO).all()
+
+
+def test_fp32_bubble_ensemble_against_double(pkg, oracle):
+    """FP32 bubble ensemble (64 units, dense coupling summed in FP32 on the scalar path): against the single-precision checker
+    and against the FP64 run of the same sweep.  Both comparisons at the accuracy single precision with rtol = 1e-5 can give."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl32 = WC.bubble_ensemble(NS=24, UPS=64, amplitude=(0.1, 0.8), dtype=np.float32)
+    wl64 = WC.bubble_ensemble(NS=24, UPS=64, amplitude=(0.1, 0.8))
+    out32, att32, acc32 = pkg.run_coupled_workload(wl32, phases=1)
+    out64, att64, acc64 = pkg.run_coupled_workload(wl64, phases=1)
+    ref32, ratt32, _ = oracle.run_coupled_oracle(wl32, phases=1, host_threads=8)
+    assert out32.ActualState.dtype == np.float32
+    assert np.array_equal(out32.ActualTime, np.ones(24, np.float32))                # every system ends exactly on TD[1]
+    assert np.isfinite(out32.ActualState).all()
+    assert rel_err(out32.ActualState, ref32.ActualState).max() < 2e-2
+    assert np.median(rel_err(out32.ActualState, ref32.ActualState)) < 1e-3
+    assert np.median(rel_err(out32.ActualState.astype(np.float64), out64.ActualState)) < 1e-3
+    assert (att32 < att64).all()                                                    # looser tolerances, fewer steps
+    assert np.abs(att32 - ratt32).max() <= 0.15 * ratt32.max()

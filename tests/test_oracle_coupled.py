@@ -9,7 +9,7 @@ import pytest
 from cases import make_coupled_cases, COUPLED_RESULT_FIELDS
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ["bubble_u8_rkck45", "bubble_u16_rkck45", "bubble_u16_rk4", "ring_b1c1_rkck45", "ring_b1c0_rkck45", "ring_b0c1_rk4", "ring_b0c0_rkck45"]
+NAMES = ["bubble_u8_rkck45", "bubble_u16_rkck45", "bubble_u16_rk4", "ring_b1c1_rkck45", "ring_b1c0_rkck45", "ring_b0c1_rk4", "ring_b0c0_rkck45", "ring_b1c1_rkck45_f32"]
 
 
 @pytest.fixture(scope="module")

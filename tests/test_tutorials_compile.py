@@ -41,3 +41,20 @@ def test_every_reference_tutorial_compiles_unmodified_against_the_dropin_headers
         results = list(pool.map(_compile, items))
     failed = [(n, err) for n, rc, err in results if rc != 0]
     assert not failed, failed
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "SourceCodes")) or shutil.which("nvcc") is None,
+                    reason="needs /root/reference and nvcc (development container)")
+def test_ring_tutorial_compiles_in_single_precision():
+    """The coupled module's FP32 instantiation through the drop-in header: the reference's ring tutorial with its own
+    `#define PRECISION` switched to float (the one edit its comment invites: "// float, double")."""
+    src = os.path.join(REF, "Tutorials_CoupledSystems_PerBlock", "T1_RingOfDuffingOscillators", "RingOfDuffingOscillators.cu")
+    text = open(src).read()
+    assert "#define PRECISION double" in text
+    with tempfile.TemporaryDirectory() as tmp:
+        f32 = os.path.join(tmp, "RingOfDuffingOscillators_f32.cu")
+        open(f32, "w").write(text.replace("#define PRECISION double", "#define PRECISION float"))
+        cmd = ["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", os.path.join(ROOT, "include"),
+               "-I", os.path.dirname(src), "-c", f32, "-o", os.path.join(tmp, "t.o")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]

@@ -7,8 +7,9 @@ pkg = importlib.import_module("massively-parallel-gpu-ode-solver_b200")
 WC = pkg.workloads_coupled
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 UPS = int(os.environ.get('UPS', '64'))
-wl = WC.bubble_ensemble(NS=NS, UPS=UPS)
-with pkg.CoupledProblemSolver("bubble_ensemble", NS, UPS) as ps:
+DT = np.float32 if os.environ.get('F32') else np.float64
+wl = WC.bubble_ensemble(NS=NS, UPS=UPS, dtype=DT)
+with pkg.CoupledProblemSolver("bubble_ensemble", NS, UPS, Precision=DT) as ps:
     pkg.apply_coupled_workload(ps, wl)
     ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, int(os.environ.get('TC', '1')))
     best = None
