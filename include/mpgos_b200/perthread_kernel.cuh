@@ -140,6 +140,9 @@ template <> __device__ __forceinline__ float  ck<float>(int i)  { constexpr floa
 #ifndef MPGOS_B200_TABLEAU_IMMEDIATES
 #define MPGOS_B200_TABLEAU_IMMEDIATES 1
 #endif
+#ifndef MPGOS_B200_TABLEAU_COMMON_FACTORS
+#define MPGOS_B200_TABLEAU_COMMON_FACTORS 1
+#endif
 template <class P, int FIRST, int N> struct CkRow
 {
 	static __device__ __forceinline__ void load(P* c)
@@ -423,17 +426,32 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			for (int i = 0; i < SD; i++) k2[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C3);
+#if MPGOS_B200_TABLEAU_COMMON_FACTORS
+			// Exact rational relations inside the tableau -- row 3 = (3/40)(1, 3), row 4 = (3/10)(1, -3, 4), a53 = -2 a54,
+			// a64 = (77/8) a63, e5 = 4.5 e1 -- let a dyadic immediate stand in for a second tableau constant: 6 fewer constants
+			// compete for the 63 uniform registers (fewer R2UR moves of parked constants per step), same instruction count.
+			CkRow<P, CK_A31, 1>::load(c);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(c[0], fma(P(3.0), k2[i], k1[i]), s.x[i]);
+#else
 			CkRow<P, CK_A31, 2>::load(c);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]));
+#endif
 			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k3[i] *= dt;
 
 			T = s.t + dt * ck<P>(CK_C4);
+#if MPGOS_B200_TABLEAU_COMMON_FACTORS
+			CkRow<P, CK_A41, 1>::load(c);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) X[i] = fma(c[0], fma(P(4.0), k3[i], fma(P(-3.0), k2[i], k1[i])), s.x[i]);
+#else
 			CkRow<P, CK_A41, 3>::load(c);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) X[i] = fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])));
+#endif
 			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k4[i] *= dt;
@@ -441,7 +459,11 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			T = s.t + dt;
 			CkRow<P, CK_A51, 4>::load(c);
 			#pragma unroll
+#if MPGOS_B200_TABLEAU_COMMON_FACTORS
+			for (int i = 0; i < SD; i++) X[i] = fma(c[3], fma(P(-2.0), k3[i], k4[i]), fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])));      // a53 = -2 a54
+#else
 			for (int i = 0; i < SD; i++) X[i] = fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]))));
+#endif
 			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k5[i] *= dt;
@@ -449,7 +471,11 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			T = s.t + dt * ck<P>(CK_C6);
 			CkRow<P, CK_A61, 5>::load(c);
 			#pragma unroll
+#if MPGOS_B200_TABLEAU_COMMON_FACTORS
+			for (int i = 0; i < SD; i++) X[i] = fma(c[4], k5[i], fma(c[2], fma(P(77.0 / 8.0), k4[i], k3[i]), fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]))));   // a64 = (77/8) a63
+#else
 			for (int i = 0; i < SD; i++) X[i] = fma(c[4], k5[i], fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])))));
+#endif
 			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
 			#pragma unroll
 			for (int i = 0; i < SD; i++) k6[i] *= dt;
@@ -461,7 +487,11 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
+#if MPGOS_B200_TABLEAU_COMMON_FACTORS
+				const P e = fma(c[4], k6[i], fma(c[2], k4[i], fma(c[1], k3[i], c[0] * fma(P(4.5), k5[i], k1[i]))));       // e5 = 4.5 e1
+#else
 				const P e = fma(c[4], k6[i], fma(c[3], k5[i], fma(c[2], k4[i], fma(c[1], k3[i], c[0] * k1[i]))));
+#endif
 				err[i] = fabs(e) + c[5];
 			}
 #else
