@@ -257,7 +257,7 @@ def main():
     config = {"workload": f"{args.workload}: {N} {unit} per GPU x {world} GPU(s), {args.phases} integration phase(s) per step (BASELINE {cfg_name})",
               f"{unit}_per_gpu": N, "phases_per_step": args.phases,
               "sharding": "tile-cyclic, no collective on the data path",
-              "l2": "state is restored device-to-device from a snapshot before every step; the kernel is FP64-pipe bound, its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
+              "l2": "state is restored device-to-device from a snapshot before every step; the kernel is bound by instruction issue (an FP64 instruction takes two issue slots), its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
               "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
 
     # ------------------------------------------------------------------ reference arm (CPU) ------
@@ -414,7 +414,7 @@ def main():
             gbs = dense_samples * bytes_per_sample / (kmean * args.phases * 1e-3) / 1e9
             out["dense_output"] = {"stored_points_per_step_per_gpu": dense_samples, "bytes_per_point": bytes_per_sample, "achieved_gbs": gbs,
                                    "hbm_peak_gbs": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None,
-                                   "note": "rank 0; algorithmic bytes of the dense-output stream over the kernel time -- the kernel is FP64-pipe bound, the stream is far from the HBM roof"}
+                                   "note": "rank 0; algorithmic bytes of the dense-output stream over the kernel time -- the kernel is issue-bound (FP64), the stream is far from the HBM roof"}
         if world == 1 and not args.no_reference_gpu:
             # reported baseline, not a target: the reference MPGOS compiled for sm_100a, same inputs, same event bracket
             try:
