@@ -15,7 +15,9 @@ if which == "coupled":
     cc = make_coupled_cases(WC)
     for name in ("ring_b1c1_rkck45", "ring_b0c0_rkck45", "bubble_u16_rkck45"):
         tag, wl, phases = cc[name]; out, att, acc = pkg.run_coupled_workload(wl, phases=1); print(name, int(att.sum()))
-    wl = WC.swing_ring(NS=5); out, att, acc = pkg.run_coupled_workload(wl, phases=1) if False else (None, np.zeros(1), None)
+    tag, wl, phases = cc["ring_b1c1_rkck45_f32"]; out, att, acc = pkg.run_coupled_workload(wl, phases=1); print("ring f32", int(att.sum()))
+    wl = WC.bubble_ensemble(NS=7, UPS=64, amplitude=(0.2, 1.2), dtype=np.float32); wl.buffers.TimeDomain[1][:] = 0.05
+    out, att, acc = pkg.run_coupled_workload(wl, phases=1); print("bubble f32 64", int(att.sum()))
 else:
     c = make_cases(pkg.workloads)
     for name in ("lorenz_rkck45_f64", "duffing_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64", "lorenz_rkck45_f32"):
