@@ -125,6 +125,22 @@ class Workload:
         return self.buffers.NT
 
 
+def single_precision(wl: "Workload", tolerance: float = 1e-5, event_tolerance: float = 1e-4, minimum_time_step: float = 1e-6) -> "Workload":
+    """The same sweep for the FP32 instantiation: buffers cast to float32 and tolerances a float can resolve.  The reference
+    ships single-precision settings for none of its tutorials, so these are our choice (stated wherever they are used)."""
+    shape = dataclasses.replace(wl.shape, dtype=np.float32)
+    b = Buffers(shape, wl.NT)
+    for f in Buffers.FIELDS:
+        getattr(b, f)[...] = getattr(wl.buffers, f)
+    o = dataclasses.replace(wl.options)
+    o.RelativeTolerance = np.full(shape.SD, tolerance, np.float32)
+    o.AbsoluteTolerance = np.full(shape.SD, tolerance, np.float32)
+    if shape.NE:
+        o.EventTolerance = np.full(shape.NE, event_tolerance, np.float32)
+    o.MinimumTimeStep = max(o.MinimumTimeStep, minimum_time_step)
+    return Workload(wl.name, shape, o, b, wl.phases, wl.flops_per_step, wl.note + " (single precision)")
+
+
 def linspace(B: float, E: float, N: int, dtype=np.float64) -> np.ndarray:
     """``Linspace`` of the tutorials (T2_Lorenz/Lorenz.cu:85-101): x[i] = B + i*((E-B)/(N-1)),
     first and last element set exactly."""

@@ -158,6 +158,35 @@ def test_fp32_lorenz(cases, pkg, oracle):
     assert np.abs(att - ratt).max() <= 0.1 * ratt.max()
 
 
+FP32_CASES = {
+    # name: (workload factory, sub-sample, phases, median tolerance, fraction of instances within 100 x that)
+    "poincare_rk4": (lambda W: W.poincare_t3(NT=4096, algorithm=W.RK4), 64, 2, 1e-5, 1.0),
+    "duffing_rkck45_events_dense": (lambda W: W.duffing_t1(NT=4096, algorithm=W.RKCK45), 64, 2, 1e-4, 0.95),
+    "impact_rkck45_events": (lambda W: W.impact_t6(NT=1 << 14), 64, 4, 1e-3, 0.85),
+    "kellermiksis_rkck45": (lambda W: W.keller_miksis_t5(NT=4096, ndo=0), 64, 1, 1e-4, 0.95),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FP32_CASES))
+def test_fp32_instantiations_of_the_other_systems(name, pkg, workloads, oracle):
+    """Every built-in system also exists in single precision (true FP32: literals in the run's precision).  Against the
+    single-precision checker; tolerances 1e-5 / event tolerance 1e-4 / minimum step 1e-6 (workloads.single_precision -- the
+    reference ships no FP32 settings).  Single-precision step sequences decorrelate quickly, so the gate is on the median and
+    on the bulk of the sweep, and events may be located on neighbouring steps."""
+    factory, n, phases, med_tol, frac = FP32_CASES[name]
+    from cases import subsample
+    wl = workloads.single_precision(subsample(factory(workloads), n))
+    ref, ratt, _ = oracle.run_oracle(wl, phases=phases, double_literals=False)
+    out, att, _ = pkg.run_workload(wl, phases=phases)
+    assert out.ActualState.dtype == np.float32 and np.isfinite(out.ActualState).all()
+    err = rel_err(out.ActualState.astype(np.float64), ref.ActualState.astype(np.float64)).max(axis=0)
+    assert np.median(err) < med_tol
+    assert (err < 100 * med_tol).mean() >= frac
+    assert np.abs(att - ratt).max() <= max(4, 0.15 * ratt.max())
+    if "rk4" in name:
+        assert np.array_equal(att, ratt) and np.array_equal(out.ActualTime, ref.ActualTime)
+
+
 def test_lane_refill_is_bit_identical_to_direct_mapping(cases, pkg):
     for name in ("lorenz_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64"):
         wl, phases = cases[name]
