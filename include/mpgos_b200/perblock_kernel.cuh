@@ -55,6 +55,9 @@ struct PerBlockArgs
 	P   EventTolerance[AtLeastOne<NE>::value];  int EventDirection[AtLeastOne<NE>::value];
 };
 
+// resident blocks per SM the kernel is compiled for: as many as keep 512 threads (128 registers each) on the SM
+__host__ __device__ constexpr int coupled_min_blocks(int threads) { return threads >= 512 ? 1 : (512 / threads > 4 ? 4 : 512 / threads); }
+
 __host__ __device__ constexpr int packed_matrix_elements(int UPS, int NC, int CBW, int CCI)
 {
 	return (CCI == 0 && CBW == 0) ? NC * UPS * UPS : (CCI == 0) ? NC * UPS * (2 * CBW + 1) : (CBW > 0) ? NC * (2 * CBW + 1) : NC * UPS;
@@ -192,7 +195,7 @@ __device__ __forceinline__ void mma_coupling_product(const double* __restrict__ 
 
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
           int NE, bool DENSE, int ALG, int SPBK, bool MMA>
-__global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), 1)
+__global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), coupled_min_blocks(SPBK * (((UPS + 31) / 32) * 32)))
 perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 {
 	constexpr int UPSP = ((UPS + 31) / 32) * 32;
@@ -666,7 +669,10 @@ struct PerBlockLauncher
 
 	// tensor-core coupling: dense FP64 matrices shared by all systems, whole-warp systems, 8 systems x UPS threads <= 512
 	static constexpr bool kCanMMA = (sizeof(P) == 8) && CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64 || UPS == 128);
-	static constexpr int  kMmaSlots = (UPS == 128) ? 4 : 8;      // 512 threads; with 128 units half of the instruction's N extent is used
+#ifndef MPGOS_B200_MMA_SLOTS
+#define MPGOS_B200_MMA_SLOTS 8
+#endif
+	static constexpr int  kMmaSlots = (UPS == 128) ? 4 : MPGOS_B200_MMA_SLOTS;      // 512 threads; with 128 units half of the instruction's N extent is used
 
 	template <int SLOTS, bool MMA>
 	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
