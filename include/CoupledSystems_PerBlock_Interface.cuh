@@ -19,8 +19,7 @@
 //   * SharedGlobalVariables / SharedCouplingMatrices are accepted and ignored: both always live in shared memory;
 //   * device-side warnings are printed only after SolverOption(DeviceMessages, 1);
 //   * extra options DeviceMessages / TensorCoreCoupling and the StepCounters() accessor;
-//   * Precision = double or float; the tensor-core coupling exists in double only (a float instantiation sums the coupling
-//     in FP32 on the scalar path).
+//   * Precision = double or float; dense shared matrices are multiplied on the tensor cores in both (FP64 DMMA; FP32 as 3xTF32).
 #ifndef COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
 #define COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
 

@@ -22,7 +22,8 @@
 //    form needs one 8-byte shared-memory operand per FMA and is bound by shared-memory bandwidth (ncu: 45 % of the LSU
 //    wavefront peak at 44 % FP64-pipe activity, profiles/); one DMMA performs 256 FMAs on two 8-byte operands per lane.
 //    The 8 systems then advance in lockstep through the stages (two block barriers per stage); everything else stays
-//    per slot.
+//    per slot.  The FP32 instantiation does the same product with mma.m16n8k8 on TF32 operands split into big + small parts
+//    (3xTF32: FP32 accuracy from 10-bit operands), UPS = 32 or 64.
 #ifndef MPGOS_B200_PERBLOCK_KERNEL_CUH
 #define MPGOS_B200_PERBLOCK_KERNEL_CUH
 
@@ -165,6 +166,7 @@ struct MmaGeometry
 	static constexpr int KPG = KT / KG;
 	static constexpr int CS = UPS + 4;                 // stride of a system's coupling terms  (conflict-free B fragment loads)
 	static constexpr int VS = UPS + 2;                 // stride of a system's partial sums    (conflict-free D fragment stores)
+	static constexpr int MCOPIES = 1, CCOPIES = 1;
 	static_assert(UPS % 32 == 0 && SLOTS >= 1 && SLOTS <= NCOL && ITEMS % WARPS == 0 && KT % KG == 0 && KPG % 2 == 0, "unsupported shape for the tensor-core coupling");
 };
 
@@ -193,6 +195,77 @@ __device__ __forceinline__ void mma_coupling_product(const double* __restrict__ 
 	}
 }
 
+// ---- tensor-core coupling in single precision: 3xTF32 ------------------------------------------------------------------
+// D[16x8] += A[16x8] . B[8x8] with TF32 operands and FP32 accumulation (mma.m16n8k8).  A TF32 operand keeps 10 mantissa bits, so
+// every FP32 value is split into big = tf32(v) and small = tf32(v - big) and the product is formed as
+// A_small.B_big + A_big.B_small + A_big.B_big (the small.small term is below FP32 resolution): ~2e-7 relative, FP32 accuracy.
+// Fragments (PTX ISA, mma.m16n8k8 .tf32), g = lane/4, t = lane%4: A: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4);
+// B: b0 (k = t, n = g), b1 (k = t+4, n = g); D: d0 (g, 2t), d1 (g, 2t+1), d2 (g+8, 2t), d3 (g+8, 2t+1).
+__device__ __forceinline__ unsigned to_tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void tf32_split(float v, float& big, float& small)
+{
+	big = __uint_as_float(to_tf32(v));
+	small = __uint_as_float(to_tf32(v - big));
+}
+__device__ __forceinline__ void mma_16x8x8_tf32(float (&d)[4], const float4& a, float b0, float b1)
+{
+	asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	    : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	    : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+template <int UPS, int SLOTS_>
+struct MmaGeometryF32
+{
+	static constexpr int SLOTS = SLOTS_;
+	static constexpr int NCOL = 8;
+	static constexpr int RT = UPS / 16;                // row tiles
+	static constexpr int KT = UPS / 8;                 // k tiles
+	static constexpr int WARPS = SLOTS * UPS / 32;
+	static constexpr int KG = (WARPS >= RT) ? WARPS / RT : 1;
+	static constexpr int ITEMS = RT * KG;
+	static constexpr int KPG = KT / KG;
+	static constexpr int CS = UPS + 4;                 // conflict-free B fragment loads (bank = 4 g + t)
+	static constexpr int VS = UPS + 4;                 // conflict-free D fragment stores (bank = 8 t + g)
+	static constexpr int MCOPIES = 2, CCOPIES = 2;     // big and small parts
+	static_assert(UPS % 32 == 0 && SLOTS >= 1 && SLOTS <= NCOL && ITEMS % WARPS == 0 && KT % KG == 0, "unsupported shape for the TF32 tensor-core coupling");
+};
+
+// frag: the matrix in fragment order [RT][KT][32] float4, big part then small part (`small_offset` float4s further);
+// cpt: [8][CS] big, then small (`cpt_small` floats further); vpart: [KG][8][VS].
+template <int UPS, int SLOTS>
+__device__ __forceinline__ void mma_coupling_product_f32(const float4* __restrict__ frag, int small_offset, const float* cpt, int cpt_small, float* vpart, int warp, int lane)
+{
+	using G = MmaGeometryF32<UPS, SLOTS>;
+	const int g = lane >> 2, t = lane & 3;
+	#pragma unroll
+	for (int item = warp; item < G::ITEMS; item += G::WARPS)
+	{
+		const int rt = item % G::RT, kg = item / G::RT;
+		float d[4] = {0.f, 0.f, 0.f, 0.f};
+		#pragma unroll
+		for (int j = 0; j < G::KPG; j++)
+		{
+			const int kt = kg * G::KPG + j;
+			const float4 ab = frag[(rt * G::KT + kt) * 32 + lane];
+			const float4 as = frag[(rt * G::KT + kt) * 32 + lane + small_offset];
+			const float* B = cpt + g * G::CS + kt * 8 + t;
+			const float bb0 = B[0], bb1 = B[4], bs0 = B[cpt_small], bs1 = B[cpt_small + 4];
+			mma_16x8x8_tf32(d, as, bb0, bb1);
+			mma_16x8x8_tf32(d, ab, bs0, bs1);
+			mma_16x8x8_tf32(d, ab, bb0, bb1);
+		}
+		float* V = vpart + (size_t)kg * G::NCOL * G::VS + rt * 16 + g;
+		V[(2 * t) * G::VS]         = d[0];
+		V[(2 * t + 1) * G::VS]     = d[1];
+		V[(2 * t) * G::VS + 8]     = d[2];
+		V[(2 * t + 1) * G::VS + 8] = d[3];
+	}
+}
+
+template <class P, int UPS, int SLOTS> struct MmaGeometryFor { using type = MmaGeometry<UPS, SLOTS>; };
+template <int UPS, int SLOTS> struct MmaGeometryFor<float, UPS, SLOTS> { using type = MmaGeometryF32<UPS, SLOTS>; };
+
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
           int NE, bool DENSE, int ALG, int SPBK, bool MMA>
 __global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), coupled_min_blocks(SPBK * (((UPS + 31) / 32) * 32)))
@@ -203,15 +276,17 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	constexpr int MSIZE = packed_matrix_elements(UPS, NC, CBW, CCI);
 	constexpr int MSTRIDE = MSIZE / (NC > 0 ? NC : 1);
 	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA, MMA>;
-	using G = MmaGeometry<MMA ? UPS : 32, MMA ? SPBK : 8>;
+	using G = typename MmaGeometryFor<P, MMA ? UPS : 32, MMA ? SPBK : 8>::type;
+	constexpr int MCOPIES   = MMA ? G::MCOPIES : 1;                        // FP32: big and small TF32 parts of the matrix
 	constexpr int CPT_ELEMS = MMA ? NC * G::NCOL * G::CS : 0;              // coupling terms of the systems of the block (MMA variant)
+	constexpr int CPT_ALL   = MMA ? CPT_ELEMS * G::CCOPIES : 0;
 	constexpr int V_ELEMS   = MMA ? NC * G::KG * G::NCOL * G::VS : 0;      // partial column sums per k group
-	static_assert(!MMA || (CBW == 0 && CCI == 0 && NC > 0 && sizeof(P) == 8), "tensor-core coupling: dense FP64 matrices");
+	static_assert(!MMA || (CBW == 0 && CCI == 0 && NC > 0), "tensor-core coupling: dense matrices shared by all systems");
 
 	extern __shared__ __align__(16) unsigned char dyn_smem[];
-	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE]  packed (scalar) or in fragment order (MMA)
-	P*   s_cptm   = s_matrix + MSIZE;                                   // [CPT_ELEMS]
-	P*   s_vpart  = s_cptm + CPT_ELEMS;                                 // [V_ELEMS]
+	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE x MCOPIES]  packed (scalar) or in fragment order (MMA)
+	P*   s_cptm   = s_matrix + MSIZE * MCOPIES;                         // [CPT_ALL]
+	P*   s_vpart  = s_cptm + CPT_ALL;                                   // [V_ELEMS]
 	P*   s_gpar   = s_vpart + V_ELEMS;                                  // [NGP]
 	int* s_igpar  = reinterpret_cast<int*>(s_gpar + NGP);               // [NiGP]
 	__shared__ Slot s_slots[SPBK];
@@ -219,14 +294,30 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 
 	if (MMA)
 	{
-		// fragment order: tile (rt, kt) = rows 8 rt .. 8 rt + 7, columns 4 kt .. 4 kt + 3; lane l holds M[8 rt + l/4][4 kt + l%4]
-		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x)
+		if constexpr (sizeof(P) == 8)
 		{
-			const int k = i / (UPS * UPS), r = i % (UPS * UPS), tile = r / 32, l = r % 32;
-			const int row = (tile / G::KT) * 8 + (l >> 2), col = (tile % G::KT) * 4 + (l & 3);
-			s_matrix[i] = a.CouplingMatrix[(size_t)k * UPS * UPS + row + col * UPS];
+			// fragment order: tile (rt, kt) = rows 8 rt .. 8 rt + 7, columns 4 kt .. 4 kt + 3; lane l holds M[8 rt + l/4][4 kt + l%4]
+			for (int i = threadIdx.x; i < MSIZE; i += blockDim.x)
+			{
+				const int k = i / (UPS * UPS), r = i % (UPS * UPS), tile = r / 32, l = r % 32;
+				const int row = (tile / G::KT) * 8 + (l >> 2), col = (tile % G::KT) * 4 + (l & 3);
+				s_matrix[i] = a.CouplingMatrix[(size_t)k * UPS * UPS + row + col * UPS];
+			}
 		}
-		for (int i = threadIdx.x; i < CPT_ELEMS; i += blockDim.x) s_cptm[i] = P(0);    // columns without a slot stay zero
+		else
+		{
+			// fragment order of m16n8k8: tile (rt, kt) = rows 16 rt .., columns 8 kt ..; lane l holds the float4 (a0, a1, a2, a3); big
+			// parts first, small parts MSIZE elements further
+			for (int i = threadIdx.x; i < MSIZE; i += blockDim.x)
+			{
+				const int k = i / (UPS * UPS), r = i % (UPS * UPS), tile = r / 128, w = r % 128, l = w >> 2, reg = w & 3;
+				const int row = (tile / G::KT) * 16 + (l >> 2) + ((reg & 1) ? 8 : 0), col = (tile % G::KT) * 8 + (l & 3) + ((reg & 2) ? 4 : 0);
+				float big, small;
+				tf32_split((float)a.CouplingMatrix[(size_t)k * UPS * UPS + row + col * UPS], big, small);
+				s_matrix[i] = (P)big;  s_matrix[i + MSIZE] = (P)small;
+			}
+		}
+		for (int i = threadIdx.x; i < CPT_ALL; i += blockDim.x) s_cptm[i] = P(0);      // columns without a slot stay zero
 	}
 	else
 		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
@@ -337,13 +428,30 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				{
 					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
 					#pragma unroll
-					for (int k = 0; k < NC; k++) s_cptm[(k * G::NCOL + slot) * G::CS + unit] = cpt[k];
+					for (int k = 0; k < NC; k++)
+					{
+						if constexpr (sizeof(P) == 8) s_cptm[(k * G::NCOL + slot) * G::CS + unit] = cpt[k];
+						else
+						{
+							float big, small;
+							tf32_split((float)cpt[k], big, small);
+							s_cptm[(k * G::NCOL + slot) * G::CS + unit] = (P)big;
+							s_cptm[CPT_ELEMS + (k * G::NCOL + slot) * G::CS + unit] = (P)small;
+						}
+					}
 				}
 				__syncthreads();
 				#pragma unroll
 				for (int k = 0; k < NC; k++)
-					mma_coupling_product<MMA ? UPS : 32, MMA ? SPBK : 8>((const double*)s_matrix + (size_t)k * UPS * UPS, (const double*)s_cptm + k * G::NCOL * G::CS,
-					                                                     (double*)s_vpart + k * G::KG * G::NCOL * G::VS, warp, lane);
+				{
+					if constexpr (sizeof(P) == 8)
+						mma_coupling_product<MMA ? UPS : 32, MMA ? SPBK : 8>((const double*)s_matrix + (size_t)k * UPS * UPS, (const double*)s_cptm + k * G::NCOL * G::CS,
+						                                                     (double*)s_vpart + k * G::KG * G::NCOL * G::VS, warp, lane);
+					else
+						mma_coupling_product_f32<MMA ? UPS : 32, MMA ? SPBK : 8>((const float4*)((const float*)s_matrix + (size_t)k * UPS * UPS), MSIZE / 4,
+						                                                         (const float*)s_cptm + k * G::NCOL * G::CS, CPT_ELEMS,
+						                                                         (float*)s_vpart + k * G::KG * G::NCOL * G::VS, warp, lane);
+				}
 				__syncthreads();
 				if (live)
 				{
@@ -668,7 +776,7 @@ struct PerBlockLauncher
 	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
 
 	// tensor-core coupling: dense FP64 matrices shared by all systems, whole-warp systems, 8 systems x UPS threads <= 512
-	static constexpr bool kCanMMA = (sizeof(P) == 8) && CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64 || UPS == 128);
+	static constexpr bool kCanMMA = CBW == 0 && CCI == 0 && NC > 0 && (UPS == 32 || UPS == 64 || (UPS == 128 && sizeof(P) == 8));
 #ifndef MPGOS_B200_MMA_SLOTS
 #define MPGOS_B200_MMA_SLOTS 8
 #endif
@@ -678,9 +786,9 @@ struct PerBlockLauncher
 	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
 	{
 		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA>;
-		using G = MmaGeometry<MMA ? UPS : 32, MMA ? SLOTS : 8>;
-		const size_t extra = MMA ? (size_t)NC * G::NCOL * G::CS + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
-		const size_t smem = sizeof(P) * (packed_matrix_elements(UPS, NC, CBW, CCI) + extra + NGP) + sizeof(int) * NiGP + 16;
+		using G = typename MmaGeometryFor<P, MMA ? UPS : 32, MMA ? SLOTS : 8>::type;
+		const size_t extra = MMA ? (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
+		const size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * (MMA ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return (int)e;
 		int per_sm = 0;

@@ -111,7 +111,7 @@ void* mpgos_coupled_stream(mpgos_coupled_solver* s);
 /* systems compiled into the library: "bubble_ensemble" (UPS 8, 16, 32, 64, 128), "duffing_ring" (UPS 14; CBW/CCI 1/1, 1/0, 0/1, 0/0; UPS 32 with full matrices) */
 int   mpgos_coupled_builtin_desc(const char* system, int ups, int cbw, int cci, mpgos_coupled_desc* desc);
 mpgos_coupled_launcher mpgos_coupled_builtin_launcher(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output);   /* double precision */
-/* the same with the precision stated (bytes: 8, or 4 for the FP32 instantiations -- scalar coupling; the tensor-core product is FP64 only) */
+/* the same with the precision stated (bytes: 8, or 4 for the FP32 instantiations; their dense coupling runs on the tensor cores as 3xTF32) */
 mpgos_coupled_launcher mpgos_coupled_builtin_launcher_p(const char* system, int ups, int cbw, int cci, int algorithm, int dense_output, int precision_bytes);
 
 #ifdef __cplusplus

@@ -27,8 +27,9 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 1, kAlgRK4, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 32, 0, 0, kAlgRKCK45, true),      // full matrices, 2 couplings, events: the tensor-core path with everything on
-	// FP32 instantiations (scalar coupling; the tensor-core product exists in FP64 only)
+	// FP32 instantiations (dense coupling on the tensor cores as 3xTF32 for UPS 32 / 64)
 	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 16, 0, 0, kAlgRKCK45, false),
+	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 32, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 64, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 64, 0, 0, kAlgRK4, false),
 	COUPLED_ENTRY_P("duffing_ring", DuffingRing, float, 14, 1, 1, kAlgRKCK45, true),

@@ -209,3 +209,22 @@ def test_fp32_bubble_ensemble_against_double(pkg, oracle):
     assert np.median(rel_err(out32.ActualState.astype(np.float64), out64.ActualState)) < 1e-3
     assert (att32 < att64).all()                                                    # looser tolerances, fewer steps
     assert np.abs(att32 - ratt32).max() <= 0.15 * ratt32.max()
+
+
+@pytest.mark.parametrize("ups,ns", [(64, 21), (32, 13)])
+def test_fp32_tensor_core_coupling_3xtf32(ups, ns, pkg, oracle):
+    """Single-precision dense coupling on the tensor cores: TF32 operands split into big + small parts (3xTF32), FP32
+    accumulation.  Against the scalar FP32 path of the same kernel and the single-precision checker; ns is not a multiple of
+    8, so the last block runs with idle slots."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=ns, UPS=ups, amplitude=(0.2, 1.4), dtype=np.float32)
+    tc, tatt, _ = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=1)
+    sc, satt, _ = pkg.run_coupled_workload(wl, phases=1, tensor_core_coupling=0)
+    ref, ratt, _ = oracle.run_coupled_oracle(wl, phases=1, host_threads=8)
+    assert tc.ActualState.dtype == np.float32 and np.isfinite(tc.ActualState).all()
+    assert np.array_equal(tc.ActualTime, np.ones(ns, np.float32))
+    assert not np.array_equal(tc.ActualState, sc.ActualState)                       # it is a different summation
+    assert np.median(rel_err(tc.ActualState, sc.ActualState)) < 2e-5
+    assert rel_err(tc.ActualState, sc.ActualState).max() < 5e-3
+    assert np.median(rel_err(tc.ActualState, ref.ActualState)) < 2e-5
+    assert np.abs(tatt - satt).max() <= 0.1 * satt.max() and np.abs(tatt - ratt).max() <= 0.15 * ratt.max()
