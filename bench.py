@@ -63,21 +63,22 @@ def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int
     """This rank's shard: tile-cyclic slices of the global (world x n)-instance sweep."""
     W = pkg.workloads
     sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    dtype = np.float64 if precision == "f64" else np.float32
     if name == "coupled":
-        full = pkg.workloads_coupled.bubble_ensemble(NS=n * world, UPS=64)
+        full = pkg.workloads_coupled.bubble_ensemble(NS=n * world, UPS=64, dtype=dtype)
         if world > 1:
             import copy
             wl = copy.copy(full)
             wl.buffers = full.buffers.take(sharding.shard_indices(n, rank, world, COUPLED_TILE))
             return wl
         return full
-    dtype = np.float64 if precision == "f64" else np.float32
+    single = (lambda wl: W.single_precision(wl)) if precision == "f32" else (lambda wl: wl)     # our FP32 settings: tolerances 1e-5
     gen = {"lorenz": lambda m: W.lorenz(NT=m, algorithm=W.RKCK45, dtype=dtype),
            "lorenz_rk4": lambda m: W.lorenz(NT=m, algorithm=W.RK4, dtype=dtype),
-           "impact": lambda m: W.impact_t6(NT=m),
-           "kellermiksis": lambda m: W.keller_miksis_t5(NT=m, ndo=0),
-           "kellermiksis_dense": lambda m: W.keller_miksis_t5(NT=m, ndo=200),
-           "duffing": lambda m: W.duffing_t1(NT=m, algorithm=W.RK4)}[name]
+           "impact": lambda m: single(W.impact_t6(NT=m)),
+           "kellermiksis": lambda m: single(W.keller_miksis_t5(NT=m, ndo=0)),
+           "kellermiksis_dense": lambda m: single(W.keller_miksis_t5(NT=m, ndo=200)),
+           "duffing": lambda m: single(W.duffing_t1(NT=m, algorithm=W.RK4))}[name]
     tile = sharding.TILE if n % sharding.TILE == 0 else 1
     return sharding.shard_workload(gen(n * world), n, rank, world, tile)
 
@@ -163,7 +164,7 @@ class Arm:
         if kind == "coupled":
             self.V = pkg.CoupledVariables
             self.ps = pkg.CoupledProblemSolver(wl.name, wl.buffers.NS, sh.UPS, CBW=sh.CBW, CCI=sh.CCI, NDO=sh.NDO, Algorithm=sh.Algorithm, Device=device,
-                                               TPB=sh.TPB, SPB=sh.SPB)
+                                               TPB=sh.TPB, SPB=sh.SPB, Precision=sh.dtype)
             pkg.apply_coupled_workload(self.ps, wl)
             if args.tensor_core_coupling >= 0:
                 self.ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, args.tensor_core_coupling)
@@ -423,7 +424,7 @@ def main():
                 ref_ms = None
                 if kind == "coupled":
                     tag = "bubble_ensemble_u64_s2"
-                    if N == 8192 and os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
+                    if N == 8192 and args.precision == "f64" and os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
                         _, ref_ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=args.phases, shared_matrices=1, repeats=3)
                         what = "reference MPGOS CoupledSystems_PerBlock kernel (TPB 128, SPB 2, SharedCouplingMatrices 1: its fastest setting here) compiled unmodified by nvcc for sm_100a"
                 elif oracle_py.ref_gpu_available(wl):
