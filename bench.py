@@ -83,6 +83,21 @@ def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int
     return sharding.shard_workload(gen(n * world), n, rank, world, tile)
 
 
+class quiet_stdout:
+    """The reference's host object narrates its construction on stdout (C++ iostream); the contract is ONE line there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *exc):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -198,30 +213,16 @@ class Arm:
 
     def enqueue_e2e(self, phases: int):
         ps = self.ps
-        if self.kind == "coupled":
-            # the reference's flow: fill the solver's pinned mirrors (SetHost), SynchroniseFromHostToDevice, Solve,
-            # SynchroniseFromDeviceToHost, read the mirrors (GetHost)
-            for v, t in self.user_in.items():
-                np.copyto(ps.host(v), t.numpy().reshape(ps.host(v).shape))
-                ps.SynchroniseFromHostToDevice(v)
-            for _ in range(phases):
-                ps.Solve()
-            for v in self.user_out:
-                ps.SynchroniseFromDeviceToHost(v)
-        else:
-            for v, t in self.user_in.items():
-                ps.Upload(v, t.data_ptr(), t.numel() * t.element_size())
-            for _ in range(phases):
-                ps.Solve()
-            for v, t in self.user_out.items():
-                ps.Download(v, t.data_ptr(), t.numel() * t.element_size())
+        for v, t in self.user_in.items():
+            ps.Upload(v, t.data_ptr(), t.numel() * t.element_size())
+        for _ in range(phases):
+            ps.Solve()
+        for v, t in self.user_out.items():
+            ps.Download(v, t.data_ptr(), t.numel() * t.element_size())
         ps.InsertSynchronisationPoint()
 
     def finish_e2e(self):
         self.ps.SynchroniseSolver()
-        if self.kind == "coupled":
-            for v, t in self.user_out.items():
-                np.copyto(t.numpy().reshape(self.ps.host(v).shape), self.ps.host(v))
 
     def close(self):
         self.ps.close()
@@ -425,10 +426,12 @@ def main():
                 if kind == "coupled":
                     tag = "bubble_ensemble_u64_s2"
                     if N == 8192 and args.precision == "f64" and os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
-                        _, ref_ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=args.phases, shared_matrices=1, repeats=3)
+                        with quiet_stdout():
+                            _, ref_ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=args.phases, shared_matrices=1, repeats=3)
                         what = "reference MPGOS CoupledSystems_PerBlock kernel (TPB 128, SPB 2, SharedCouplingMatrices 1: its fastest setting here) compiled unmodified by nvcc for sm_100a"
                 elif oracle_py.ref_gpu_available(wl):
-                    _, ref_ms = oracle_py.run_ref_gpu(wl, phases=args.phases, threads_per_block=64, repeats=3)
+                    with quiet_stdout():
+                        _, ref_ms = oracle_py.run_ref_gpu(wl, phases=args.phases, threads_per_block=64, repeats=3)
                     what = "reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a, 64 threads/block"
                 if ref_ms is not None:
                     ref_ms /= args.phases

@@ -101,6 +101,10 @@ int   mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher 
 int   mpgos_coupled_insert_sync_point(mpgos_coupled_solver* s);
 int   mpgos_coupled_sync_solver(mpgos_coupled_solver* s);
 int   mpgos_coupled_sync_device(mpgos_coupled_solver* s);
+/* additions: copies between caller-owned host arrays (pinned for true asynchrony; unit scope [unit + system*UPS + serial*NS*UPS],
+ * system scope [system + serial*NS]; not for CouplingMatrix, which is packed by set_matrix_entry) and the device buffers, on the solver's stream */
+int   mpgos_coupled_upload(mpgos_coupled_solver* s, int variable, const void* host_src, size_t bytes);
+int   mpgos_coupled_download(mpgos_coupled_solver* s, int variable, void* host_dst, size_t bytes);
 /* additions: per-system step counters, device-resident checkpoint, raw stream */
 int   mpgos_coupled_read_step_counters(mpgos_coupled_solver* s, unsigned long long* attempted, unsigned long long* accepted);
 int   mpgos_coupled_reset_step_counters(mpgos_coupled_solver* s);

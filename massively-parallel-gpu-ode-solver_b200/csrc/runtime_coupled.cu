@@ -241,6 +241,28 @@ static int ccopy(mpgos_coupled_solver* s, int variable, bool to_device)
 int mpgos_coupled_sync_h2d(mpgos_coupled_solver* s, int variable) { return ccopy(s, variable, true); }
 int mpgos_coupled_sync_d2h(mpgos_coupled_solver* s, int variable) { return ccopy(s, variable, false); }
 
+int mpgos_coupled_upload(mpgos_coupled_solver* s, int variable, const void* host_src, size_t bytes)
+{
+	if (!s || !is_cbuffer(variable) || variable == MPGOS_CVAR_CouplingMatrix || (!host_src && bytes)) return CFAIL(MPGOS_ERR_ARGUMENT, "upload: bad argument");
+	CMirror& m = s->var[variable];
+	if (bytes != m.bytes) return CFAIL(MPGOS_ERR_BOUNDS, "upload: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
+	if (bytes == 0) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
+	return MPGOS_OK;
+}
+
+int mpgos_coupled_download(mpgos_coupled_solver* s, int variable, void* host_dst, size_t bytes)
+{
+	if (!s || !is_cbuffer(variable) || variable == MPGOS_CVAR_CouplingMatrix || (!host_dst && bytes)) return CFAIL(MPGOS_ERR_ARGUMENT, "download: bad argument");
+	CMirror& m = s->var[variable];
+	if (bytes != m.bytes) return CFAIL(MPGOS_ERR_BOUNDS, "download: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
+	if (bytes == 0) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	CUDA_TRY(cudaMemcpyAsync(host_dst, m.dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+	return MPGOS_OK;
+}
+
 static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 {
 	L.desc = s->desc;

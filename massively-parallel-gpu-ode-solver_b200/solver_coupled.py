@@ -59,6 +59,7 @@ COUPLED_ABI_SYMBOLS = (
     "mpgos_coupled_solve_timed", "mpgos_coupled_insert_sync_point", "mpgos_coupled_sync_solver", "mpgos_coupled_sync_device",
     "mpgos_coupled_read_step_counters", "mpgos_coupled_reset_step_counters", "mpgos_coupled_save_state", "mpgos_coupled_restore_state",
     "mpgos_coupled_stream", "mpgos_coupled_builtin_desc", "mpgos_coupled_builtin_launcher", "mpgos_coupled_builtin_launcher_p",
+    "mpgos_coupled_upload", "mpgos_coupled_download",
 )
 
 
@@ -90,6 +91,8 @@ def _bind(lib):
     for f in ("insert_sync_point", "sync_solver", "sync_device", "reset_step_counters", "save_state", "restore_state"):
         getattr(lib, "mpgos_coupled_" + f).argtypes = [v]
     lib.mpgos_coupled_read_step_counters.argtypes = [v, v, v]
+    lib.mpgos_coupled_upload.argtypes = [v, C.c_int, v, C.c_size_t]
+    lib.mpgos_coupled_download.argtypes = [v, C.c_int, v, C.c_size_t]
     lib.mpgos_coupled_stream.restype = v
     lib.mpgos_coupled_stream.argtypes = [v]
     lib.mpgos_coupled_builtin_desc.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_CDesc)]
@@ -206,6 +209,13 @@ class CoupledProblemSolver:
 
     def SynchroniseDevice(self):
         _check(self._lib, self._lib.mpgos_coupled_sync_device(self._h))
+
+    # copies between caller-owned (pinned) host arrays and the device buffers, asynchronous on the solver's stream
+    def Upload(self, variable: int, host_ptr: int, nbytes: int):
+        _check(self._lib, self._lib.mpgos_coupled_upload(self._h, int(variable), host_ptr, nbytes))
+
+    def Download(self, variable: int, host_ptr: int, nbytes: int):
+        _check(self._lib, self._lib.mpgos_coupled_download(self._h, int(variable), host_ptr, nbytes))
 
     def StepCounters(self):
         att, acc = np.zeros(self.desc.NS, np.uint64), np.zeros(self.desc.NS, np.uint64)

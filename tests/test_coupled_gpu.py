@@ -228,3 +228,27 @@ def test_fp32_tensor_core_coupling_3xtf32(ups, ns, pkg, oracle):
     assert rel_err(tc.ActualState, sc.ActualState).max() < 5e-3
     assert np.median(rel_err(tc.ActualState, ref.ActualState)) < 2e-5
     assert np.abs(tatt - satt).max() <= 0.1 * satt.max() and np.abs(tatt - ratt).max() <= 0.15 * ratt.max()
+
+
+def test_upload_download_with_caller_owned_arrays(pkg):
+    """mpgos_coupled_upload / _download move caller-owned host arrays (the e2e path of bench.py) and give the same result as
+    filling the solver's pinned mirrors; wrong sizes and the packed coupling matrix are refused."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=16, UPS=64, amplitude=(0.2, 1.0))
+    ref, ratt, _ = pkg.run_coupled_workload(wl, phases=1)
+    V = pkg.CoupledVariables
+    with pkg.CoupledProblemSolver(wl.name, 16, 64) as ps:
+        pkg.apply_coupled_workload(ps, wl)
+        ps.SynchroniseFromHostToDevice(V.All)
+        state = np.ascontiguousarray(wl.buffers.ActualState) * 1.0
+        ps.host(V.ActualState)[...] = -7.0                                  # the mirror is NOT what gets integrated
+        ps.Upload(V.ActualState, state.ctypes.data, state.nbytes)
+        ps.Solve()
+        out = np.empty_like(state)
+        ps.Download(V.ActualState, out.ctypes.data, out.nbytes)
+        ps.SynchroniseDevice()
+        assert np.array_equal(out, ref.ActualState)
+        with pytest.raises(pkg.MpgosError):
+            ps.Upload(V.ActualState, state.ctypes.data, state.nbytes - 8)
+        with pytest.raises(pkg.MpgosError):
+            ps.Upload(V.CouplingMatrix, state.ctypes.data, 64 * 64 * 8)
