@@ -22,8 +22,9 @@ Timed regions (all after W >= 3 warm-up steps):
           from pinned host memory, integrates, and downloads state + time.  The sweep is driven as
           ``--e2e-chunks`` solver objects with their own streams so that copies overlap kernels --
           the double-buffering pattern of the reference's own tutorial
-          (Tutorials_SingleSystem_PerThread/T7_DoubleBuffering/DoubleBuffering.cu:89-144); host wall
-          clock between synchronisation points, max over ranks.
+          (Tutorials_SingleSystem_PerThread/T7_DoubleBuffering/DoubleBuffering.cu:89-144): an object is
+          waited for, refilled and relaunched while the others compute; every step uploads and downloads
+          every chunk, the region ends when the last result is in host memory; host wall clock, max over ranks.
 Multi-GPU: one process per GPU (torchrun); instances are independent, so each rank integrates its own
 tile-cyclic shard of a (N x per-GPU)-instance sweep with no collective on the data path (weak
 scaling); torch.distributed/NCCL only carries the barrier and the reduction of the timings.
@@ -360,19 +361,26 @@ def main():
         d2h += do
 
     def step_e2e():
+        # T7's loop: wait for a solver object (its previous sweep is then in the caller's arrays), refill it and launch it again,
+        # while the other objects compute -- so the copies of one step also overlap the kernels of its neighbours
         for a in e2e_arms:
+            a.finish_e2e()
             a.enqueue_e2e(args.phases)
+
+    def drain_e2e():
         for a in e2e_arms:
             a.finish_e2e()
 
     for _ in range(2):
         step_e2e()
+    drain_e2e()
     for a in e2e_arms:
         a.ps.ResetStepCounters()
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    drain_e2e()
     torch.cuda.synchronize(); barrier()
     e2e_s = time.perf_counter() - t0
     e2e_attempted = sum(a.total_steps()[0] for a in e2e_arms)

@@ -21,7 +21,7 @@
 //   * callbacks receive the run-time instance count through `NT` exactly as before, but the
 //     device-side warnings of the reference are printed only after
 //     SolverOption(DeviceMessages, 1);
-//   * extra options LaneRefill / DeviceMessages and the StepCounters() accessor.
+//   * extra options LaneRefill / DeviceMessages / DispatchOrder and the StepCounters() accessor.
 #ifndef SINGLESYSTEM_PERTHREAD_INTERFACE_H
 #define SINGLESYSTEM_PERTHREAD_INTERFACE_H
 
@@ -47,7 +47,7 @@ enum ListOfVariables { All, TimeDomain, ActualState, ActualTime, ControlParamete
 enum ListOfSolverOptions { ThreadsPerBlock, InitialTimeStep, ActiveNumberOfThreads, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit,
                            TimeStepShrinkLimit, RelativeTolerance, AbsoluteTolerance, EventTolerance, EventDirection,
                            DenseOutputMinimumTimeStep, DenseOutputSaveFrequency, PreferSharedMemory,
-                           LaneRefill, DeviceMessages };
+                           LaneRefill, DeviceMessages, DispatchOrder };
 
 inline std::string VariablesToString(ListOfVariables v)
 {
@@ -62,8 +62,8 @@ inline std::string SolverOptionsToString(ListOfSolverOptions o)
 	static const char* const names[] = { "ThreadsPerBlock", "InitialTimeStep", "ActiveNumberOfThreads", "MaximumTimeStep", "MinimumTimeStep",
 	                                     "TimeStepGrowLimit", "TimeStepShrinkLimit", "RelativeTolerance", "AbsoluteTolerance", "EventTolerance",
 	                                     "EventDirection", "DenseOutputMinimumTimeStep", "DenseOutputSaveFrequency", "PreferSharedMemory",
-	                                     "LaneRefill", "DeviceMessages" };
-	return ((int)o >= 0 && (int)o <= (int)DeviceMessages) ? names[(int)o] : "Non-existent solver option!";
+	                                     "LaneRefill", "DeviceMessages", "DispatchOrder" };
+	return ((int)o >= 0 && (int)o <= (int)DispatchOrder) ? names[(int)o] : "Non-existent solver option!";
 }
 
 // ---- device discovery helpers (Interface.cuh:218-304) ---------------------------------------------

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPGOS_B200_ABI_VERSION 1
+#define MPGOS_B200_ABI_VERSION 2
 
 typedef enum mpgos_status
 {
@@ -69,7 +69,10 @@ typedef enum mpgos_option
 	                               n = 1..32: persistent warps; when a warp ballot counts >= n idle
 	                               lanes they take the next n instances from a device-side queue
 	                               together (1 = every finished lane at once, 32 = whole warps) */
-	MPGOS_OPT_DeviceMessages    /* 1: device-side printf of the reference's warnings; 0 (default) */
+	MPGOS_OPT_DeviceMessages,   /* 1: device-side printf of the reference's warnings; 0 (default) */
+	MPGOS_OPT_DispatchOrder     /* direct mapping: 1 (default): from the second phase on, thread blocks are dispatched in order of
+	                               decreasing cost of their instances in the previous phase (longest first: the tail of the launch
+	                               is then made of the cheapest blocks); 0: in index order, as the reference */
 } mpgos_option;
 
 /* Template arguments of the reference's ProblemSolver (ST/Interface.cuh:117-118) as run-time data.
@@ -100,6 +103,10 @@ typedef struct mpgos_perthread_launch
 	unsigned long long* d_StepsAttempted;   /* [NT] accumulated stepper invocations, never NULL */
 	unsigned long long* d_StepsAccepted;    /* [NT] accumulated accepted steps, never NULL */
 	unsigned int*       d_WorkQueue;        /* [1] device-side instance queue head (lane refill) */
+	unsigned int*       d_LastPhaseSteps;   /* [NT] stepper invocations of the phase just integrated, written at phase end */
+	int*                d_DispatchOrder;    /* [NT/32 + 1] scratch: tile ids in dispatch order */
+	unsigned int*       d_DispatchScratch;  /* [NT/32 + 1 + 768] scratch: cost bucket per tile, histogram, bucket starts, fill counts */
+	int                 DispatchHistory;    /* 1: d_LastPhaseSteps describes the previous phase of these instances and cost order is wanted */
 	const double* RelativeTolerance;        /* host [SD] */
 	const double* AbsoluteTolerance;        /* host [SD] */
 	const double* EventTolerance;           /* host [NE] */

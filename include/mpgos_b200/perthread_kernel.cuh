@@ -65,6 +65,8 @@ struct PerThreadArgs
 	unsigned long long* StepsAttempted;
 	unsigned long long* StepsAccepted;
 	unsigned int*       WorkQueue;
+	unsigned int*       LastPhaseSteps;     // [Stride] attempted steps of this phase (cost history for the dispatch order)
+	const int*          DispatchOrder;      // tile ids in dispatch order, or nullptr: block b integrates tile b
 	int  Stride;             // instances held by the buffers (SoA stride)
 	int  Active;             // instances [0, Active) are integrated
 	int  InstanceOffset;     // global id of local instance 0
@@ -726,12 +728,15 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 		if (DENSE) a.DenseOutputIndex[inst] = s.dense_index;
 		a.StepsAttempted[inst] += s.attempted;
 		a.StepsAccepted[inst]  += s.accepted;
+		a.LastPhaseSteps[inst] = s.attempted;
 	};
 
 	if (!REFILL)
 	{
 		// direct mapping: thread i integrates instance i; the step loop is the whole kernel
-		const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+		// blocks are dispatched in blockIdx order; with a cost history the launcher lists the tiles longest first
+		const int tile = a.DispatchOrder ? a.DispatchOrder[blockIdx.x] : (int)blockIdx.x;
+		const int inst = tile * blockDim.x + threadIdx.x;
 		if (inst >= a.Active) return;
 		load(inst);
 		P dt;
@@ -776,6 +781,58 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Dispatch order of the direct mapping.  The hardware hands out thread blocks in blockIdx order, so a launch ends with
+// whatever its last blocks cost: when the expensive instances sit at the end of a sweep the SMs idle behind them (the
+// "tailing effect"; Keller-Miksis frequency sweep, cost ratio 28 along the sweep: 37.5 ms with the expensive end first,
+// 48.4 ms with it last; Lorenz: 4.66 vs 4.77 ms).  From the second phase on the previous phase's step counts say what
+// each tile costs, and three small kernels list the tiles in order of decreasing cost (counting sort over 256
+// logarithmic buckets, 8 per octave).  Results do not depend on the order: instances are independent.
+static __global__ void dispatch_cost_histogram(const unsigned int* __restrict__ last, int active, int block, int tiles,
+                                               unsigned int* __restrict__ bucket_of, unsigned int* __restrict__ hist)
+{
+	const int tile = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (tile >= tiles) return;
+	unsigned cost = 0;
+	for (int i = lane; i < block; i += 32)
+	{
+		const int inst = tile * block + i;
+		if (inst < active) cost += last[inst];
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+	if (lane == 0)
+	{
+		unsigned b = 0;
+		if (cost)
+		{
+			const int e = 31 - __clz(cost);
+			b = (unsigned)e * 8u + ((e >= 3 ? cost >> (e - 3) : cost << (3 - e)) & 7u);
+		}
+		bucket_of[tile] = b;
+		atomicAdd(&hist[b], 1u);
+	}
+}
+
+static __global__ void dispatch_bucket_starts(unsigned int* __restrict__ hist)      // hist[0..255] -> starts [256..511] (descending cost), fill [512..767] = 0
+{
+	__shared__ unsigned int h[256];
+	h[threadIdx.x] = hist[threadIdx.x];
+	__syncthreads();
+	unsigned start = 0;
+	for (int b = 255; b > (int)threadIdx.x; b--) start += h[b];
+	hist[256 + threadIdx.x] = start;
+	hist[512 + threadIdx.x] = 0;
+}
+
+static __global__ void dispatch_scatter(const unsigned int* __restrict__ bucket_of, unsigned int* __restrict__ hist, int tiles, int* __restrict__ order)
+{
+	const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tile >= tiles) return;
+	const unsigned b = bucket_of[tile];
+	order[hist[256 + b] + atomicAdd(&hist[512 + b], 1u)] = tile;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host-side launcher generated next to the kernel.
 
 // MINB = resident 256-thread blocks per SM the kernel is compiled for, i.e. its register cap: 1 -> 255, 2 -> 128,
@@ -787,7 +844,7 @@ template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA
 struct PerThreadLauncher
 {
 	template <bool REFILL>
-	static cudaError_t enqueue(const mpgos_perthread_launch* L, const PerThreadArgs<P, SD, NE>& args, cudaStream_t stream)
+	static cudaError_t enqueue(const mpgos_perthread_launch* L, PerThreadArgs<P, SD, NE>& args, cudaStream_t stream)
 	{
 		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL, MINB>;
 		int block = L->ThreadsPerBlock;
@@ -809,6 +866,23 @@ struct PerThreadLauncher
 			e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
 			if (e != cudaSuccess) return e;
 		}
+		else
+		{
+			// cost-ordered dispatch (see dispatch_cost_histogram): only when the launch spans several waves of blocks
+			args.DispatchOrder = nullptr;
+			const int sms = L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148;
+			if (L->DispatchHistory && L->d_DispatchOrder && L->d_DispatchScratch && grid > 16 * sms)
+			{
+				unsigned int* bucket_of = L->d_DispatchScratch;
+				unsigned int* hist = L->d_DispatchScratch + (L->desc.NT / 32 + 1);
+				cudaError_t e = cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), stream);
+				if (e != cudaSuccess) return e;
+				dispatch_cost_histogram<<<(grid + 7) / 8, 256, 0, stream>>>(L->d_LastPhaseSteps, active, block, grid, bucket_of, hist);
+				dispatch_bucket_starts<<<1, 256, 0, stream>>>(hist);
+				dispatch_scatter<<<(grid + 255) / 256, 256, 0, stream>>>(bucket_of, hist, grid, L->d_DispatchOrder);
+				args.DispatchOrder = L->d_DispatchOrder;
+			}
+		}
 		kernel<<<grid, block, 0, stream>>>(args);
 		return cudaGetLastError();
 	}
@@ -828,6 +902,7 @@ struct PerThreadLauncher
 		a.IntegerAccessories = L->d_IntegerAccessories;  a.DenseOutputIndex = L->d_DenseOutputIndex;
 		a.DenseOutputTimeInstances = (P*)L->d_DenseOutputTimeInstances;  a.DenseOutputStates = (P*)L->d_DenseOutputStates;
 		a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
+		a.LastPhaseSteps = L->d_LastPhaseSteps;  a.DispatchOrder = nullptr;
 		a.Stride = d.NT;
 		a.Active = L->ActiveNumberOfThreads < d.NT ? L->ActiveNumberOfThreads : d.NT;
 		a.InstanceOffset = d.InstanceOffset;

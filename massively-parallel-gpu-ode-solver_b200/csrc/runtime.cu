@@ -133,6 +133,10 @@ struct mpgos_perthread_solver
 	unsigned long long* d_accepted = nullptr;
 	unsigned long long* d_totals = nullptr;   // [2]
 	unsigned int*       d_queue = nullptr;
+	unsigned int*       d_last_steps = nullptr;   // [NT] steps of the previous phase (cost history of the dispatch order)
+	int*                d_order = nullptr;        // [NT/32 + 1]
+	unsigned int*       d_order_scratch = nullptr;   // [NT/32 + 1 + 768]
+	bool                history_valid = false;    // d_last_steps describes the previous phase of the instances now on the device
 	void*               snapshot[13] = {};        // device-side checkpoint, allocated on first save
 	// options (Interface.cuh:475-496 defaults)
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12;
@@ -143,6 +147,7 @@ struct mpgos_perthread_solver
 	int    PreferSharedMemory = 1;
 	int    LaneRefill = 0;      // measured on B200: the direct mapping wins once the register cap gives >= 5 warps per sub-partition (profiles/)
 	int    DeviceMessages = 0;
+	int    DispatchOrder = 1;
 	std::vector<double> rtol, atol, evtol;
 	std::vector<int>    evdir;
 };
@@ -228,8 +233,12 @@ int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_sol
 		ok(cudaMalloc(&s->d_accepted, 8 * NT), "cudaMalloc");
 		ok(cudaMalloc(&s->d_totals, 16), "cudaMalloc");
 		ok(cudaMalloc(&s->d_queue, 4), "cudaMalloc");
+		ok(cudaMalloc(&s->d_last_steps, 4 * NT), "cudaMalloc");
+		ok(cudaMalloc(&s->d_order, 4 * (NT / 32 + 1)), "cudaMalloc");
+		ok(cudaMalloc(&s->d_order_scratch, 4 * (NT / 32 + 1 + 768)), "cudaMalloc");
 		if (rc == MPGOS_OK)
 		{
+			ok(cudaMemset(s->d_last_steps, 0, 4 * NT), "cudaMemset");
 			ok(cudaMemset(s->d_attempted, 0, 8 * NT), "cudaMemset");
 			ok(cudaMemset(s->d_accepted, 0, 8 * NT), "cudaMemset");
 			ok(cudaMemset(s->d_queue, 0, 4), "cudaMemset");
@@ -251,6 +260,9 @@ int mpgos_perthread_destroy(mpgos_perthread_solver* s)
 	if (s->d_accepted) cudaFree(s->d_accepted);
 	if (s->d_totals) cudaFree(s->d_totals);
 	if (s->d_queue) cudaFree(s->d_queue);
+	if (s->d_last_steps) cudaFree(s->d_last_steps);
+	if (s->d_order) cudaFree(s->d_order);
+	if (s->d_order_scratch) cudaFree(s->d_order_scratch);
 	if (s->t0) cudaEventDestroy(s->t0);
 	if (s->t1) cudaEventDestroy(s->t1);
 	if (s->event) cudaEventDestroy(s->event);
@@ -295,6 +307,7 @@ int mpgos_perthread_set_option(mpgos_perthread_solver* s, int option, double val
 		case MPGOS_OPT_PreferSharedMemory:         s->PreferSharedMemory = (int)value; break;
 		case MPGOS_OPT_LaneRefill:                 s->LaneRefill = (int)value < 0 ? 0 : ((int)value > 32 ? 32 : (int)value); break;
 		case MPGOS_OPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
+		case MPGOS_OPT_DispatchOrder:              s->DispatchOrder = (int)value != 0; break;
 		default: return fail(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
 	}
 	return MPGOS_OK;
@@ -341,6 +354,7 @@ int mpgos_perthread_get_option(mpgos_perthread_solver* s, int option, int index,
 		case MPGOS_OPT_PreferSharedMemory:         *value = s->PreferSharedMemory; break;
 		case MPGOS_OPT_LaneRefill:                 *value = s->LaneRefill; break;
 		case MPGOS_OPT_DeviceMessages:             *value = s->DeviceMessages; break;
+		case MPGOS_OPT_DispatchOrder:              *value = s->DispatchOrder; break;
 		case MPGOS_OPT_RelativeTolerance: if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->rtol[index]; break;
 		case MPGOS_OPT_AbsoluteTolerance: if (index < 0 || index >= SD) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->atol[index]; break;
 		case MPGOS_OPT_EventTolerance:    if (index < 0 || index >= NE) return fail(MPGOS_ERR_BOUNDS, "index"); *value = s->evtol[index]; break;
@@ -365,6 +379,7 @@ static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device
 	else if (variable == MPGOS_VAR_DenseOutput) { list[n++] = MPGOS_VAR_DenseIndex;  list[n++] = MPGOS_VAR_DenseTime;  list[n++] = MPGOS_VAR_DenseState; }
 	else if (is_buffer_variable(variable)) list[n++] = variable;
 	else return fail(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
+	if (to_device) s->history_valid = false;      // new instances or parameters: the cost history no longer describes them
 	for (int i = 0; i < n; i++)
 	{
 		Mirror& m = s->var[list[i]];
@@ -386,6 +401,7 @@ int mpgos_perthread_upload(mpgos_perthread_solver* s, int variable, const void* 
 	if (bytes == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
+	s->history_valid = false;
 	return MPGOS_OK;
 }
 
@@ -411,6 +427,8 @@ static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
 	L.d_DenseOutputIndex = (int*)s->var[MPGOS_VAR_DenseIndex].dev;
 	L.d_DenseOutputTimeInstances = s->var[MPGOS_VAR_DenseTime].dev;  L.d_DenseOutputStates = s->var[MPGOS_VAR_DenseState].dev;
 	L.d_StepsAttempted = s->d_attempted;  L.d_StepsAccepted = s->d_accepted;  L.d_WorkQueue = s->d_queue;
+	L.d_LastPhaseSteps = s->d_last_steps;  L.d_DispatchOrder = s->d_order;  L.d_DispatchScratch = s->d_order_scratch;
+	L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
 	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();
 	L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
 	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
@@ -429,6 +447,7 @@ int mpgos_perthread_solve(mpgos_perthread_solver* s, mpgos_perthread_launcher la
 	fill_launch(s, L);
 	const int e = launcher(&L, (void*)s->stream);
 	if (e != 0) return fail(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+	s->history_valid = true;
 	return MPGOS_OK;
 }
 
@@ -441,8 +460,10 @@ int mpgos_perthread_solve_timed(mpgos_perthread_solver* s, mpgos_perthread_launc
 	CUDA_TRY(cudaEventRecord(s->t0, s->stream));
 	for (int p = 0; p < phases; p++)
 	{
+		L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
 		const int e = launcher(&L, (void*)s->stream);
 		if (e != 0) return fail(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+		s->history_valid = true;
 	}
 	CUDA_TRY(cudaEventRecord(s->t1, s->stream));
 	CUDA_TRY(cudaEventSynchronize(s->t1));
@@ -538,6 +559,7 @@ int mpgos_perthread_restore_state(mpgos_perthread_solver* s)
 		if (!s->snapshot[v]) return fail(MPGOS_ERR_ARGUMENT, "restore_state: no snapshot saved");
 		CUDA_TRY(cudaMemcpyAsync(m.dev, s->snapshot[v], m.bytes, cudaMemcpyDeviceToDevice, s->stream));
 	}
+	s->history_valid = false;      // another trajectory from here on: the step counts of the last phase say nothing about it
 	return MPGOS_OK;
 }
 

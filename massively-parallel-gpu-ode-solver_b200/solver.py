@@ -64,6 +64,7 @@ class Options(enum.IntEnum):             # Interface.cuh:49-62 (+ two of ours)
     PreferSharedMemory = 13
     LaneRefill = 14
     DeviceMessages = 15
+    DispatchOrder = 16
 
 
 _INDEXED = (Options.RelativeTolerance, Options.AbsoluteTolerance, Options.EventTolerance, Options.EventDirection)

@@ -276,3 +276,27 @@ def test_rkck45_against_reference_mpgos_on_the_same_gpu(name, tol, frac, cases, 
     assert np.median(err) < 1e-12
     if ref.IntegerAccessories.size:
         assert (out.IntegerAccessories == ref.IntegerAccessories).mean() >= frac
+
+
+def test_cost_ordered_dispatch_changes_nothing_but_the_order(cases, pkg, workloads):
+    """DispatchOrder = 1 (default) lists the thread blocks of the second and later phases longest first, from the previous
+    phase's step counts; instances are independent, so every result is bit-identical to index-order dispatch.  A launch must
+    span many waves of blocks for the order to be computed at all, hence the larger sweep."""
+    from cases import subsample
+    wl = subsample(workloads.impact_t6(NT=1 << 20), 1 << 18)
+    runs = []
+    for order in (0, 1):
+        with pkg.ProblemSolver(wl.name, wl.NT, NDO=wl.shape.NDO, Algorithm=wl.shape.Algorithm, Precision=wl.shape.dtype) as ps:
+            pkg.apply_workload(ps, wl)
+            ps.SolverOption(pkg.Options.DispatchOrder, order)
+            ps.SolverOption(pkg.Options.ThreadsPerBlock, 64)
+            ps.SynchroniseFromHostToDevice(pkg.Variables.All)
+            for _ in range(3):
+                ps.Solve()
+            out = pkg.read_back(ps, wl)
+            att, acc = ps.StepCounters()
+            runs.append((out, att, acc))
+    (a, aatt, aacc), (b, batt, bacc) = runs
+    for f in RESULT_FIELDS:
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+    assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc)
