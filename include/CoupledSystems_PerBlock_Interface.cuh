@@ -18,7 +18,7 @@
 //     system, as many systems per block as fit 512 threads; 8 in lockstep on the FP64 tensor cores for dense matrices);
 //   * SharedGlobalVariables / SharedCouplingMatrices are accepted and ignored: both always live in shared memory;
 //   * device-side warnings are printed only after SolverOption(DeviceMessages, 1);
-//   * extra options DeviceMessages / TensorCoreCoupling and the StepCounters() accessor;
+//   * extra options DeviceMessages / TensorCoreCoupling / DispatchOrder and the StepCounters() accessor;
 //   * Precision = double or float; dense shared matrices are multiplied on the tensor cores in both (FP64 DMMA; FP32 as 3xTF32).
 #ifndef COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
 #define COUPLEDSYSTEMS_PERBLOCK_INTERFACE_H
@@ -47,7 +47,7 @@ enum ListOfVariables { All, TimeDomain, ActualTime, ActualState, UnitParameters,
 enum ListOfSolverOptions { InitialTimeStep, ActiveSystems, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit,
                            RelativeTolerance, AbsoluteTolerance, EventTolerance, EventDirection, DenseOutputSaveFrequency,
                            DenseOutputMinimumTimeStep, SharedGlobalVariables, SharedCouplingMatrices,
-                           DeviceMessages, TensorCoreCoupling };
+                           DeviceMessages, TensorCoreCoupling, DispatchOrder };
 
 inline std::string VariablesToString(ListOfVariables v)
 {
@@ -63,8 +63,8 @@ inline std::string SolverOptionsToString(ListOfSolverOptions o)
 	static const char* const names[] = { "InitialTimeStep", "ActiveSystems", "MaximumTimeStep", "MinimumTimeStep", "TimeStepGrowLimit",
 	                                     "TimeStepShrinkLimit", "RelativeTolerance", "AbsoluteTolerance", "EventTolerance", "EventDirection",
 	                                     "DenseOutputSaveFrequency", "DenseOutputMinimumTimeStep", "SharedGlobalVariables",
-	                                     "SharedCouplingMatrices", "DeviceMessages", "TensorCoreCoupling" };
-	return ((int)o >= 0 && (int)o <= (int)TensorCoreCoupling) ? names[(int)o] : "Non-existent solver option!";
+	                                     "SharedCouplingMatrices", "DeviceMessages", "TensorCoreCoupling", "DispatchOrder" };
+	return ((int)o >= 0 && (int)o <= (int)DispatchOrder) ? names[(int)o] : "Non-existent solver option!";
 }
 
 // ---- device discovery helpers (CP/Interface.cuh:258-344) ---------------------------------------------------------------

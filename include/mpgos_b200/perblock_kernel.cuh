@@ -50,6 +50,7 @@ struct PerBlockArgs
 	P* CouplingMatrix;  P* CouplingStrength;  int* CouplingIndex;
 	int* DenseOutputIndex;  P* DenseOutputTimeInstances;  P* DenseOutputStates;
 	unsigned long long* StepsAttempted;  unsigned long long* StepsAccepted;  unsigned int* WorkQueue;
+	unsigned int* LastPhaseSteps;  const int* DispatchOrder;      // cost history and queue order (perthread_kernel.cuh, dispatch_cost_histogram)
 	int NS, Active, SystemOffset, DenseCapacity, DenseOutputSaveFrequency, DeviceMessages;
 	P   InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep, MinimumTimeStepGuard;
 	P   RelativeTolerance[UD];  P AbsoluteTolerance[UD];
@@ -340,7 +341,8 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	int iuacc[AtLeastOne<NiUA>::value];
 	P   dt_new = a.InitialTimeStep;
 	unsigned attempted = 0, accepted = 0;
-	int    sys = blockIdx.x * SPBK + slot, gsys = 0;
+	int    pos = blockIdx.x * SPBK + slot;      // position in the system queue
+	int    sys = 0, gsys = 0;
 	size_t ug = 0;
 	bool   have = false, dry = false, first = true;
 	int    buf = 0;
@@ -357,12 +359,13 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			{
 				if (unit == 0) S.next_system = (int)(gridDim.x * SPBK + atomicAdd(a.WorkQueue, 1u));
 				slot_barrier<UPSP>(slot);
-				sys = S.next_system;
+				pos = S.next_system;
 			}
 			first = false;
-			if (sys >= a.Active) dry = true;
+			if (pos >= a.Active) dry = true;
 			else
 			{
+				sys = a.DispatchOrder ? a.DispatchOrder[pos] : pos;      // with a cost history: the longest systems first
 				gsys = sys + a.SystemOffset;
 				ug   = (size_t)sys * UPS + (is_unit ? unit : 0);
 				// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
@@ -757,6 +760,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				if (DENSE) a.DenseOutputIndex[sys] = S.dense_index;
 				a.StepsAttempted[sys] += attempted;
 				a.StepsAccepted[sys]  += accepted;
+				a.LastPhaseSteps[sys] = attempted;
 			}
 			slot_barrier<UPSP>(slot);
 			have = false;
@@ -800,7 +804,22 @@ struct PerBlockLauncher
 		if (grid > resident) grid = resident;
 		e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
 		if (e != cudaSuccess) return (int)e;
-		kernel<<<grid, SLOTS * UPSP, smem, stream>>>(a);
+		// queue order: with the previous phase's step counts at hand and more systems than two rounds of slots, the longest first
+		// (C5, whose expensive systems sit at the end of the amplitude sweep: 18.0 instead of 19.4 ms)
+		PerBlockArgs<P, UD, NE> args = a;
+		args.DispatchOrder = nullptr;
+		if (L->DispatchHistory && L->d_DispatchOrder && L->d_DispatchScratch && a.Active > 2 * grid * SLOTS)
+		{
+			unsigned int* bucket_of = L->d_DispatchScratch;
+			unsigned int* hist = L->d_DispatchScratch + L->desc.NS;
+			e = cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), stream);
+			if (e != cudaSuccess) return (int)e;
+			dispatch_cost_histogram<<<(a.Active + 7) / 8, 256, 0, stream>>>(L->d_LastPhaseSteps, a.Active, 1, a.Active, bucket_of, hist);
+			dispatch_bucket_starts<<<1, 256, 0, stream>>>(hist);
+			dispatch_scatter<<<(a.Active + 255) / 256, 256, 0, stream>>>(bucket_of, hist, a.Active, L->d_DispatchOrder);
+			args.DispatchOrder = L->d_DispatchOrder;
+		}
+		kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
 		return (int)cudaGetLastError();
 	}
 
@@ -818,6 +837,7 @@ struct PerBlockLauncher
 		a.IntegerSystemAccessories = L->d_IntegerSystemAccessories;  a.CouplingMatrix = (P*)L->d_CouplingMatrix;  a.CouplingStrength = (P*)L->d_CouplingStrength;
 		a.CouplingIndex = L->d_CouplingIndex;  a.DenseOutputIndex = L->d_DenseOutputIndex;  a.DenseOutputTimeInstances = (P*)L->d_DenseOutputTimeInstances;
 		a.DenseOutputStates = (P*)L->d_DenseOutputStates;  a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
+		a.LastPhaseSteps = L->d_LastPhaseSteps;  a.DispatchOrder = nullptr;
 		a.NS = d.NS;  a.Active = L->ActiveSystems < d.NS ? L->ActiveSystems : d.NS;  a.SystemOffset = d.SystemOffset;  a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;  a.DeviceMessages = L->DeviceMessages;
 		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;  a.MinimumTimeStep = (P)L->MinimumTimeStep;

@@ -45,7 +45,9 @@ typedef enum mpgos_coupled_option
 	MPGOS_COPT_EventTolerance, MPGOS_COPT_EventDirection, MPGOS_COPT_DenseOutputSaveFrequency, MPGOS_COPT_DenseOutputMinimumTimeStep,
 	MPGOS_COPT_SharedGlobalVariables, MPGOS_COPT_SharedCouplingMatrices,
 	MPGOS_COPT_DeviceMessages,
-	MPGOS_COPT_TensorCoreCoupling   /* 1 (default): dense shared coupling matrices go through FP64 tensor-core MMA where the shape allows; 0: scalar sums */
+	MPGOS_COPT_TensorCoreCoupling,  /* 1 (default): dense shared coupling matrices go through tensor-core MMA where the shape allows; 0: scalar sums */
+	MPGOS_COPT_DispatchOrder        /* 1 (default): from the second phase on the system queue hands out the systems in order of decreasing cost in the
+	                                   previous phase (longest first); 0: in index order */
 } mpgos_coupled_option;
 
 /* Template arguments of the reference's coupled ProblemSolver (CP/Interface.cuh:135-136) as run-time data.  TPB and SPB
@@ -69,6 +71,10 @@ typedef struct mpgos_coupled_launch
 	unsigned long long* d_StepsAttempted;   /* [NS] */
 	unsigned long long* d_StepsAccepted;    /* [NS] */
 	unsigned int*       d_WorkQueue;        /* [1] */
+	unsigned int*       d_LastPhaseSteps;   /* [NS] stepper invocations of the phase just integrated */
+	int*                d_DispatchOrder;    /* [NS] scratch: system ids in queue order */
+	unsigned int*       d_DispatchScratch;  /* [NS + 768] scratch of the ordering kernels */
+	int                 DispatchHistory;    /* 1: d_LastPhaseSteps describes the previous phase of these systems and cost order is wanted */
 	size_t CouplingMatrixElements;
 	const double* RelativeTolerance;  const double* AbsoluteTolerance;  const double* EventTolerance;  const int* EventDirection;   /* host */
 	double InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep;

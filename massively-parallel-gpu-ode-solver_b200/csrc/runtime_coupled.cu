@@ -36,6 +36,11 @@ struct mpgos_coupled_solver
 	std::vector<double> original_matrix;     // h_CouplingMatrixOriginal (host only, CP/Interface.cuh:461)
 	unsigned long long *d_attempted = nullptr, *d_accepted = nullptr;
 	unsigned int* d_queue = nullptr;
+	unsigned int* d_last_steps = nullptr;      // [NS] steps of the previous phase (cost history of the queue order)
+	int*          d_order = nullptr;           // [NS]
+	unsigned int* d_order_scratch = nullptr;   // [NS + 768]
+	bool          history_valid = false;
+	int           DispatchOrder = 1;
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12, TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1;
 	double DenseOutputMinimumTimeStep = 0.0;
 	int DenseOutputSaveFrequency = 1, ActiveSystems = 0, DeviceMessages = 0, SharedGlobalVariables = 1, SharedCouplingMatrices = 0, TensorCoreCoupling = 1;
@@ -114,6 +119,10 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_attempted, 8 * NS);
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_accepted, 8 * NS);
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_queue, 4);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_last_steps, 4 * NS);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_order, 4 * NS);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_order_scratch, 4 * (NS + 768));
+	if (e == cudaSuccess) e = cudaMemset(s->d_last_steps, 0, 4 * NS);
 	if (e == cudaSuccess) e = cudaMemset(s->d_attempted, 0, 8 * NS);
 	if (e == cudaSuccess) e = cudaMemset(s->d_accepted, 0, 8 * NS);
 	if (e != cudaSuccess) { mpgos_coupled_destroy(s); return CFAIL(MPGOS_ERR_CUDA, "coupled solver construction failed -> %s", cudaGetErrorString(e)); }
@@ -130,6 +139,9 @@ int mpgos_coupled_destroy(mpgos_coupled_solver* s)
 	if (s->d_attempted) cudaFree(s->d_attempted);
 	if (s->d_accepted) cudaFree(s->d_accepted);
 	if (s->d_queue) cudaFree(s->d_queue);
+	if (s->d_last_steps) cudaFree(s->d_last_steps);
+	if (s->d_order) cudaFree(s->d_order);
+	if (s->d_order_scratch) cudaFree(s->d_order_scratch);
 	if (s->t0) cudaEventDestroy(s->t0);
 	if (s->t1) cudaEventDestroy(s->t1);
 	if (s->event) cudaEventDestroy(s->event);
@@ -200,6 +212,7 @@ int mpgos_coupled_set_option(mpgos_coupled_solver* s, int option, double value)
 		case MPGOS_COPT_SharedCouplingMatrices:     s->SharedCouplingMatrices = (int)value; break;    // accepted, ignored: always shared
 		case MPGOS_COPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
 		case MPGOS_COPT_TensorCoreCoupling:         s->TensorCoreCoupling = (int)value != 0; break;
+		case MPGOS_COPT_DispatchOrder:              s->DispatchOrder = (int)value != 0; break;
 		default: return CFAIL(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
 	}
 	return MPGOS_OK;
@@ -229,6 +242,7 @@ static int ccopy(mpgos_coupled_solver* s, int variable, bool to_device)
 	else if (variable == MPGOS_CVAR_DenseOutput) { list[n++] = MPGOS_CVAR_DenseIndex; list[n++] = MPGOS_CVAR_DenseTime; list[n++] = MPGOS_CVAR_DenseState; }
 	else if (is_cbuffer(variable)) list[n++] = variable;
 	else return CFAIL(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
+	if (to_device) s->history_valid = false;      // new systems or parameters: the cost history no longer describes them
 	for (int i = 0; i < n; i++)
 	{
 		CMirror& m = s->var[list[i]];
@@ -249,6 +263,7 @@ int mpgos_coupled_upload(mpgos_coupled_solver* s, int variable, const void* host
 	if (bytes == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
+	s->history_valid = false;
 	return MPGOS_OK;
 }
 
@@ -275,6 +290,8 @@ static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 	L.d_CouplingIndex = (int*)s->var[MPGOS_CVAR_CouplingIndex].dev;  L.d_DenseOutputIndex = (int*)s->var[MPGOS_CVAR_DenseIndex].dev;
 	L.d_DenseOutputTimeInstances = s->var[MPGOS_CVAR_DenseTime].dev;  L.d_DenseOutputStates = s->var[MPGOS_CVAR_DenseState].dev;
 	L.d_StepsAttempted = s->d_attempted;  L.d_StepsAccepted = s->d_accepted;  L.d_WorkQueue = s->d_queue;
+	L.d_LastPhaseSteps = s->d_last_steps;  L.d_DispatchOrder = s->d_order;  L.d_DispatchScratch = s->d_order_scratch;
+	L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
 	L.CouplingMatrixElements = s->var[MPGOS_CVAR_CouplingMatrix].elements;
 	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();  L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
 	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
@@ -291,6 +308,7 @@ int mpgos_coupled_solve(mpgos_coupled_solver* s, mpgos_coupled_launcher launcher
 	cfill(s, L);
 	const int e = launcher(&L, (void*)s->stream);
 	if (e != 0) return CFAIL(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+	s->history_valid = true;
 	return MPGOS_OK;
 }
 
@@ -303,8 +321,10 @@ int mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher la
 	CUDA_TRY(cudaEventRecord(s->t0, s->stream));
 	for (int p = 0; p < phases; p++)
 	{
+		L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
 		const int e = launcher(&L, (void*)s->stream);
 		if (e != 0) return CFAIL(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
+		s->history_valid = true;
 	}
 	CUDA_TRY(cudaEventRecord(s->t1, s->stream));
 	CUDA_TRY(cudaEventSynchronize(s->t1));
@@ -364,6 +384,7 @@ int mpgos_coupled_restore_state(mpgos_coupled_solver* s)
 		if (!m.snap) return CFAIL(MPGOS_ERR_ARGUMENT, "restore_state: no snapshot saved");
 		CUDA_TRY(cudaMemcpyAsync(m.dev, m.snap, m.bytes, cudaMemcpyDeviceToDevice, s->stream));
 	}
+	s->history_valid = false;
 	return MPGOS_OK;
 }
 

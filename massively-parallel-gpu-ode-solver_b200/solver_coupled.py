@@ -51,6 +51,7 @@ class CoupledOptions(enum.IntEnum):       # CoupledSystems_PerBlock_Interface.cu
     SharedCouplingMatrices = 13
     DeviceMessages = 14
     TensorCoreCoupling = 15
+    DispatchOrder = 16
 
 
 COUPLED_ABI_SYMBOLS = (

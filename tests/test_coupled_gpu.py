@@ -252,3 +252,27 @@ def test_upload_download_with_caller_owned_arrays(pkg):
             ps.Upload(V.ActualState, state.ctypes.data, state.nbytes - 8)
         with pytest.raises(pkg.MpgosError):
             ps.Upload(V.CouplingMatrix, state.ctypes.data, 64 * 64 * 8)
+
+
+def test_cost_ordered_queue_changes_nothing_but_the_order(pkg):
+    """DispatchOrder = 1 (default): from the second phase on the system queue hands out the systems longest first (previous
+    phase's step counts).  Systems are independent: results are bit-identical to index order.  2000 systems, so that the
+    queue is longer than two rounds of slots and the order is actually computed."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=2600, UPS=16, amplitude=(0.1, 2.0))
+    wl.buffers.TimeDomain[1][:] = 0.2
+    runs = []
+    for order in (0, 1):
+        with pkg.CoupledProblemSolver(wl.name, wl.buffers.NS, 16) as ps:
+            pkg.apply_coupled_workload(ps, wl)
+            ps.SolverOption(pkg.CoupledOptions.DispatchOrder, order)
+            ps.SynchroniseFromHostToDevice(pkg.CoupledVariables.All)
+            for _ in range(3):
+                ps.Solve()
+            out = pkg.read_back_coupled(ps, wl)
+            att, acc = ps.StepCounters()
+            runs.append((out, att, acc))
+    (a, aatt, aacc), (b, batt, bacc) = runs
+    for f in COUPLED_RESULT_FIELDS:
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+    assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc) and (aatt > 0).all()
