@@ -18,6 +18,12 @@ if which == "coupled":
     tag, wl, phases = cc["ring_b1c1_rkck45_f32"]; out, att, acc = pkg.run_coupled_workload(wl, phases=1); print("ring f32", int(att.sum()))
     wl = WC.bubble_ensemble(NS=7, UPS=64, amplitude=(0.2, 1.2), dtype=np.float32); wl.buffers.TimeDomain[1][:] = 0.05
     out, att, acc = pkg.run_coupled_workload(wl, phases=1); print("bubble f32 64", int(att.sum()))
+elif which == "dispatch":
+    # launches large enough for the cost-ordered dispatch kernels to run (second phase), short time domains
+    wl = pkg.workloads.impact_t6(NT=1 << 18)
+    out, att, acc = pkg.run_workload(wl, phases=2); print("impact dispatch order", int(att.sum()))
+    wl = WC.bubble_ensemble(NS=2600, UPS=16, amplitude=(0.1, 2.0)); wl.buffers.TimeDomain[1][:] = 0.02
+    out, att, acc = pkg.run_coupled_workload(wl, phases=2); print("bubble queue order", int(att.sum()))
 else:
     c = make_cases(pkg.workloads)
     for name in ("lorenz_rkck45_f64", "duffing_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64", "lorenz_rkck45_f32"):
@@ -26,7 +32,7 @@ else:
             out, att, acc = pkg.run_workload(wl, phases=1, lane_refill=refill); print(name, refill, int(att.sum()))
 PY
 for tool in memcheck racecheck; do
-  for which in coupled perthread; do
+  for which in coupled perthread dispatch; do
     timeout 600 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san_case.py $which > gpurun_out/sanitize_${tool}_${which}.txt 2>&1
     echo "== $tool $which: rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" gpurun_out/sanitize_${tool}_${which}.txt | sort | uniq -c | head -5; grep -cE "^(bubble|ring|lorenz|duffing|impact|keller)" gpurun_out/sanitize_${tool}_${which}.txt
   done
