@@ -10,9 +10,16 @@
 //    (all loops over SD/NE/... are fully unrolled; callbacks are inlined through `Sys`);
 //  * solver options and tolerances travel in the by-value kernel argument (constant bank), so
 //    they cost neither registers nor loads; shared parameters are staged in shared memory;
+//  * the kernel is bound by instruction issue, an FP64 instruction taking two issue slots: everything
+//    below is about executing fewer instructions per step;
 //  * the RKCK45 controller needs no FP64 division and no pow(): the limiting component is found
 //    by cross-multiplication and (tol/err)^(1/5 | 1/4) by division-free Newton steps from a
-//    single-precision seed (error ~1 ulp; exotic operand ranges take the exact slow path);
+//    single-precision seed (3e-14; exotic operand ranges take the exact slow path); whether a step-size limit can
+//    be active at all is screened in single precision;
+//  * the Cash-Karp tableau comes from constant memory row by row, dyadic entries and exact rational relations between
+//    entries as instruction immediates, so that few constants compete for the 63 uniform registers;
+//  * DispatchOrder: from the second phase on, thread blocks integrate the tiles of the sweep longest first (previous
+//    phase's step counts), because a launch ends with whatever its last blocks cost;
 //  * LaneRefill = n: persistent warps.  Lanes that finish their instance store it and go idle;
 //    once a warp ballot counts at least n idle lanes, the warp takes that many instance ids from
 //    a device-side queue with ONE atomic and the idle lanes load them together (coalesced when
