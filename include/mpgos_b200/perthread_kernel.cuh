@@ -265,6 +265,59 @@ __device__ __forceinline__ P ratio_root_fast(P tol, P err, bool accept, float& y
 }
 
 // ---------------------------------------------------------------------------------------------
+// Component-wise helpers of the stages.  FP32: two components per instruction with the packed single-precision
+// instructions of sm_100 (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2; a scalar factor is broadcast by the instruction
+// itself) -- the FP32 kernel is issue-bound, a packed instruction takes one issue slot for two FMAs.  Same roundings as the
+// scalar instructions (results are bit-identical).  Measured: Lorenz (3 components) 0.901 -> 0.838 ms, impact 0.563 -> 0.545;
+// with 2 components the pairing constrains register allocation more than it saves (Keller-Miksis 1.305 -> 1.346 ms), so
+// the packed form is used from 3 components on.
+#ifndef MPGOS_B200_PACKED_F32
+#define MPGOS_B200_PACKED_F32 1
+#endif
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{ unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b)
+{ unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+template <class P, int N, bool PACKED = (MPGOS_B200_PACKED_F32 != 0) && (sizeof(P) == 4) && (N >= 3)>
+struct Vec
+{
+	// out = c * a + b, out = c * a   (out may alias a or b)
+	static __device__ __forceinline__ void fma_c(P* out, P c, const P* a, const P* b)
+	{
+		#pragma unroll
+		for (int i = 0; i < N; i++) out[i] = fma(c, a[i], b[i]);
+	}
+	static __device__ __forceinline__ void mul_c(P* out, P c, const P* a)
+	{
+		#pragma unroll
+		for (int i = 0; i < N; i++) out[i] = c * a[i];
+	}
+};
+template <int N>
+struct Vec<float, N, true>
+{
+	static __device__ __forceinline__ void fma_c(float* out, float c, const float* a, const float* b)
+	{
+		const unsigned long long cc = f32x2_pack(c, c);
+		#pragma unroll
+		for (int i = 0; i + 1 < N; i += 2)
+			f32x2_unpack(f32x2_fma(cc, f32x2_pack(a[i], a[i + 1]), f32x2_pack(b[i], b[i + 1])), out[i], out[i + 1]);
+		if (N & 1) out[N - 1] = fmaf(c, a[N - 1], b[N - 1]);
+	}
+	static __device__ __forceinline__ void mul_c(float* out, float c, const float* a)
+	{
+		const unsigned long long cc = f32x2_pack(c, c);
+		#pragma unroll
+		for (int i = 0; i + 1 < N; i += 2)
+			f32x2_unpack(f32x2_mul(cc, f32x2_pack(a[i], a[i + 1])), out[i], out[i + 1]);
+		if (N & 1) out[N - 1] = c * a[N - 1];
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
 // One instance's registers.
 
 template <class P, int SD, int NCP, int NE, int NA, int NIA>
@@ -421,18 +474,16 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			// no FMA reads three register pairs: on sm_100a such a DFMA occupies the FP64 pipe for 3 cycles instead of 2
 			// (register-file read bandwidth; tools/microbench_fp64.cu).  Rounding differs from the reference's shape by
 			// O(1 ulp) per stage, as FMA contraction already does; the parity build keeps the reference's shape (#else).
-			P c[6];
+			using V = Vec<P, SD>;
+			P c[6], u[SD];
 			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k1[i] *= dt;
+			V::mul_c(k1, dt, k1);
 
 			T = s.t + dt * ck<P>(CK_C2);
 			CkRow<P, CK_A21, 1>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(c[0], k1[i], s.x[i]);
+			V::fma_c(X, c[0], k1, s.x);
 			Sys::OdeFunction(gid, NTG, k2, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k2[i] *= dt;
+			V::mul_c(k2, dt, k2);
 
 			T = s.t + dt * ck<P>(CK_C3);
 #if MPGOS_B200_TABLEAU_COMMON_FACTORS
@@ -440,69 +491,78 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			// a64 = (77/8) a63, e5 = 4.5 e1 -- let a dyadic immediate stand in for a second tableau constant: 6 fewer constants
 			// compete for the 63 uniform registers (fewer R2UR moves of parked constants per step), same instruction count.
 			CkRow<P, CK_A31, 1>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(c[0], fma(P(3.0), k2[i], k1[i]), s.x[i]);
+			V::fma_c(u, P(3.0), k2, k1);
+			V::fma_c(X, c[0], u, s.x);
 #else
 			CkRow<P, CK_A31, 2>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]));
+			V::fma_c(u, c[0], k1, s.x);
+			V::fma_c(X, c[1], k2, u);
 #endif
 			Sys::OdeFunction(gid, NTG, k3, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k3[i] *= dt;
+			V::mul_c(k3, dt, k3);
 
 			T = s.t + dt * ck<P>(CK_C4);
 #if MPGOS_B200_TABLEAU_COMMON_FACTORS
 			CkRow<P, CK_A41, 1>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(c[0], fma(P(4.0), k3[i], fma(P(-3.0), k2[i], k1[i])), s.x[i]);
+			V::fma_c(u, P(-3.0), k2, k1);
+			V::fma_c(u, P(4.0), k3, u);
+			V::fma_c(X, c[0], u, s.x);
 #else
 			CkRow<P, CK_A41, 3>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) X[i] = fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])));
+			V::fma_c(u, c[0], k1, s.x);
+			V::fma_c(u, c[1], k2, u);
+			V::fma_c(X, c[2], k3, u);
 #endif
 			Sys::OdeFunction(gid, NTG, k4, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k4[i] *= dt;
+			V::mul_c(k4, dt, k4);
 
 			T = s.t + dt;
 			CkRow<P, CK_A51, 4>::load(c);
-			#pragma unroll
+			V::fma_c(X, c[0], k1, s.x);
+			V::fma_c(X, c[1], k2, X);
 #if MPGOS_B200_TABLEAU_COMMON_FACTORS
-			for (int i = 0; i < SD; i++) X[i] = fma(c[3], fma(P(-2.0), k3[i], k4[i]), fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])));      // a53 = -2 a54
+			V::fma_c(u, P(-2.0), k3, k4);                 // a53 = -2 a54
+			V::fma_c(X, c[3], u, X);
 #else
-			for (int i = 0; i < SD; i++) X[i] = fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]))));
+			V::fma_c(X, c[2], k3, X);
+			V::fma_c(X, c[3], k4, X);
 #endif
 			Sys::OdeFunction(gid, NTG, k5, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k5[i] *= dt;
+			V::mul_c(k5, dt, k5);
 
 			T = s.t + dt * ck<P>(CK_C6);
 			CkRow<P, CK_A61, 5>::load(c);
-			#pragma unroll
+			V::fma_c(X, c[0], k1, s.x);
+			V::fma_c(X, c[1], k2, X);
 #if MPGOS_B200_TABLEAU_COMMON_FACTORS
-			for (int i = 0; i < SD; i++) X[i] = fma(c[4], k5[i], fma(c[2], fma(P(77.0 / 8.0), k4[i], k3[i]), fma(c[1], k2[i], fma(c[0], k1[i], s.x[i]))));   // a64 = (77/8) a63
+			V::fma_c(u, P(77.0 / 8.0), k4, k3);           // a64 = (77/8) a63
+			V::fma_c(X, c[2], u, X);
 #else
-			for (int i = 0; i < SD; i++) X[i] = fma(c[4], k5[i], fma(c[3], k4[i], fma(c[2], k3[i], fma(c[1], k2[i], fma(c[0], k1[i], s.x[i])))));
+			V::fma_c(X, c[2], k3, X);
+			V::fma_c(X, c[3], k4, X);
 #endif
+			V::fma_c(X, c[4], k5, X);
 			Sys::OdeFunction(gid, NTG, k6, X, T, s.cpar, p_par, p_pari, s.acc, s.acci);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) k6[i] *= dt;
+			V::mul_c(k6, dt, k6);
 
 			CkRow<P, CK_B1, 4>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++) xn[i] = fma(c[3], k6[i], fma(c[2], k4[i], fma(c[1], k3[i], fma(c[0], k1[i], s.x[i]))));
+			V::fma_c(xn, c[0], k1, s.x);
+			V::fma_c(xn, c[1], k3, xn);
+			V::fma_c(xn, c[2], k4, xn);
+			V::fma_c(xn, c[3], k6, xn);
 			CkRow<P, CK_E1, 6>::load(c);
-			#pragma unroll
-			for (int i = 0; i < SD; i++)
-			{
 #if MPGOS_B200_TABLEAU_COMMON_FACTORS
-				const P e = fma(c[4], k6[i], fma(c[2], k4[i], fma(c[1], k3[i], c[0] * fma(P(4.5), k5[i], k1[i]))));       // e5 = 4.5 e1
+			V::fma_c(u, P(4.5), k5, k1);                  // e5 = 4.5 e1
+			V::mul_c(u, c[0], u);
 #else
-				const P e = fma(c[4], k6[i], fma(c[3], k5[i], fma(c[2], k4[i], fma(c[1], k3[i], c[0] * k1[i]))));
+			V::mul_c(u, c[0], k1);
+			V::fma_c(u, c[3], k5, u);
 #endif
-				err[i] = fabs(e) + c[5];
-			}
+			V::fma_c(u, c[1], k3, u);
+			V::fma_c(u, c[2], k4, u);
+			V::fma_c(u, c[4], k6, u);
+			#pragma unroll
+			for (int i = 0; i < SD; i++) err[i] = fabs(u[i]) + c[5];
 #else
 			// expression shapes as in the reference
 			Sys::OdeFunction(gid, NTG, k1, s.x, s.t, s.cpar, p_par, p_pari, s.acc, s.acci);
