@@ -402,6 +402,13 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(f"{args.workload}_{args.precision}")
+        # solver kernels of the timed region, plus the three ordering kernels in front of every phase that has a cost history
+        # (second and later phases of a step; per-thread module: only launches of more than 16 blocks per SM, coupled module: queues
+        # longer than two rounds of slots)
+        tpb = (args.threads_per_block or getattr(wl.options, "ThreadsPerBlock", None) or 128) if kind == "perthread" else 1
+        tiles = (N + tpb - 1) // tpb
+        ordered = (tiles > 16 * 148) if kind == "perthread" else (N > 2 * 148 * 8)
+        ordering_kernels = 3 * (args.phases - 1) if (ordered and args.lane_refill <= 0) else 0
         out = {"metric": metric, "value": value, "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": region_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": args.precision, "data": "synthetic", "config": config,
@@ -413,7 +420,7 @@ def main():
                             "kernel_ms": kmean, "algorithmic_flops_per_launch": per_rank_attempted_per_launch * flops_per_step},
                "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_s / args.steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
-               "gpu_launches": args.steps * args.phases, "clocks": clocks}
+               "gpu_launches": args.steps * (args.phases + ordering_kernels), "clocks": clocks}
         if dense_samples is not None:
             # the only HBM stream that matters on this path: (SD + 1) words per stored point (24 B for Keller-Miksis)
             bytes_per_sample = (wl.shape.SD + 1) * precision_bytes
