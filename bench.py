@@ -16,8 +16,9 @@ coupled module: of one whole system of 64 units).
 
 Timed regions (all after W >= 3 warm-up steps):
   value : inputs resident in HBM; each step restores the initial condition device-to-device and
-          launches the phase(s); CUDA events on the solver's stream, barrier + synchronize on both
-          sides, max over ranks.
+          launches the phase(s); L2 is flushed before every step (256 MiB overwritten on the same
+          stream); the step time is the sum of the CUDA-event brackets around (restore + phases) on
+          the solver's stream, barrier + synchronize on both sides of the K steps, max over ranks.
   e2e   : the same K steps through the public API with HOST buffers: every step uploads the inputs
           from pinned host memory, integrates, and downloads state + time.  The sweep is driven as
           ``--e2e-chunks`` solver objects with their own streams so that copies overlap kernels --
@@ -260,7 +261,7 @@ def main():
     config = {"workload": f"{args.workload}: {N} {unit} per GPU x {world} GPU(s), {args.phases} integration phase(s) per step (BASELINE {cfg_name})",
               f"{unit}_per_gpu": N, "phases_per_step": args.phases,
               "sharding": "tile-cyclic, no collective on the data path",
-              "l2": "state is restored device-to-device from a snapshot before every step; the kernel is bound by instruction issue (an FP64 instruction takes two issue slots), its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
+              "l2": "flushed between timed iterations (a 256 MiB buffer is overwritten on the solver's stream, outside the summed event brackets); state is restored device-to-device from a snapshot before every step; the kernel is bound by instruction issue (an FP64 instruction takes two issue slots), its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
               "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
 
     # ------------------------------------------------------------------ reference arm (CPU) ------
@@ -315,12 +316,19 @@ def main():
 
     # ---- value: device-resident ---------------------------------------------------------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # L2 (126 MB) is flushed between timed iterations by overwriting a 256 MiB buffer on the solver's stream; the flush itself is
+    # outside the event brackets that are summed into the step time
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     sampler = ClockSampler(local_rank)
     time.sleep(0.25)
     barrier(); torch.cuda.synchronize()
     t_host0 = time.time()
     ev[0].record(stream)
     for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(k & 0xff)
+        ev_step[k].record(stream)
         ps.RestoreState()
         ev[2 + 2 * k].record(stream)
         for _ in range(args.phases):
@@ -330,7 +338,7 @@ def main():
     torch.cuda.synchronize(); barrier()
     t_host1 = time.time()
     clocks = sampler.stop(t_host0, t_host1)
-    region_ms = ev[0].elapsed_time(ev[1])
+    region_ms = sum(ev_step[k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps))      # K x (restore + phases), flushes excluded
     kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) / args.phases for k in range(args.steps)]
     attempted, accepted = arm.total_steps()
     dense_samples = None
