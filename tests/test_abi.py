@@ -149,3 +149,36 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert line["e2e"] == {"value": line["value"], "unit": "system-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
         assert "workload" in line["config"] and line["higher_is_better"] is True
+
+
+def test_single_precision_workloads(workloads, pkg):
+    """workloads.single_precision / the coupled generators' dtype argument: same sweep, float32 buffers, tolerances a float resolves."""
+    wl = workloads.impact_t6(NT=256)
+    w32 = workloads.single_precision(wl)
+    assert w32.shape.dtype == np.float32 and w32.buffers.ActualState.dtype == np.float32 and w32.buffers.IntegerAccessories.dtype == np.int32
+    assert np.array_equal(w32.buffers.ControlParameters, wl.buffers.ControlParameters.astype(np.float32))
+    o = w32.options.resolved(w32.shape, w32.NT)
+    assert o.RelativeTolerance.dtype == np.float32 and (o.RelativeTolerance == np.float32(1e-5)).all() and (o.EventTolerance == np.float32(1e-4)).all()
+    assert o.MinimumTimeStep >= 1e-6 and wl.shape.dtype == np.float64                 # the original is untouched
+    WC = pkg.workloads_coupled
+    c32 = WC.bubble_ensemble(NS=3, UPS=16, dtype=np.float32)
+    c64 = WC.bubble_ensemble(NS=3, UPS=16)
+    assert c32.buffers.UnitParameters.dtype == np.float32 and c32.buffers.CouplingMatrix.dtype == np.float32
+    assert np.array_equal(c32.buffers.UnitParameters, c64.buffers.UnitParameters.astype(np.float32))
+    assert (c32.options.RelativeTolerance == 1e-5).all() and (c64.options.RelativeTolerance == np.array([1e-10, 1e-8])).all()
+
+
+def test_option_enums_match_the_headers(pkg):
+    """The Python mirrors' option numbers are the C enums' (both modules), including the options added by this implementation."""
+    def enum(header, name):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        body = re.search(r"typedef enum " + name + r"\s*\{(.*?)\}", text, flags=re.S).group(1)
+        return [t.split("=")[0].strip() for t in body.split(",") if t.strip()]
+    per = enum("mpgos_b200.h", "mpgos_option")
+    for i, n in enumerate(per):
+        assert int(getattr(pkg.Options, n.replace("MPGOS_OPT_", ""))) == i, n
+    cpl = enum("mpgos_b200_coupled.h", "mpgos_coupled_option")
+    for i, n in enumerate(cpl):
+        assert int(getattr(pkg.CoupledOptions, n.replace("MPGOS_COPT_", ""))) == i, n
+    assert per[-1] == "MPGOS_OPT_DispatchOrder" and cpl[-1] == "MPGOS_COPT_DispatchOrder"
