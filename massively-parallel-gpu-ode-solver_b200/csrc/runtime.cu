@@ -379,7 +379,8 @@ static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device
 	else if (variable == MPGOS_VAR_DenseOutput) { list[n++] = MPGOS_VAR_DenseIndex;  list[n++] = MPGOS_VAR_DenseTime;  list[n++] = MPGOS_VAR_DenseState; }
 	else if (is_buffer_variable(variable)) list[n++] = variable;
 	else return fail(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
-	if (to_device) s->history_valid = false;      // new instances or parameters: the cost history no longer describes them
+	// new instances or parameters: the cost history no longer describes them (a new time domain alone leaves the instances what they were)
+	if (to_device && variable != MPGOS_VAR_TimeDomain && variable != MPGOS_VAR_DenseOutput && variable != MPGOS_VAR_DenseIndex) s->history_valid = false;
 	for (int i = 0; i < n; i++)
 	{
 		Mirror& m = s->var[list[i]];
