@@ -242,7 +242,8 @@ static int ccopy(mpgos_coupled_solver* s, int variable, bool to_device)
 	else if (variable == MPGOS_CVAR_DenseOutput) { list[n++] = MPGOS_CVAR_DenseIndex; list[n++] = MPGOS_CVAR_DenseTime; list[n++] = MPGOS_CVAR_DenseState; }
 	else if (is_cbuffer(variable)) list[n++] = variable;
 	else return CFAIL(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
-	if (to_device) s->history_valid = false;      // new systems or parameters: the cost history no longer describes them
+	// new systems or parameters: the cost history no longer describes them (a new time domain alone leaves the systems what they were)
+	if (to_device && variable != MPGOS_CVAR_TimeDomain && variable != MPGOS_CVAR_DenseOutput && variable != MPGOS_CVAR_DenseIndex) s->history_valid = false;
 	for (int i = 0; i < n; i++)
 	{
 		CMirror& m = s->var[list[i]];
