@@ -51,6 +51,12 @@ struct PerBlockArgs
 	int* DenseOutputIndex;  P* DenseOutputTimeInstances;  P* DenseOutputStates;
 	unsigned long long* StepsAttempted;  unsigned long long* StepsAccepted;  unsigned int* WorkQueue;
 	unsigned int* LastPhaseSteps;  const int* DispatchOrder;      // cost history and queue order (perthread_kernel.cuh, dispatch_cost_histogram)
+	// time slices inside one phase (first phase of a sweep: no cost history yet).  SliceMode 1: the pilot -- every system is paused on
+	// its first accepted step at or past t0 + SliceFraction (TD1 - t0), nothing is clipped, so the step sequence is the one of the
+	// unsliced phase; its controller state goes to the Slice* arrays.  SliceMode 2: the continuation, in the order the pilot's step
+	// counts give; systems that ended inside the pilot are skipped.  0: the whole phase in one launch.
+	int SliceMode;  P SliceFraction;
+	P* SliceDt;  P* SliceLastDt;  P* SliceDenseNext;  int* SliceSkipped;  int* SlicePaused;
 	int NS, Active, SystemOffset, DenseCapacity, DenseOutputSaveFrequency, DeviceMessages;
 	P   InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep, MinimumTimeStepGuard;
 	P   RelativeTolerance[UD];  P AbsoluteTolerance[UD];
@@ -91,6 +97,7 @@ struct SlotShared
 	P   t, dt, td[2];
 	P   spar[AtLeastOne<NSP>::value], sacc[AtLeastOne<NSA>::value], strength[AtLeastOne<NC>::value];
 	P   dense_next_time;
+	P   slice_time;          // SliceMode 1: pause at the first accepted step at or past this time
 	P   red_ratio[WPS];      // per-warp max of err/tol
 	P   red_evdt[WPS];       // per-warp min of the secant event step
 	int red_flags[WPS];      // bit 0: all accepted, bit 1: all finite
@@ -344,7 +351,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	int    pos = blockIdx.x * SPBK + slot;      // position in the system queue
 	int    sys = 0, gsys = 0;
 	size_t ug = 0;
-	bool   have = false, dry = false, first = true;
+	bool   have = false, dry = false, first = true, resumed = false;
 	int    buf = 0;
 
 	// One trip of this loop = one attempted step of the slot's system.  Scalar variant: slots are independent.  MMA variant:
@@ -366,14 +373,19 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			else
 			{
 				sys = a.DispatchOrder ? a.DispatchOrder[pos] : pos;      // with a cost history: the longest systems first
+				resumed = (a.SliceMode == 2);
+			}
+			if (!dry && !(resumed && a.SlicePaused[sys] == 0))      // continuation: a system that ended inside the pilot is skipped
+			{
 				gsys = sys + a.SystemOffset;
 				ug   = (size_t)sys * UPS + (is_unit ? unit : 0);
 				// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
 				if (unit == 0)
 				{
 					S.td[0] = a.TimeDomain[sys];  S.td[1] = a.TimeDomain[sys + a.NS];
-					S.t = a.ActualTime[sys];  S.dt = a.InitialTimeStep;
-					S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.dense_skipped = 0;  S.udt = 0;  S.dense_next_time = P(0);
+					S.t = a.ActualTime[sys];  S.dt = resumed ? a.SliceLastDt[sys] : a.InitialTimeStep;
+					S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.udt = 0;
+					S.dense_skipped = resumed ? a.SliceSkipped[sys] : 0;  S.dense_next_time = resumed ? a.SliceDenseNext[sys] : P(0);
 				}
 				if (unit < NSP)  S.spar[unit]     = a.SystemParameters[sys + unit * a.NS];
 				if (unit < NSA)  S.sacc[unit]     = a.SystemAccessories[sys + unit * a.NS];
@@ -389,14 +401,19 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				for (int i = 0; i < NiUA; i++) iuacc[i] = a.IntegerUnitAccessories[ug + i * NU];
 				slot_barrier<UPSP>(slot);
 
-				if (is_unit) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+				if (is_unit && !resumed) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
 				slot_barrier<UPSP>(slot);
+				if (a.SliceMode == 1)
+				{
+					if (unit == 0) S.slice_time = S.t + a.SliceFraction * (S.td[1] - S.t);
+					slot_barrier<UPSP>(slot);
+				}
 				if (NE > 0)
 				{
 					if (is_unit) Sys::EventFunction(gsys, unit, ev, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
 					slot_barrier<UPSP>(slot);
 				}
-				if (DENSE)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
+				if (DENSE && !resumed)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
 				{
 					const int di = S.dense_index;
 					if (di < a.DenseCapacity)
@@ -412,13 +429,15 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 					if (unit == 0) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
 					slot_barrier<UPSP>(slot);
 				}
-				dt_new = a.InitialTimeStep;
+				dt_new = resumed ? a.SliceDt[sys] : a.InitialTimeStep;
 				attempted = 0;  accepted = 0;
 				have = true;
 			}
+			else if (!dry) slot_barrier<UPSP>(slot);      // skipped: everybody has read the queue position before unit 0 asks for the next one
 		}
-		if (MMA) { if (!__syncthreads_or(have ? 1 : 0)) break; }
-		else if (!have) break;
+		// leave when no slot has a system and none can get one any more (a slot that skipped a system takes another next trip)
+		if (MMA) { if (!__syncthreads_or((have || !dry) ? 1 : 0)) break; }
+		else if (!have) { if (dry) break; else continue; }
 		const bool live = have && is_unit;
 
 		// right-hand side of this unit including the coupling term
@@ -735,12 +754,13 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		}
 
 		if (update && (end_reached || user_stop)) terminated = true;
+		const bool paused = (a.SliceMode == 1) && have && update && !terminated && (S.t >= S.slice_time);
 
-		// ---- end of the phase for this system (Solver.cuh:2812-2887) -------------------------------------------
-		if (terminated)
+		// ---- end of the phase for this system (Solver.cuh:2812-2887), or of its pilot slice ------------------------
+		if (terminated || paused)
 		{
 			slot_barrier<UPSP>(slot);
-			if (live) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+			if (live && !paused) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
 			slot_barrier<UPSP>(slot);
 			if (live)
 			{
@@ -760,7 +780,9 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				if (DENSE) a.DenseOutputIndex[sys] = S.dense_index;
 				a.StepsAttempted[sys] += attempted;
 				a.StepsAccepted[sys]  += accepted;
-				a.LastPhaseSteps[sys] = attempted;
+				a.LastPhaseSteps[sys] = attempted + (resumed ? a.LastPhaseSteps[sys] : 0u);
+				if (a.SliceMode == 1) a.SlicePaused[sys] = paused ? 1 : 0;
+				if (paused) { a.SliceDt[sys] = dt_new;  a.SliceLastDt[sys] = S.dt;  a.SliceDenseNext[sys] = S.dense_next_time;  a.SliceSkipped[sys] = S.dense_skipped; }
 			}
 			slot_barrier<UPSP>(slot);
 			have = false;
@@ -807,17 +829,41 @@ struct PerBlockLauncher
 		// queue order: with the previous phase's step counts at hand and more systems than two rounds of slots, the longest first
 		// (C5, whose expensive systems sit at the end of the amplitude sweep: 18.0 instead of 19.4 ms)
 		PerBlockArgs<P, UD, NE> args = a;
-		args.DispatchOrder = nullptr;
-		if (L->DispatchHistory && L->d_DispatchOrder && L->d_DispatchScratch && a.Active > 2 * grid * SLOTS)
+		args.DispatchOrder = nullptr;  args.SliceMode = 0;
+		const bool many = (a.Active > 2 * grid * SLOTS) || L->DispatchHistory >= 2 || L->DispatchPilot >= 2;      // >= 2: forced (tests)
+		const bool can_order = L->d_DispatchOrder && L->d_DispatchScratch && many;
+		auto order_by_cost = [&]() -> cudaError_t
 		{
 			unsigned int* bucket_of = L->d_DispatchScratch;
 			unsigned int* hist = L->d_DispatchScratch + L->desc.NS;
-			e = cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), stream);
-			if (e != cudaSuccess) return (int)e;
+			cudaError_t err = cudaMemsetAsync(hist, 0, 256 * sizeof(unsigned int), stream);
+			if (err != cudaSuccess) return err;
 			dispatch_cost_histogram<<<(a.Active + 7) / 8, 256, 0, stream>>>(L->d_LastPhaseSteps, a.Active, 1, a.Active, bucket_of, hist);
 			dispatch_bucket_starts<<<1, 256, 0, stream>>>(hist);
 			dispatch_scatter<<<(a.Active + 255) / 256, 256, 0, stream>>>(bucket_of, hist, a.Active, L->d_DispatchOrder);
+			return cudaGetLastError();
+		};
+		if (L->DispatchHistory && can_order)
+		{
+			e = order_by_cost();
+			if (e != cudaSuccess) return (int)e;
 			args.DispatchOrder = L->d_DispatchOrder;
+		}
+		else if (L->DispatchPilot && can_order && L->d_SliceState)
+		{
+			// no history yet: the first tenth of the phase in index order tells what each system costs (for sweeps whose cost is set by a
+			// parameter -- C5's pressure amplitude), the rest follows in that order.  Emulated with two phases before it was built:
+			// 18.3 instead of 19.4 ms on C5 (tools/probe_time_slices_coupled.py).
+			P* base = (P*)L->d_SliceState;
+			args.SliceDt = base;  args.SliceLastDt = base + L->desc.NS;  args.SliceDenseNext = base + 2 * (size_t)L->desc.NS;
+			args.SliceSkipped = (int*)(base + 3 * (size_t)L->desc.NS);  args.SlicePaused = args.SliceSkipped + L->desc.NS;
+			args.SliceMode = 1;  args.SliceFraction = P(0.1);
+			kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
+			e = cudaGetLastError();
+			if (e == cudaSuccess) e = order_by_cost();
+			if (e == cudaSuccess) e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
+			if (e != cudaSuccess) return (int)e;
+			args.SliceMode = 2;  args.DispatchOrder = L->d_DispatchOrder;
 		}
 		kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
 		return (int)cudaGetLastError();
@@ -838,6 +884,7 @@ struct PerBlockLauncher
 		a.CouplingIndex = L->d_CouplingIndex;  a.DenseOutputIndex = L->d_DenseOutputIndex;  a.DenseOutputTimeInstances = (P*)L->d_DenseOutputTimeInstances;
 		a.DenseOutputStates = (P*)L->d_DenseOutputStates;  a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
 		a.LastPhaseSteps = L->d_LastPhaseSteps;  a.DispatchOrder = nullptr;
+		a.SliceMode = 0;  a.SliceFraction = P(0);  a.SliceDt = a.SliceLastDt = a.SliceDenseNext = nullptr;  a.SliceSkipped = a.SlicePaused = nullptr;
 		a.NS = d.NS;  a.Active = L->ActiveSystems < d.NS ? L->ActiveSystems : d.NS;  a.SystemOffset = d.SystemOffset;  a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;  a.DeviceMessages = L->DeviceMessages;
 		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;  a.MinimumTimeStep = (P)L->MinimumTimeStep;

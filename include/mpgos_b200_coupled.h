@@ -46,8 +46,10 @@ typedef enum mpgos_coupled_option
 	MPGOS_COPT_SharedGlobalVariables, MPGOS_COPT_SharedCouplingMatrices,
 	MPGOS_COPT_DeviceMessages,
 	MPGOS_COPT_TensorCoreCoupling,  /* 1 (default): dense shared coupling matrices go through tensor-core MMA where the shape allows; 0: scalar sums */
-	MPGOS_COPT_DispatchOrder        /* 1 (default): from the second phase on the system queue hands out the systems in order of decreasing cost in the
-	                                   previous phase (longest first); 0: in index order */
+	MPGOS_COPT_DispatchOrder        /* 1 (default): the system queue hands out the systems in order of decreasing cost (longest first): from the previous
+	                                   phase's step counts, or, in the first phase of a sweep, from a pilot slice (the first tenth of the phase, after which
+	                                   every system is paused on an accepted step and continued); only for queues longer than two rounds of slots;
+	                                   2: the same for any queue length (tests); 0: in index order, one launch per phase */
 } mpgos_coupled_option;
 
 /* Template arguments of the reference's coupled ProblemSolver (CP/Interface.cuh:135-136) as run-time data.  TPB and SPB
@@ -74,7 +76,9 @@ typedef struct mpgos_coupled_launch
 	unsigned int*       d_LastPhaseSteps;   /* [NS] stepper invocations of the phase just integrated */
 	int*                d_DispatchOrder;    /* [NS] scratch: system ids in queue order */
 	unsigned int*       d_DispatchScratch;  /* [NS + 768] scratch of the ordering kernels */
-	int                 DispatchHistory;    /* 1: d_LastPhaseSteps describes the previous phase of these systems and cost order is wanted */
+	int                 DispatchHistory;    /* 1: d_LastPhaseSteps describes the previous phase of these systems and cost order is wanted (2: also for short queues) */
+	void*               d_SliceState;       /* [NS x 40 bytes] controller state of systems paused at the end of a pilot slice */
+	int                 DispatchPilot;      /* 1: no history: integrate a pilot slice first and order the rest by its step counts (2: also for short queues) */
 	size_t CouplingMatrixElements;
 	const double* RelativeTolerance;  const double* AbsoluteTolerance;  const double* EventTolerance;  const int* EventDirection;   /* host */
 	double InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep;

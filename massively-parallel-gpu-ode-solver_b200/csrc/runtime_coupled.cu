@@ -39,6 +39,7 @@ struct mpgos_coupled_solver
 	unsigned int* d_last_steps = nullptr;      // [NS] steps of the previous phase (cost history of the queue order)
 	int*          d_order = nullptr;           // [NS]
 	unsigned int* d_order_scratch = nullptr;   // [NS + 768]
+	void*         d_slice = nullptr;           // [NS x 40 bytes] pilot-slice state
 	bool          history_valid = false;
 	int           DispatchOrder = 1;
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12, TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1;
@@ -123,6 +124,8 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_order, 4 * NS);
 	if (e == cudaSuccess) e = cudaMalloc(&s->d_order_scratch, 4 * (NS + 768));
 	if (e == cudaSuccess) e = cudaMemset(s->d_last_steps, 0, 4 * NS);
+	if (e == cudaSuccess) e = cudaMalloc(&s->d_slice, 40 * NS);
+	if (e == cudaSuccess) e = cudaMemset(s->d_slice, 0, 40 * NS);
 	if (e == cudaSuccess) e = cudaMemset(s->d_attempted, 0, 8 * NS);
 	if (e == cudaSuccess) e = cudaMemset(s->d_accepted, 0, 8 * NS);
 	if (e != cudaSuccess) { mpgos_coupled_destroy(s); return CFAIL(MPGOS_ERR_CUDA, "coupled solver construction failed -> %s", cudaGetErrorString(e)); }
@@ -142,6 +145,7 @@ int mpgos_coupled_destroy(mpgos_coupled_solver* s)
 	if (s->d_last_steps) cudaFree(s->d_last_steps);
 	if (s->d_order) cudaFree(s->d_order);
 	if (s->d_order_scratch) cudaFree(s->d_order_scratch);
+	if (s->d_slice) cudaFree(s->d_slice);
 	if (s->t0) cudaEventDestroy(s->t0);
 	if (s->t1) cudaEventDestroy(s->t1);
 	if (s->event) cudaEventDestroy(s->event);
@@ -212,7 +216,7 @@ int mpgos_coupled_set_option(mpgos_coupled_solver* s, int option, double value)
 		case MPGOS_COPT_SharedCouplingMatrices:     s->SharedCouplingMatrices = (int)value; break;    // accepted, ignored: always shared
 		case MPGOS_COPT_DeviceMessages:             s->DeviceMessages = (int)value != 0; break;
 		case MPGOS_COPT_TensorCoreCoupling:         s->TensorCoreCoupling = (int)value != 0; break;
-		case MPGOS_COPT_DispatchOrder:              s->DispatchOrder = (int)value != 0; break;
+		case MPGOS_COPT_DispatchOrder:              s->DispatchOrder = (int)value < 0 ? 0 : ((int)value > 2 ? 2 : (int)value); break;
 		default: return CFAIL(MPGOS_ERR_ARGUMENT, "SolverOption: option %d needs 2 input arguments or is not applicable", option);
 	}
 	return MPGOS_OK;
@@ -292,7 +296,7 @@ static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 	L.d_DenseOutputTimeInstances = s->var[MPGOS_CVAR_DenseTime].dev;  L.d_DenseOutputStates = s->var[MPGOS_CVAR_DenseState].dev;
 	L.d_StepsAttempted = s->d_attempted;  L.d_StepsAccepted = s->d_accepted;  L.d_WorkQueue = s->d_queue;
 	L.d_LastPhaseSteps = s->d_last_steps;  L.d_DispatchOrder = s->d_order;  L.d_DispatchScratch = s->d_order_scratch;
-	L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
+	L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? s->DispatchOrder : 0;  L.DispatchPilot = (s->DispatchOrder && !s->history_valid) ? s->DispatchOrder : 0;  L.d_SliceState = s->d_slice;
 	L.CouplingMatrixElements = s->var[MPGOS_CVAR_CouplingMatrix].elements;
 	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();  L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
 	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
@@ -322,7 +326,7 @@ int mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher la
 	CUDA_TRY(cudaEventRecord(s->t0, s->stream));
 	for (int p = 0; p < phases; p++)
 	{
-		L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? 1 : 0;
+		L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? s->DispatchOrder : 0;  L.DispatchPilot = (s->DispatchOrder && !s->history_valid) ? s->DispatchOrder : 0;  L.d_SliceState = s->d_slice;
 		const int e = launcher(&L, (void*)s->stream);
 		if (e != 0) return CFAIL(MPGOS_ERR_CUDA, "Solve: kernel launch failed -> %s", cudaGetErrorString((cudaError_t)e));
 		s->history_valid = true;

@@ -287,7 +287,8 @@ def read_back_coupled(ps: CoupledProblemSolver, wl):
     return out
 
 
-def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device: int = 0, tensor_core_coupling: Optional[int] = None):
+def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device: int = 0, tensor_core_coupling: Optional[int] = None,
+                         dispatch_order: Optional[int] = None):
     """Integrate a coupled workload on the GPU through the public API; returns (buffers_after, attempted, accepted)."""
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
@@ -296,6 +297,8 @@ def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device:
         apply_coupled_workload(ps, wl, b)
         if tensor_core_coupling is not None:
             ps.SolverOption(CoupledOptions.TensorCoreCoupling, tensor_core_coupling)
+        if dispatch_order is not None:
+            ps.SolverOption(CoupledOptions.DispatchOrder, dispatch_order)
         ps.SynchroniseFromHostToDevice(CoupledVariables.All)
         for _ in range(wl.phases if phases is None else phases):
             ps.Solve()

@@ -254,25 +254,34 @@ def test_upload_download_with_caller_owned_arrays(pkg):
             ps.Upload(V.CouplingMatrix, state.ctypes.data, 64 * 64 * 8)
 
 
-def test_cost_ordered_queue_changes_nothing_but_the_order(pkg):
-    """DispatchOrder = 1 (default): from the second phase on the system queue hands out the systems longest first (previous
-    phase's step counts).  Systems are independent: results are bit-identical to index order.  2000 systems, so that the
-    queue is longer than two rounds of slots and the order is actually computed."""
+ALL_COUPLED_CASES = ["bubble_u8_rkck45", "bubble_u16_rkck45", "bubble_u16_rk4", "ring_b1c1_rkck45", "ring_b1c0_rkck45", "ring_b0c1_rk4",
+                     "ring_b0c0_rkck45", "ring_b1c1_rkck45_f32"]
+
+
+@pytest.mark.parametrize("name", ALL_COUPLED_CASES)
+def test_cost_ordered_queue_and_pilot_slice_change_nothing_but_the_order(name, ccases, pkg):
+    """DispatchOrder: the system queue hands out the systems longest first -- in the first phase of a sweep after a pilot slice (the
+    first tenth of the phase in index order, every system PAUSED on an accepted step, its controller state kept, then continued
+    in cost order), in later phases from the previous phase's step counts.  Nothing is clipped and systems are independent, so
+    every result -- end states, event counters, accessories kept by unit 0, every dense output point, step counts -- is
+    bit-identical to index order in one launch.  DispatchOrder = 2 forces the mechanism on these short queues (1 applies it to
+    queues longer than two rounds of slots); three phases: pilot + continuation, then two history-ordered phases."""
+    tag, wl, phases = ccases[name]
+    a, aatt, aacc = pkg.run_coupled_workload(wl, phases=3, dispatch_order=0)
+    b, batt, bacc = pkg.run_coupled_workload(wl, phases=3, dispatch_order=2)
+    for f in COUPLED_RESULT_FIELDS:
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), (name, f)
+    assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc) and (aatt > 0).all()
+
+
+def test_cost_ordered_queue_on_a_long_queue_and_the_tensor_core_path(pkg):
+    """The same on a queue long enough for DispatchOrder = 1 (default) to act by itself, through the tensor-core variant (blocks of 8
+    systems in lockstep, slots skipping and idling while the queue drains)."""
     WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
-    wl = WC.bubble_ensemble(NS=2600, UPS=16, amplitude=(0.1, 2.0))
-    wl.buffers.TimeDomain[1][:] = 0.2
-    runs = []
-    for order in (0, 1):
-        with pkg.CoupledProblemSolver(wl.name, wl.buffers.NS, 16) as ps:
-            pkg.apply_coupled_workload(ps, wl)
-            ps.SolverOption(pkg.CoupledOptions.DispatchOrder, order)
-            ps.SynchroniseFromHostToDevice(pkg.CoupledVariables.All)
-            for _ in range(3):
-                ps.Solve()
-            out = pkg.read_back_coupled(ps, wl)
-            att, acc = ps.StepCounters()
-            runs.append((out, att, acc))
-    (a, aatt, aacc), (b, batt, bacc) = runs
+    wl = WC.bubble_ensemble(NS=3000, UPS=32, amplitude=(0.1, 2.0))
+    wl.buffers.TimeDomain[1][:] = 0.1
+    a, aatt, aacc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=0)
+    b, batt, bacc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=1)
     for f in COUPLED_RESULT_FIELDS:
         assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
     assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc) and (aatt > 0).all()
