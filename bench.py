@@ -412,11 +412,14 @@ def main():
             traffic = json.load(open(tpath)).get(f"{args.workload}_{args.precision}")
         # solver kernels of the timed region, plus the three ordering kernels in front of every phase that has a cost history
         # (second and later phases of a step; per-thread module: only launches of more than 16 blocks per SM, coupled module: queues
-        # longer than two rounds of slots)
+        # longer than two rounds of slots, and there the first phase too: pilot slice + ordered continuation)
         tpb = (args.threads_per_block or getattr(wl.options, "ThreadsPerBlock", None) or 128) if kind == "perthread" else 1
         tiles = (N + tpb - 1) // tpb
         ordered = (tiles > 16 * 148) if kind == "perthread" else (N > 2 * 148 * 8)
-        ordering_kernels = 3 * (args.phases - 1) if (ordered and args.lane_refill <= 0) else 0
+        if kind == "coupled":      # every phase is cost-ordered (3 kernels); the first one of a step after a pilot slice (one more solver launch)
+            ordering_kernels = (3 * args.phases + 1) if ordered else 0
+        else:
+            ordering_kernels = 3 * (args.phases - 1) if (ordered and args.lane_refill <= 0) else 0
         out = {"metric": metric, "value": value, "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": region_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": args.precision, "data": "synthetic", "config": config,
