@@ -23,7 +23,12 @@ elif which == "dispatch":
     wl = pkg.workloads.impact_t6(NT=1 << 18)
     out, att, acc = pkg.run_workload(wl, phases=2); print("impact dispatch order", int(att.sum()))
     wl = WC.bubble_ensemble(NS=2600, UPS=16, amplitude=(0.1, 2.0)); wl.buffers.TimeDomain[1][:] = 0.02
-    out, att, acc = pkg.run_coupled_workload(wl, phases=2); print("bubble queue order", int(att.sum()))
+    out, att, acc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=2); print("bubble pilot slice + queue order", int(att.sum()))
+    cc = make_coupled_cases(WC)
+    for name in ("ring_b1c1_rkck45", "ring_b0c0_rkck45"):      # multi-warp slots, events, dense output: pause / skip / resume paths
+        tag, wl, phases = cc[name]; out, att, acc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=2); print(name, "pilot slice", int(att.sum()))
+    wl = WC.bubble_ensemble(NS=21, UPS=64, amplitude=(0.2, 1.2)); wl.buffers.TimeDomain[1][:] = 0.05
+    out, att, acc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=2); print("bubble 64 tensor-core pilot slice", int(att.sum()))
 else:
     c = make_cases(pkg.workloads)
     for name in ("lorenz_rkck45_f64", "duffing_rkck45_f64", "impact_rkck45_f64", "kellermiksis_dense_rkck45_f64", "lorenz_rkck45_f32"):
