@@ -54,3 +54,23 @@ def test_reduction_over_two_ranks_gloo(pkg):
     for rank, maxima, sums in results:
         assert maxima == [11.0, 1.0]                        # MAX over ranks
         assert abs(sums[0] - total_rho) < 1e-6 and sums[1] == 2.0   # SUM over ranks; shards cover the sweep
+
+
+def test_coupled_systems_shard_like_instances(pkg):
+    """bench.py --workload coupled --gpus N: systems are dealt to the ranks in tiles of 64; unit-scope arrays keep their
+    [serial, system, unit] shape, the coupling matrix and the coupling index (shared by all systems) are replicated."""
+    sharding = importlib.import_module(PACKAGE + ".sharding")
+    WC = pkg.workloads_coupled
+    world, per_rank, tile = 2, 128, 64
+    full = WC.bubble_ensemble(NS=world * per_rank, UPS=16)
+    parts = [full.buffers.take(sharding.shard_indices(per_rank, r, world, tile)) for r in range(world)]
+    for r, b in enumerate(parts):
+        assert b.NS == per_rank and b.UnitParameters.shape == (21, per_rank, 16) and b.ActualState.shape == (2, per_rank, 16)
+        assert np.array_equal(b.CouplingMatrix, full.buffers.CouplingMatrix) and np.array_equal(b.CouplingIndex, full.buffers.CouplingIndex)
+        ids = sharding.shard_indices(per_rank, r, world, tile)
+        assert np.array_equal(b.UnitParameters[5], full.buffers.UnitParameters[5][ids])          # the swept pressure amplitude
+        assert np.array_equal(b.CouplingStrength, full.buffers.CouplingStrength[:, ids])
+    amplitude = np.concatenate([b.UnitParameters[5][:, 0] for b in parts])
+    assert np.array_equal(np.sort(amplitude), np.sort(full.buffers.UnitParameters[5][:, 0]))
+    # both ranks see both ends of the sweep
+    assert all(b.UnitParameters[5][:, 0].max() > 0.7 * full.buffers.UnitParameters[5][:, 0].max() for b in parts)
