@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- "parity pinned": this restatement is checked bit for bit against
 // oracle/_ref (the reference's own kernel source compiled for the host with the same compiler
-// flags) by tests/test_oracle_vs_reference.py, and against the fixtures under tests/golden/
+// flags) by tests/test_oracle_golden.py (tutorial options) and tests/test_oracle_option_fuzz.py (random solver options), and against the fixtures under tests/golden/
 // that were generated from oracle/_ref (tests/golden/make_golden.py).
 //
 // CPU restatement of the reference's thread-per-system integration phase.  One call of

@@ -2,6 +2,8 @@
 
 Each case is a sub-sweep of a BASELINE configuration (same generators, same options, fewer
 instances / phases) that the CPU checker finishes in about a second."""
+import copy
+
 import numpy as np
 
 
@@ -28,6 +30,33 @@ def make_cases(W):
     c["kellermiksis_rkck45_f64"] = (subsample(W.keller_miksis_t5(NT=4096, ndo=0), 64), 2)
     c["kellermiksis_dense_rkck45_f64"] = (subsample(W.keller_miksis_t5(NT=4096, ndo=200), 64), 2)
     return c
+
+
+def random_options(rng, wl, trial):
+    """A copy of the workload's options with every run-time knob redrawn; extreme draws are deliberate."""
+    sh = wl.shape
+    o = copy.copy(wl.options)
+    o.InitialTimeStep = float(10.0 ** rng.uniform(-5, -1))
+    o.MaximumTimeStep = float(10.0 ** rng.uniform(-2, 3))
+    # one trial in three pushes the lower limit up into the working range: steps are then accepted by force
+    o.MinimumTimeStep = float(10.0 ** (rng.uniform(-5, -3) if trial % 3 == 0 else rng.uniform(-14, -8)))
+    o.TimeStepGrowLimit = float(rng.uniform(1.2, 10.0))
+    o.TimeStepShrinkLimit = float(rng.uniform(0.05, 0.7))
+    o.RelativeTolerance = 10.0 ** rng.uniform(-11, -4, sh.SD)
+    o.AbsoluteTolerance = 10.0 ** rng.uniform(-11, -4, sh.SD)
+    if sh.NE:
+        o.EventTolerance = 10.0 ** rng.uniform(-8, -3, sh.NE)
+        if wl.name != "impact":       # the impact law needs its falling-edge detection to keep the valve above the seat
+            o.EventDirection = rng.integers(-1, 2, sh.NE).astype(np.int32)
+    if sh.NDO:
+        o.DenseOutputSaveFrequency = int(rng.integers(1, 6))
+        o.DenseOutputMinimumTimeStep = float(rng.choice([0.0, 10.0 ** rng.uniform(-4, -1)]))
+    o.ActiveNumberOfThreads = int(rng.integers(wl.NT // 2, wl.NT + 1))
+    if wl.name.startswith("kellermiksis"):
+        # dimensionless bubble dynamics: keep the controller inside the range where the collapse stays finite
+        o.MaximumTimeStep = 1.0e6
+        o.MinimumTimeStep = min(o.MinimumTimeStep, 1e-10)
+    return o
 
 
 RESULT_FIELDS = ("TimeDomain", "ActualState", "ActualTime", "ControlParameters", "Accessories",

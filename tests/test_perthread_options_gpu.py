@@ -1,0 +1,87 @@
+"""The CUDA thread-per-system path against the CPU checker under RANDOM solver options, through the public API.
+
+tests/test_perthread_gpu.py holds every system at its tutorial's options; here every run-time knob of
+SolverOption (ST/Interface.cuh:932-1082) is redrawn per trial (cases.random_options -- the same draws that pin the
+checker against the host-compiled reference in tests/test_oracle_option_fuzz.py), so that the kernel's less-travelled
+branches run on the device: forced acceptance below 1.01*dtmin and the clamps of the step-size factor and of the
+new step (ST/ExplicitRungeKutta_ErrorControllers.cuh:60-85 -- the exact code behind the single-precision screening),
+all three event directions with loose and tight bands (ST/EventHandling.cuh:21-44), dense output with a save
+frequency > 1, a minimum spacing and a buffer that fills up (ST/DenseOutput.cuh:6-58), ActiveNumberOfThreads < NT.
+
+Tolerances.  GPU and CPU differ by O(1e-16) perturbations per step (FMA contraction, CUDA math library vs glibc, the
+pow-free step-size factor); the same draws run through the checker compiled with and without FMA contraction agree to
+1e-6 on > 99 % of the instances with identical step counts on > 99 % (the rest sit on accept/reject or event ties).
+The gates below leave room for that and still catch any semantic difference, which would move every instance."""
+import copy
+
+import numpy as np
+import pytest
+
+from cases import make_cases, random_options
+
+pytestmark = pytest.mark.gpu
+
+TRIALS = 8
+# name -> (lane mappings, fraction of instances that must agree, largest step-count difference tolerated anywhere,
+#          tolerance on the stored dense-output samples of instances with identical step sequences)
+SYSTEMS = {
+    "duffing_rk4_f64": ((0, 1), 0.97, 4, 1e-9),
+    "duffing_rkck45_f64": ((0, 1), 0.90, 12, 1e-5),
+    "poincare_rkck45_f64": ((0,), 0.90, 12, None),
+    "lorenz_rkck45_f64": ((0, 1), 0.90, 12, None),
+    "impact_rkck45_f64": ((0,), 0.85, 40, None),
+    # the wall velocity at a collapse amplifies a rounding difference a million times: samples are compared to 1e-3
+    "kellermiksis_dense_rkck45_f64": ((0,), 0.85, 40, 1e-3),
+}
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+
+
+@pytest.mark.parametrize("name", sorted(SYSTEMS))
+def test_random_solver_options_against_the_checker(name, workloads, pkg, oracle):
+    refills, frac, max_diff, sample_tol = SYSTEMS[name]
+    wl0, phases = make_cases(workloads)[name]
+    rng = np.random.default_rng(20261017 + sum(map(ord, name)))       # the draws of tests/test_oracle_option_fuzz.py
+    idx = np.unique(np.linspace(0, wl0.NT - 1, 24).round().astype(np.int64))
+    n_phases = min(phases, 2)
+    state_ok, steps_same, steps_diff, dense_same, events_same, state_err, samples_ok = [], [], [], [], [], [], []
+    for trial in range(TRIALS):
+        wl = copy.copy(wl0)
+        wl.buffers = wl0.buffers.take(idx)
+        wl.options = random_options(rng, wl, trial)
+        active = wl.options.ActiveNumberOfThreads
+        ref, ratt, racc = oracle.run_oracle(wl, phases=n_phases)
+        for refill in refills:
+            out, att, acc = pkg.run_workload(wl, phases=n_phases, lane_refill=refill)
+            # inactive instances: untouched, bit for bit (ST/Solver.cuh:91)
+            assert np.array_equal(out.ActualState[:, active:], wl.buffers.ActualState[:, active:]), (name, trial)
+            assert (att[active:] == 0).all() and (att[:active] > 0).all(), (name, trial)
+            assert (att >= acc).all()
+            err = np.maximum(rel_err(out.ActualState, ref.ActualState).max(axis=0), rel_err(out.ActualTime, ref.ActualTime))[:active]
+            state_err.append(err)
+            state_ok.append(err < 1e-6)
+            steps_same.append(((att == ratt) & (acc == racc))[:active])
+            steps_diff.append(np.abs(att - ratt)[:active])
+            if wl.shape.NIA:
+                events_same.append((out.IntegerAccessories == ref.IntegerAccessories).all(axis=0)[:active])
+            if wl.shape.NDO:
+                same = (out.DenseIndex == ref.DenseIndex)[:active]
+                dense_same.append(same)
+                # stored samples of the instances whose step sequences agree: same times, same states
+                cols = np.where(same & (att == ratt)[:active])[0]
+                for c in cols[:8]:
+                    n = min(int(ref.DenseIndex[c]), wl.shape.NDO)
+                    samples_ok.append(rel_err(out.DenseTime[:n, c], ref.DenseTime[:n, c]).max() < sample_tol and
+                                      rel_err(out.DenseState[:n, :, c], ref.DenseState[:n, :, c]).max() < sample_tol)
+    cat = np.concatenate
+    assert cat(state_ok).mean() >= frac, (name, "endpoints", cat(state_ok).mean())
+    assert np.median(cat(state_err)) < 1e-9, (name, "median endpoint error", np.median(cat(state_err)))
+    assert cat(steps_same).mean() >= frac, (name, "step counts", cat(steps_same).mean())
+    assert cat(steps_diff).max() <= max_diff, (name, "largest step-count difference", cat(steps_diff).max())
+    if events_same:
+        assert cat(events_same).mean() >= frac, (name, "event counters", cat(events_same).mean())
+    if dense_same:
+        assert cat(dense_same).mean() >= frac, (name, "dense index", cat(dense_same).mean())
+        assert len(samples_ok) >= TRIALS and np.mean(samples_ok) >= frac - 0.1, (name, "stored samples", np.mean(samples_ok))
