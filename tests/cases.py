@@ -82,3 +82,28 @@ def make_coupled_cases(WC):
 
 COUPLED_RESULT_FIELDS = ("TimeDomain", "ActualState", "ActualTime", "UnitAccessories", "IntegerUnitAccessories", "SystemAccessories",
                          "IntegerSystemAccessories", "DenseIndex", "DenseTime", "DenseState")
+
+
+def random_coupled_options(rng, wl, trial):
+    """The block-per-system module's run-time knobs (CP/Interface.cuh:1083-1215) redrawn; same intent as random_options."""
+    sh = wl.shape
+    o = copy.copy(wl.options)
+    # fixed-step RK4 takes (time domain) / InitialTimeStep steps: keep it within what the host emulation of the reference can do
+    o.InitialTimeStep = float(10.0 ** (rng.uniform(-2.7, -2) if sh.Algorithm == 0 else rng.uniform(-5, -2)))
+    o.MaximumTimeStep = float(10.0 ** rng.uniform(-1, 3))
+    o.MinimumTimeStep = float(10.0 ** (rng.uniform(-4.5, -3) if trial % 3 == 0 else rng.uniform(-13, -8)))
+    o.TimeStepGrowLimit = float(rng.uniform(1.2, 10.0))
+    o.TimeStepShrinkLimit = float(rng.uniform(0.05, 0.7))
+    o.RelativeTolerance = 10.0 ** rng.uniform(-10, -4, sh.UD)
+    o.AbsoluteTolerance = 10.0 ** rng.uniform(-10, -4, sh.UD)
+    if sh.NE:
+        o.EventTolerance = 10.0 ** rng.uniform(-7, -3, sh.NE)
+        o.EventDirection = rng.integers(-1, 2, sh.NE).astype(np.int32)
+    if sh.NDO:
+        o.DenseOutputSaveFrequency = int(rng.integers(1, 5))
+        o.DenseOutputMinimumTimeStep = float(rng.choice([0.0, 10.0 ** rng.uniform(-4, -1)]))
+    o.ActiveSystems = int(rng.integers(max(1, wl.buffers.NS - 1), wl.buffers.NS + 1))
+    if wl.name.startswith("bubble"):
+        o.MaximumTimeStep = 1.0e6
+        o.MinimumTimeStep = min(o.MinimumTimeStep, 1e-10)
+    return o
