@@ -4,7 +4,7 @@ Runs the coupled controller's clamps and forced acceptance at the minimum step (
 504-539), unit-scope events in all three directions (CP/EventHandling.cuh), dense output with save frequency / minimum spacing
 (CP/DenseOutput.cuh) and ActiveSystems < NS on the device, for the four coupling-matrix layouts, RK4 and RKCK45, FP64.
 
-Gates as in tests/test_perthread_options_gpu.py: GPU and CPU differ by rounding-level perturbations per step, so a system whose
+Gates as in tests/test_zz_options_perthread_gpu.py: GPU and CPU differ by rounding-level perturbations per step, so a system whose
 accept/reject or event decision sits on a tie may take another step sequence; a semantic difference would move every system."""
 import copy
 import importlib
