@@ -37,6 +37,7 @@
 #include <math.h>
 #include <stdio.h>
 #include "../mpgos_b200.h"
+#include "ptx_primitives.cuh"
 
 namespace mpgos_b200 {
 
@@ -185,12 +186,6 @@ template <int FIRST, int N> struct CkRow<double, FIRST, N>
 };
 #endif
 
-// SFU approximations without the denormal / special-case wrappers of the CUDA math library
-// (operands are range-checked by the caller).
-__device__ __forceinline__ float sfu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sfu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sfu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
 // ---------------------------------------------------------------------------------------------
 // numeric helpers
 
@@ -274,13 +269,6 @@ __device__ __forceinline__ P ratio_root_fast(P tol, P err, bool accept, float& y
 #ifndef MPGOS_B200_PACKED_F32
 #define MPGOS_B200_PACKED_F32 1
 #endif
-__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
-{ unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b)
-{ unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-
 template <class P, int N, bool PACKED = (MPGOS_B200_PACKED_F32 != 0) && (sizeof(P) == 4) && (N >= 3)>
 struct Vec
 {
@@ -847,6 +835,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 	}
 }
 
+#ifdef __CUDACC__      // from here on: kernel launches (the host-compiled test harness of tests/kernel_on_host stops here)
 // ---------------------------------------------------------------------------------------------
 // Dispatch order of the direct mapping.  The hardware hands out thread blocks in blockIdx order, so a launch ends with
 // whatever its last blocks cost: when the expensive instances sit at the end of a sweep the SMs idle behind them (the
@@ -996,6 +985,7 @@ struct PerThreadLauncher
 		return (int)(L->LaneRefill ? enqueue<true>(L, a, stream) : enqueue<false>(L, a, stream));
 	}
 };
+#endif // __CUDACC__
 
 } // namespace mpgos_b200
 #endif
