@@ -110,7 +110,7 @@ template <int UPSP>
 __device__ __forceinline__ void slot_barrier(int slot)
 {
 	if (UPSP == 32) __syncwarp();
-	else asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "r"(UPSP) : "memory");
+	else named_barrier_sync(slot + 1, UPSP);
 }
 
 // Steppers.cuh:2551-2713 on the packed matrix; `cpt` is one coupling term of all units of the system.
@@ -153,10 +153,6 @@ __device__ __forceinline__ P coupling_value(const P* __restrict__ M, const P* cp
 // ---- tensor-core coupling -------------------------------------------------------------------------------------------
 // D[8x8] += A[8x4] . B[4x8] in FP64.  Fragments (PTX ISA, mma.m8n8k4 .f64): lane l holds A[l/4][l%4], B[l%4][l/4] and
 // D[l/4][2*(l%4) + {0,1}].
-__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b)
-{
-	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // Geometry of the block-wide product for UPS units and SLOTS <= 8 systems (warp-groups of UPS threads; the N extent of the
 // instruction is 8, columns SLOTS..7 stay zero).  The RT x KG work items (one row tile x one group of k tiles) are dealt
@@ -209,17 +205,10 @@ __device__ __forceinline__ void mma_coupling_product(const double* __restrict__ 
 // A_small.B_big + A_big.B_small + A_big.B_big (the small.small term is below FP32 resolution): ~2e-7 relative, FP32 accuracy.
 // Fragments (PTX ISA, mma.m16n8k8 .tf32), g = lane/4, t = lane%4: A: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4);
 // B: b0 (k = t, n = g), b1 (k = t+4, n = g); D: d0 (g, 2t), d1 (g, 2t+1), d2 (g+8, 2t), d3 (g+8, 2t+1).
-__device__ __forceinline__ unsigned to_tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void tf32_split(float v, float& big, float& small)
 {
 	big = __uint_as_float(to_tf32(v));
 	small = __uint_as_float(to_tf32(v - big));
-}
-__device__ __forceinline__ void mma_16x8x8_tf32(float (&d)[4], const float4& a, float b0, float b1)
-{
-	asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	    : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-	    : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
 }
 
 template <int UPS, int SLOTS_>
@@ -291,7 +280,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	constexpr int V_ELEMS   = MMA ? NC * G::KG * G::NCOL * G::VS : 0;      // partial column sums per k group
 	static_assert(!MMA || (CBW == 0 && CCI == 0 && NC > 0), "tensor-core coupling: dense matrices shared by all systems");
 
-	extern __shared__ __align__(16) unsigned char dyn_smem[];
+	MPGOS_B200_DYNAMIC_SHARED_MEMORY(dyn_smem);
 	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE x MCOPIES]  packed (scalar) or in fragment order (MMA)
 	P*   s_cptm   = s_matrix + MSIZE * MCOPIES;                         // [CPT_ALL]
 	P*   s_vpart  = s_cptm + CPT_ALL;                                   // [V_ELEMS]
@@ -790,6 +779,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	}
 }
 
+#ifdef __CUDACC__      // from here on: kernel launches (the host-compiled test harness of tests/kernel_on_host stops here)
 // ---------------------------------------------------------------------------------------------------------------
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
           int NE, bool DENSE, int ALG>
@@ -900,6 +890,7 @@ struct PerBlockLauncher
 		return enqueue<SPBK, false>(L, a, stream);
 	}
 };
+#endif // __CUDACC__
 
 } // namespace mpgos_b200
 #endif

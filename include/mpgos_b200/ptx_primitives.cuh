@@ -24,5 +24,24 @@ __device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, un
 __device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b)
 { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// ---- block-per-system kernel (perblock_kernel.cuh) ----------------------------------------------------------------------
+// named barrier over `count` threads (a slot of the block synchronises on its own, never with __syncthreads())
+__device__ __forceinline__ void named_barrier_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+// the block's dynamic shared memory as a byte array
+#define MPGOS_B200_DYNAMIC_SHARED_MEMORY(name) extern __shared__ __align__(16) unsigned char name[]
+// FP64 tensor-core product D[8x8] += A[8x4] . B[4x8], fragments as in the PTX ISA (mma.m8n8k4 .f64)
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b)
+{
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// TF32 rounding and the m16n8k8 TF32 product with FP32 accumulation (3xTF32 coupling of the FP32 kernel)
+__device__ __forceinline__ unsigned to_tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_16x8x8_tf32(float (&d)[4], const float4& a, float b0, float b1)
+{
+	asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+	    : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	    : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
 } // namespace mpgos_b200
 #endif
