@@ -1,0 +1,164 @@
+// TEST INFRASTRUCTURE ONLY -- lets g++ compile the BODY of the product's block-per-system kernel
+// (include/mpgos_b200/perblock_kernel.cuh above its `#ifdef __CUDACC__`) and run it with ONE std::thread PER CUDA THREAD of a block,
+// blocks one after the other:
+//   __shared__ / dynamic shared memory -> statics shared by the emulated threads
+//   __syncthreads / __syncwarp / named barriers -> spinning barriers over the block / warp / the given thread count
+//   __shfl_xor_sync, __all_sync, __any_sync -> exchange through a per-warp buffer between two warp barriers
+//   the FP64 tensor-core instruction mma.m8n8k4 -> the same product formed from the 32 lanes' fragments
+// The product itself has no CPU path; nothing under include/ or the package refers to this directory.
+#ifndef MPGOS_B200_TESTS_CUDA_BLOCK_ON_HOST_H
+#define MPGOS_B200_TESTS_CUDA_BLOCK_ON_HOST_H
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <cuda_runtime.h>      // host side of the toolkit headers (float4, the qualifiers expand to nothing under g++)
+
+#ifdef __launch_bounds__
+#undef __launch_bounds__
+#endif
+#define __launch_bounds__(...)
+#ifdef __grid_constant__
+#undef __grid_constant__
+#endif
+#define __grid_constant__
+#ifdef __shared__
+#undef __shared__
+#endif
+#define __shared__ static
+
+struct host_dim3 { unsigned x, y, z; };
+static thread_local host_dim3 host_threadIdx = {0, 0, 0}, host_blockIdx = {0, 0, 0}, host_blockDim = {1, 1, 1}, host_gridDim = {1, 1, 1};
+#define threadIdx host_threadIdx
+#define blockIdx  host_blockIdx
+#define blockDim  host_blockDim
+#define gridDim   host_gridDim
+
+// sense-reversing barrier; the emulated threads outnumber the cores, so waiting yields
+struct HostBarrier
+{
+	std::atomic<int> arrived{0};
+	std::atomic<unsigned> generation{0};
+	void wait(int count)
+	{
+		const unsigned g = generation.load(std::memory_order_acquire);
+		if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == count) { arrived.store(0, std::memory_order_relaxed); generation.fetch_add(1, std::memory_order_acq_rel); }
+		else while (generation.load(std::memory_order_acquire) == g) std::this_thread::yield();
+	}
+};
+enum { HOST_MAX_WARPS = 32 };
+struct HostWarp { HostBarrier bar; unsigned long long x[32]; int vote[32]; };
+static HostBarrier g_block_bar, g_named_bar[16];
+static HostWarp    g_warp[HOST_MAX_WARPS];
+static std::atomic<int> g_block_or{0};
+alignas(16) static unsigned char g_dynamic_shared[96 * 1024];
+
+static inline HostWarp& host_warp() { return g_warp[host_threadIdx.x >> 5]; }
+static inline void __syncthreads() { g_block_bar.wait((int)host_blockDim.x); }
+static inline void __syncwarp() { host_warp().bar.wait(32); }
+static inline int  __syncthreads_or(int p)
+{
+	if (p) g_block_or.store(1);
+	__syncthreads();
+	const int r = g_block_or.load();
+	__syncthreads();
+	if (host_threadIdx.x == 0) g_block_or.store(0);
+	__syncthreads();
+	return r;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o)
+{
+	static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+	HostWarp& w = host_warp();  const int lane = host_threadIdx.x & 31;
+	std::memcpy(&w.x[lane], &v, sizeof(T));
+	w.bar.wait(32);
+	T r;  std::memcpy(&r, &w.x[lane ^ o], sizeof(T));
+	w.bar.wait(32);
+	return r;
+}
+static inline int __all_sync(unsigned, int p)
+{
+	HostWarp& w = host_warp();  w.vote[host_threadIdx.x & 31] = p ? 1 : 0;
+	w.bar.wait(32);
+	int r = 1;  for (int i = 0; i < 32; i++) r &= w.vote[i];
+	w.bar.wait(32);
+	return r;
+}
+static inline int __any_sync(unsigned, int p)
+{
+	HostWarp& w = host_warp();  w.vote[host_threadIdx.x & 31] = p ? 1 : 0;
+	w.bar.wait(32);
+	int r = 0;  for (int i = 0; i < 32; i++) r |= w.vote[i];
+	w.bar.wait(32);
+	return r;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int  __double2hiint(double x) { long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int  __float_as_int(float x) { int b; std::memcpy(&b, &x, 4); return b; }
+static inline unsigned __float_as_uint(float x) { unsigned b; std::memcpy(&b, &x, 4); return b; }
+static inline float __uint_as_float(unsigned b) { float x; std::memcpy(&x, &b, 4); return x; }
+static inline float __double2float_rn(double x) { return (float)x; }
+static inline unsigned __ballot_sync(unsigned, int) { std::abort(); }
+static inline int  __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int  __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int  __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+template <class T> static inline T __shfl_sync(unsigned, T, int) { std::abort(); }
+template <class T> static inline T __shfl_down_sync(unsigned, T, int) { std::abort(); }
+static inline void sincospi(double x, double* s, double* c)
+{
+	const double r = std::remainder(x, 2.0);       // as the checker's stand-in (oracle/ref_coupled_shim.h)
+	*s = std::sin(3.14159265358979323846 * r);  *c = std::cos(3.14159265358979323846 * r);
+}
+static inline void sincospi(float x, float* s, float* c)
+{
+	const float r = std::remainder(x, 2.0f);
+	*s = std::sin(3.14159265358979323846f * r);  *c = std::cos(3.14159265358979323846f * r);
+}
+using std::fma;  using std::fmin;  using std::fmax;  using std::fabs;  using std::pow;  using std::sin;  using std::cos;  using std::sqrt;
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+static inline int      max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline int      min(int a, int b) { return a < b ? a : b; }
+
+// stand-ins for include/mpgos_b200/ptx_primitives.cuh (its include guard is taken here)
+#define MPGOS_B200_PTX_PRIMITIVES_CUH
+#define MPGOS_B200_DYNAMIC_SHARED_MEMORY(name) unsigned char* const name = g_dynamic_shared
+namespace mpgos_b200 {
+static inline float sfu_lg2(float x) { return std::log2(x); }
+static inline float sfu_ex2(float x) { return std::exp2(x); }
+static inline float sfu_rcp(float x) { return 1.0f / x; }
+static inline unsigned long long f32x2_pack(float, float) { std::abort(); }
+static inline void f32x2_unpack(unsigned long long, float&, float&) { std::abort(); }
+static inline unsigned long long f32x2_fma(unsigned long long, unsigned long long, unsigned long long) { std::abort(); }
+static inline unsigned long long f32x2_mul(unsigned long long, unsigned long long) { std::abort(); }
+static inline void named_barrier_sync(int id, int count) { g_named_bar[id].wait(count); }
+// D[8x8] += A[8x4] . B[4x8]: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2 (l%4) + {0,1}]  (PTX ISA, mma.m8n8k4 .f64);
+// k ascending, one fused multiply-add per term
+static inline void dmma_8x8x4(double& d0, double& d1, double a, double b)
+{
+	HostWarp& w = host_warp();  const int lane = host_threadIdx.x & 31;
+	static thread_local double fa, fb;   // unused; keeps the signature's value semantics obvious
+	fa = a;  fb = b;
+	double* A = reinterpret_cast<double*>(w.x);                 // [8][4] as lane order
+	static double Bs[HOST_MAX_WARPS][32];
+	double* B = Bs[host_threadIdx.x >> 5];
+	A[lane] = a;  B[lane] = b;
+	w.bar.wait(32);
+	const int row = lane >> 2, c0 = 2 * (lane & 3);
+	for (int k = 0; k < 4; k++)
+	{
+		d0 = std::fma(A[row * 4 + k], B[c0 * 4 + k], d0);        // B[k][n] sits in lane n*4 + k
+		d1 = std::fma(A[row * 4 + k], B[(c0 + 1) * 4 + k], d1);
+	}
+	w.bar.wait(32);
+}
+static inline unsigned to_tf32(float) { std::abort(); }
+static inline void mma_16x8x8_tf32(float (&)[4], const float4&, float, float) { std::abort(); }
+}
+
+#define MPGOS_B200_TABLEAU_ROW_LOADS 0
+
+#endif
