@@ -101,11 +101,26 @@ static inline int  __float_as_int(float x) { int b; std::memcpy(&b, &x, 4); retu
 static inline unsigned __float_as_uint(float x) { unsigned b; std::memcpy(&b, &x, 4); return b; }
 static inline float __uint_as_float(unsigned b) { float x; std::memcpy(&x, &b, 4); return x; }
 static inline float __double2float_rn(double x) { return (float)x; }
-static inline unsigned __ballot_sync(unsigned, int) { std::abort(); }
+static inline unsigned __ballot_sync(unsigned, int p)
+{
+	HostWarp& w = host_warp();  w.vote[host_threadIdx.x & 31] = p ? 1 : 0;
+	w.bar.wait(32);
+	unsigned r = 0;  for (int i = 0; i < 32; i++) r |= (unsigned)w.vote[i] << i;
+	w.bar.wait(32);
+	return r;
+}
 static inline int  __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int  __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int  __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
-template <class T> static inline T __shfl_sync(unsigned, T, int) { std::abort(); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src)
+{
+	HostWarp& w = host_warp();  const int lane = host_threadIdx.x & 31;
+	std::memcpy(&w.x[lane], &v, sizeof(T));
+	w.bar.wait(32);
+	T r;  std::memcpy(&r, &w.x[src & 31], sizeof(T));
+	w.bar.wait(32);
+	return r;
+}
 template <class T> static inline T __shfl_down_sync(unsigned, T, int) { std::abort(); }
 static inline void sincospi(double x, double* s, double* c)
 {
@@ -130,10 +145,12 @@ namespace mpgos_b200 {
 static inline float sfu_lg2(float x) { return std::log2(x); }
 static inline float sfu_ex2(float x) { return std::exp2(x); }
 static inline float sfu_rcp(float x) { return 1.0f / x; }
-static inline unsigned long long f32x2_pack(float, float) { std::abort(); }
-static inline void f32x2_unpack(unsigned long long, float&, float&) { std::abort(); }
-static inline unsigned long long f32x2_fma(unsigned long long, unsigned long long, unsigned long long) { std::abort(); }
-static inline unsigned long long f32x2_mul(unsigned long long, unsigned long long) { std::abort(); }
+static inline unsigned long long f32x2_pack(float lo, float hi) { unsigned a, b; std::memcpy(&a, &lo, 4); std::memcpy(&b, &hi, 4); return (unsigned long long)a | ((unsigned long long)b << 32); }
+static inline void f32x2_unpack(unsigned long long v, float& lo, float& hi) { unsigned a = (unsigned)v, b = (unsigned)(v >> 32); std::memcpy(&lo, &a, 4); std::memcpy(&hi, &b, 4); }
+static inline unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{ float a0, a1, b0, b1, c0, c1; f32x2_unpack(a, a0, a1); f32x2_unpack(b, b0, b1); f32x2_unpack(c, c0, c1); return f32x2_pack(std::fma(a0, b0, c0), std::fma(a1, b1, c1)); }
+static inline unsigned long long f32x2_mul(unsigned long long a, unsigned long long b)
+{ float a0, a1, b0, b1; f32x2_unpack(a, a0, a1); f32x2_unpack(b, b0, b1); return f32x2_pack(a0 * b0, a1 * b1); }
 static inline void named_barrier_sync(int id, int count) { g_named_bar[id].wait(count); }
 // D[8x8] += A[8x4] . B[4x8]: lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2 (l%4) + {0,1}]  (PTX ISA, mma.m8n8k4 .f64);
 // k ascending, one fused multiply-add per term

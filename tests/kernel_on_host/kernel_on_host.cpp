@@ -2,7 +2,12 @@
 // C-ABI (oracle/oracle_abi.h), one library per (system, algorithm, precision, dense):
 //   -DKOH_SYSTEM=Lorenz -DKOH_PREC=double -DKOH_ALG=1 -DKOH_DENSE=0 -DKOH_NDO=0
 // Each instance is one call of the kernel function with blockIdx.x = instance (direct mapping, one thread per block).
+#ifdef KOH_REFILL      // the persistent-warp lane mapping needs real warps: one std::thread per CUDA thread (cuda_block_on_host.h)
+#include "cuda_block_on_host.h"
+#include <thread>
+#else
 #include "cuda_on_host.h"
+#endif
 #include "../../include/mpgos_b200/perthread_kernel.cuh"
 #include "../../massively-parallel-gpu-ode-solver_b200/csrc/builtin_systems.cuh"
 #include "../../oracle/oracle_abi.h"
@@ -47,6 +52,24 @@ extern "C" int ref_perthread_run(const oracle_perthread_buffers* b, const oracle
 	for (int i = 0; i < SD; i++) { a.RelativeTolerance[i] = ((const P*)b->RelativeTolerance)[i];  a.AbsoluteTolerance[i] = ((const P*)b->AbsoluteTolerance)[i]; }
 	for (int i = 0; i < NE; i++) { a.EventTolerance[i] = ((const P*)b->EventTolerance)[i];  a.EventDirection[i] = b->EventDirection[i]; }
 
+#ifdef KOH_REFILL
+	// LaneRefill = KOH_REFILL idle lanes per warp trigger a refill; 2 blocks of 64 threads (2 warps each) share the instance queue
+	a.RefillThreshold = KOH_REFILL;
+	for (int phase = 0; phase < o->Phases; phase++)
+	{
+		queue = 0;
+		for (int block = 0; block < 2; block++)
+		{
+			std::vector<std::thread> pool;
+			for (int t = 0; t < 64; t++)
+				pool.emplace_back([=]() {
+					host_threadIdx.x = (unsigned)t;  host_blockIdx.x = (unsigned)block;  host_blockDim.x = 64;  host_gridDim.x = 2;
+					perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, (KOH_DENSE != 0), KOH_ALG, true, 2>(a);
+				});
+			for (auto& th : pool) th.join();
+		}
+	}
+#else
 	host_blockDim.x = 1;  host_threadIdx.x = 0;  host_gridDim.x = (unsigned)NT;
 	for (int phase = 0; phase < o->Phases; phase++)
 		for (int inst = 0; inst < NT; inst++)
@@ -54,6 +77,7 @@ extern "C" int ref_perthread_run(const oracle_perthread_buffers* b, const oracle
 			host_blockIdx.x = (unsigned)inst;
 			perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, (KOH_DENSE != 0), KOH_ALG, false, 2>(a);
 		}
+#endif
 	for (int i = 0; i < NT; i++)
 	{
 		if (b->steps_attempted) b->steps_attempted[i] += (long long)att[i];

@@ -39,8 +39,8 @@ def koh():
     return KOH
 
 
-def run_kernel_on_host(koh, oracle, name, wl, phases, strict):
-    lib = C.CDLL(os.path.join(koh, "_build", f"libkoh_{name}{'_strict' if strict else ''}.so"))
+def run_kernel_on_host(koh, oracle, name, wl, phases, strict, refill=False):
+    lib = C.CDLL(os.path.join(koh, "_build", f"libkoh_{name}{'_refill' if refill else '_strict' if strict else ''}.so"))
     s = oracle._Shape()
     lib.ref_perthread_shape(C.byref(s))
     oracle._check_shape(s, wl)
@@ -145,3 +145,22 @@ def test_kernel_source_under_random_solver_options(name, strict, koh, cases, ora
     for flags in (dense_same, events_same):
         if flags:
             assert cat(flags).all(), name
+
+
+@pytest.mark.parametrize("name", ["lorenz_rkck45_f64", "impact_rkck45_f64", "duffing_rk4_f64", "kellermiksis_dense_rkck45_f64"])
+def test_lane_refill_mapping_is_bit_identical_on_host(name, koh, cases, oracle):
+    """The persistent-warp mapping (LaneRefill: idle lanes counted by a warp ballot, instance ids taken from the queue with one
+    atomic per refill; thresholds 1, 5, 12 and 32 idle lanes) run with real 32-thread warps -- one std::thread per CUDA thread,
+    two blocks of two warps sharing the queue: every instance is integrated exactly once, the kernel terminates, and each result
+    is bit-identical to the direct mapping, also with fewer active instances than allocated."""
+    wl0, phases = cases[name]
+    for active in (None, 50):
+        wl = copy.copy(wl0)
+        wl.options = copy.copy(wl0.options)
+        wl.options.ActiveNumberOfThreads = active
+        direct, datt, dacc = run_kernel_on_host(koh, oracle, name, wl, phases, False)
+        refill, ratt, racc = run_kernel_on_host(koh, oracle, name, wl, phases, False, refill=True)
+        assert identical(direct, refill), (name, active)
+        assert np.array_equal(datt, ratt) and np.array_equal(dacc, racc)
+        n = wl.NT if active is None else active
+        assert (ratt[:n] > 0).all() and (ratt[n:] == 0).all()
