@@ -160,3 +160,29 @@ def test_block_kernel_source_under_random_solver_options(name, koh, WC, oracle):
     assert cat(close).all(), name
     if events:
         assert cat(events).all(), name
+
+
+@pytest.mark.parametrize("name", ["bubble_u16_rk4", "ring_b0c1_rk4", "ring_b1c1_rkck45", "bubble_u8_rkck45"])
+def test_non_finite_states_follow_the_reference(name, koh, WC, oracle):
+    """One unit of system 0 starts at 1e200.  Coupled RK4: message, end of the phase, the step is NOT committed (unlike the
+    thread-per-system module; CP/ExplicitRungeKutta_ErrorControllers.cuh:421-441); RKCK45: rejected and shrunk down to 1.01*dtmin,
+    then the phase ends (:504-539).  The reference's own kernels on the host == the checker bit for bit; the kernel source == the
+    checker in step counts and in what is finite, the other systems unaffected."""
+    tag, wl0, _ = make_coupled_cases(WC)[name]
+    wl = copy.copy(wl0)
+    wl.buffers = wl0.buffers.copy()
+    wl.options = copy.copy(wl0.options)
+    wl.buffers.ActualState[0, 0, 1] = 1e200
+    wl.options.MinimumTimeStep = 1e-5
+    chk, catt, cacc = oracle.run_coupled_oracle(wl, phases=1)
+    if os.path.exists(oracle.coupled_ref_library_path(tag)):
+        ref = oracle.run_coupled_ref(tag, wl, phases=1)
+        assert identical(chk, ref)
+    assert cacc[0] == 0 and (cacc[1:] > 0).all()
+    out, att, acc = run_block_kernel_on_host(koh, oracle, name, wl, 1)
+    assert np.array_equal(att, catt) and np.array_equal(acc, cacc)
+    assert np.array_equal(np.isfinite(out.ActualState), np.isfinite(chk.ActualState))
+    assert np.array_equal(out.ActualState[:, 0, :], chk.ActualState[:, 0, :], equal_nan=True)       # system 0: never advanced
+    assert rel_err(out.ActualState[:, 1:, :], chk.ActualState[:, 1:, :]) < 1e-9
+    if "rk4" in name:
+        assert identical(out, chk)

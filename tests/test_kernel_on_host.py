@@ -164,3 +164,34 @@ def test_lane_refill_mapping_is_bit_identical_on_host(name, koh, cases, oracle):
         assert np.array_equal(datt, ratt) and np.array_equal(dacc, racc)
         n = wl.NT if active is None else active
         assert (ratt[:n] > 0).all() and (ratt[n:] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["lorenz_rk4_f64", "lorenz_rkck45_f64", "duffing_rk4_f64", "duffing_rkck45_f64", "impact_rkck45_f64"])
+def test_non_finite_states_follow_the_reference(name, koh, cases, oracle):
+    """an initial condition that overflows in the first right-hand side (1e200) or a little later (1e120).
+    RK4: message, end of the phase, the non-finite state IS committed (ST/ExplicitRungeKutta_ErrorControllers.cuh:13-19).
+    RKCK45: the step is rejected and shrunk by the shrink limit until 1.01*dtmin, then the phase ends with the last finite
+    state (:60-70).  Checked three ways: host-compiled reference == checker bit for bit; kernel source == checker in step
+    counts, times and NaN pattern, healthy neighbours untouched."""
+    wl0, _ = cases[name]
+    wl = copy.copy(wl0)
+    wl.buffers = wl0.buffers.take(np.arange(16))
+    wl.options = copy.copy(wl0.options)
+    wl.buffers.ActualState[0, ::4] = 1e200
+    wl.buffers.ActualState[0, 1::4] = 1e120
+    wl.options.MinimumTimeStep = 1e-6
+    chk, catt, cacc = oracle.run_oracle(wl, phases=1, double_literals=True)
+    if oracle.ref_available(wl):
+        ref, ratt, racc = oracle.run_ref(wl, phases=1)
+        assert identical(chk, ref) and np.array_equal(catt, ratt) and np.array_equal(cacc, racc)
+    assert not np.isfinite(chk.ActualState[:, ::4]).all() or "rkck45" in name
+    for strict in (True, False):
+        out, att, acc = run_kernel_on_host(koh, oracle, name, wl, 1, strict)
+        assert np.array_equal(att, catt) and np.array_equal(acc, cacc), (name, strict)
+        assert np.array_equal(np.isfinite(out.ActualState), np.isfinite(chk.ActualState))
+        assert np.array_equal(out.ActualTime[::4], chk.ActualTime[::4])
+        assert np.array_equal(out.IntegerAccessories, chk.IntegerAccessories)
+        healthy = np.isfinite(chk.ActualState).all(axis=0)
+        assert rel_err(out.ActualState[:, healthy], chk.ActualState[:, healthy]).max() < 1e-6
+        if "rk4" in name:
+            assert identical(out, chk)
