@@ -186,3 +186,19 @@ def test_non_finite_states_follow_the_reference(name, koh, WC, oracle):
     assert rel_err(out.ActualState[:, 1:, :], chk.ActualState[:, 1:, :]) < 1e-9
     if "rk4" in name:
         assert identical(out, chk)
+
+
+def test_tensor_core_variant_with_two_couplings_events_and_dense_output(koh, WC, oracle):
+    """Ring of 32 Duffing oscillators with two FULL coupling matrices (two matrix products per stage), one event per unit with
+    user-defined termination, system accessories written by unit 0, dense output: the lockstep tensor-core variant (8 slots, 5
+    systems: idle slots, systems leaving the lockstep at different times) and the scalar variant (3 slots) against the checker."""
+    wl = WC.duffing_ring(NS=5, CBW=0, CCI=0, UPS=32, ndo=60, TPB=32, SPB=1)
+    rng = np.random.default_rng(7)
+    wl.buffers.CouplingMatrix[...] = rng.uniform(0.0, 0.08, (2, 32, 32)) * (1.0 - np.eye(32))[None]
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=1, host_threads=4)
+    assert len(set(ref.ActualTime.tolist())) == 5
+    for build in ("ring_u32_rkck45_mma", "ring_u32_rkck45"):
+        out, att, acc = run_block_kernel_on_host(koh, oracle, build, wl, 1)
+        check_against_checker(build, out, att, acc, ref, ratt, racc)
+        n = int(ref.DenseIndex.min())
+        assert rel_err(out.DenseTime[:n], ref.DenseTime[:n]) < 1e-9 and rel_err(out.DenseState[:n], ref.DenseState[:n]) < 1e-7
