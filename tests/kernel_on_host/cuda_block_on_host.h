@@ -50,7 +50,7 @@ struct HostBarrier
 	}
 };
 enum { HOST_MAX_WARPS = 32 };
-struct HostWarp { HostBarrier bar; unsigned long long x[32]; int vote[32]; };
+struct HostWarp { HostBarrier bar; unsigned long long x[32]; int vote[32]; double db[32]; float fa[128], fb[64]; };
 static HostBarrier g_block_bar, g_named_bar[16];
 static HostWarp    g_warp[HOST_MAX_WARPS];
 static std::atomic<int> g_block_or{0};
@@ -157,23 +157,38 @@ static inline void named_barrier_sync(int id, int count) { g_named_bar[id].wait(
 static inline void dmma_8x8x4(double& d0, double& d1, double a, double b)
 {
 	HostWarp& w = host_warp();  const int lane = host_threadIdx.x & 31;
-	static thread_local double fa, fb;   // unused; keeps the signature's value semantics obvious
-	fa = a;  fb = b;
-	double* A = reinterpret_cast<double*>(w.x);                 // [8][4] as lane order
-	static double Bs[HOST_MAX_WARPS][32];
-	double* B = Bs[host_threadIdx.x >> 5];
+	double* A = reinterpret_cast<double*>(w.x);                 // A[m][k] sits in lane m*4 + k
+	double* B = w.db;                                           // B[k][n] sits in lane n*4 + k
 	A[lane] = a;  B[lane] = b;
 	w.bar.wait(32);
 	const int row = lane >> 2, c0 = 2 * (lane & 3);
 	for (int k = 0; k < 4; k++)
 	{
-		d0 = std::fma(A[row * 4 + k], B[c0 * 4 + k], d0);        // B[k][n] sits in lane n*4 + k
+		d0 = std::fma(A[row * 4 + k], B[c0 * 4 + k], d0);
 		d1 = std::fma(A[row * 4 + k], B[(c0 + 1) * 4 + k], d1);
 	}
 	w.bar.wait(32);
 }
-static inline unsigned to_tf32(float) { std::abort(); }
-static inline void mma_16x8x8_tf32(float (&)[4], const float4&, float, float) { std::abort(); }
+// cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 mantissa bits kept
+static inline unsigned to_tf32(float x) { unsigned u; std::memcpy(&u, &x, 4); if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u; return u & ~0x1fffu; }
+// D[16x8] += A[16x8] . B[8x8], g = lane/4, t = lane%4: a0 (g, t), a1 (g+8, t), a2 (g, t+4), a3 (g+8, t+4); b0 (k = t, n = g), b1 (k = t+4, n = g);
+// d0 (g, 2t), d1 (g, 2t+1), d2 (g+8, 2t), d3 (g+8, 2t+1)  (PTX ISA, mma.m16n8k8 .tf32); operands are TF32 values already
+static inline void mma_16x8x8_tf32(float (&d)[4], const float4& a, float b0, float b1)
+{
+	HostWarp& w = host_warp();  const int lane = host_threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+	float* A = w.fa;  float* B = w.fb;                          // A[m][k] at m*8 + k, B[k][n] at k*8 + n
+	A[g * 8 + t] = a.x;  A[(g + 8) * 8 + t] = a.y;  A[g * 8 + t + 4] = a.z;  A[(g + 8) * 8 + t + 4] = a.w;
+	B[t * 8 + g] = b0;   B[(t + 4) * 8 + g] = b1;
+	w.bar.wait(32);
+	for (int k = 0; k < 8; k++)
+	{
+		d[0] = std::fma(A[g * 8 + k], B[k * 8 + 2 * t], d[0]);
+		d[1] = std::fma(A[g * 8 + k], B[k * 8 + 2 * t + 1], d[1]);
+		d[2] = std::fma(A[(g + 8) * 8 + k], B[k * 8 + 2 * t], d[2]);
+		d[3] = std::fma(A[(g + 8) * 8 + k], B[k * 8 + 2 * t + 1], d[3]);
+	}
+	w.bar.wait(32);
+}
 }
 
 #define MPGOS_B200_TABLEAU_ROW_LOADS 0

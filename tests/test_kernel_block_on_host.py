@@ -202,3 +202,16 @@ def test_tensor_core_variant_with_two_couplings_events_and_dense_output(koh, WC,
         check_against_checker(build, out, att, acc, ref, ratt, racc)
         n = int(ref.DenseIndex.min())
         assert rel_err(out.DenseTime[:n], ref.DenseTime[:n]) < 1e-9 and rel_err(out.DenseState[:n], ref.DenseState[:n]) < 1e-7
+
+
+def test_single_precision_tensor_core_variant_3xtf32(koh, WC, oracle):
+    """FP32 kernel, dense coupling as 3xTF32 (big + small TF32 parts, mma.m16n8k8 with FP32 accumulation, rebuilt here from the
+    lanes' fragments with cvt.rna rounding) and the scalar FP32 variant, against the single-precision checker: same step counts,
+    endpoints at single-precision accuracy -- the split keeps FP32 accuracy, a plain TF32 product (10 mantissa bits) would not."""
+    wl = WC.bubble_ensemble(NS=11, UPS=32, amplitude=(0.2, 1.2), dtype=np.float32)
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=1, host_threads=4)
+    for build in ("bubble_u32_rkck45_mma_f32", "bubble_u32_rkck45_f32"):
+        out, att, acc = run_block_kernel_on_host(koh, oracle, build, wl, 1)
+        assert out.ActualState.dtype == np.float32 and np.array_equal(out.ActualTime, ref.ActualTime)
+        assert np.abs(att - ratt).max() <= 1 and np.abs(acc - racc).max() <= 1
+        assert rel_err(out.ActualState, ref.ActualState) < 1e-5
