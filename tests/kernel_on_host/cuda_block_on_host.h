@@ -58,7 +58,11 @@ alignas(16) static unsigned char g_dynamic_shared[96 * 1024];
 
 static inline HostWarp& host_warp() { return g_warp[host_threadIdx.x >> 5]; }
 static inline void __syncthreads() { g_block_bar.wait((int)host_blockDim.x); }
+#ifdef KOH_BREAK_SYNCWARP      // negative control of the ThreadSanitizer run: a slot barrier that does not synchronise must be reported
+static inline void __syncwarp() {}
+#else
 static inline void __syncwarp() { host_warp().bar.wait(32); }
+#endif
 static inline int  __syncthreads_or(int p)
 {
 	if (p) g_block_or.store(1);
