@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- runs one host-compiled kernel library that was built with -fsanitize=thread (Makefile target
-`tsan`) on a small case; started by tests/test_kernel_race_check.py in a subprocess with libtsan preloaded.  ThreadSanitizer
+`tsan`) or -fsanitize=address,undefined (target `asan`) on a small case; started by tests/test_kernel_sanitizers_on_host.py in a subprocess with libtsan preloaded.  ThreadSanitizer
 sees the emulated CUDA threads as what they are here -- std::threads -- and the emulated barriers as acquire/release
 synchronisation, so an access to shared memory (function-local statics of the kernel) or to global memory that is not ordered
 by a barrier is reported as a data race with the kernel's own file:line.
-usage: tsan_driver.py <library> <case>"""
+usage: sanitizer_driver.py <library> <case>"""
 import copy
 import ctypes as C
 import importlib
@@ -25,6 +25,8 @@ if case.startswith("perthread:"):
     wl = copy.copy(wl0)
     wl.buffers = wl0.buffers.take(np.arange(0, wl0.NT, max(wl0.NT // 80, 1)))
     out = wl.buffers.copy()
+    if os.environ.get("KOH_SHRINK_DENSE") == "1":      # negative control of the AddressSanitizer run: a dense-output buffer a tenth as long as declared
+        out.DenseState = out.DenseState[: out.DenseState.shape[0] // 10].copy()
     cb, co, att, acc, _k = O._pack(wl, out, 1, 1)
     assert lib.ref_perthread_run(C.byref(cb), C.byref(co)) == 0
     ref, ratt, racc = O.run_oracle(wl, phases=1)
