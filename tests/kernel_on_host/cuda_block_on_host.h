@@ -54,7 +54,7 @@ struct HostWarp { HostBarrier bar; unsigned long long x[32]; int vote[32]; doubl
 static HostBarrier g_block_bar, g_named_bar[16];
 static HostWarp    g_warp[HOST_MAX_WARPS];
 static std::atomic<int> g_block_or{0};
-alignas(16) static unsigned char g_dynamic_shared[96 * 1024];
+alignas(16) static unsigned char g_dynamic_shared[227 * 1024];      // the most a block can have on sm_100a
 
 static inline HostWarp& host_warp() { return g_warp[host_threadIdx.x >> 5]; }
 static inline void __syncthreads() { g_block_bar.wait((int)host_blockDim.x); }

@@ -84,6 +84,13 @@ extern "C" int ref_coupled_run(const oracle_coupled_buffers* b, const oracle_cou
 	for (int i = 0; i < UD; i++) { a.RelativeTolerance[i] = ((const P*)b->RelativeTolerance)[i];  a.AbsoluteTolerance[i] = ((const P*)b->AbsoluteTolerance)[i]; }
 	for (int i = 0; i < NE; i++) { a.EventTolerance[i] = ((const P*)b->EventTolerance)[i];  a.EventDirection[i] = b->EventDirection[i]; }
 	if (a.Active <= 0) return 0;
+	{
+		// dynamic shared memory the launcher would ask for (PerBlockLauncher::enqueue); the shim's buffer must hold it
+		using G = typename MmaGeometryFor<P, (KOH_MMA != 0) ? UPS : 32, (KOH_MMA != 0) ? KOH_SLOTS : 8>::type;
+		const size_t extra = (KOH_MMA != 0) ? (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
+		const size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * ((KOH_MMA != 0) ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
+		if (smem > sizeof(g_dynamic_shared)) return 2;
+	}
 
 	const char* slice = std::getenv("KOH_SLICE");
 	for (int phase = 0; phase < o->Phases; phase++)
