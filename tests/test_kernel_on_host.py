@@ -195,3 +195,32 @@ def test_non_finite_states_follow_the_reference(name, koh, cases, oracle):
         assert rel_err(out.ActualState[:, healthy], chk.ActualState[:, healthy]).max() < 1e-6
         if "rk4" in name:
             assert identical(out, chk)
+
+
+FP32_CASES = {
+    # name: (workload factory, sub-sample, phases, tolerance on the median endpoint error)
+    "poincare_rk4": (lambda W: W.poincare_t3(NT=4096, algorithm=W.RK4), 64, 2, 0.0),
+    "duffing_rkck45": (lambda W: W.duffing_t1(NT=4096, algorithm=W.RKCK45), 64, 2, 1e-5),
+    "impact_rkck45": (lambda W: W.impact_t6(NT=1 << 14), 64, 4, 1e-4),
+    "kellermiksis_rkck45": (lambda W: W.keller_miksis_t5(NT=4096, ndo=0), 64, 1, 1e-5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FP32_CASES))
+def test_fp32_kernel_source_of_the_other_systems(name, koh, workloads, oracle):
+    """The single-precision instantiations (packed FFMA2 stages from 3 components on, exact limit compares instead of the
+    screening) against the true-FP32 checker with the settings of workloads.single_precision: fixed step bit for bit, adaptive
+    at single-precision accuracy (single-precision step sequences decorrelate: step counts within 10 %)."""
+    from cases import subsample
+    factory, n, phases, tol = FP32_CASES[name]
+    wl = workloads.single_precision(subsample(factory(workloads), n))
+    ref, ratt, racc = oracle.run_oracle(wl, phases=phases, double_literals=False)
+    for strict in (True, False):
+        out, att, acc = run_kernel_on_host(koh, oracle, name + "_f32", wl, phases, strict)
+        assert out.ActualState.dtype == np.float32 and np.isfinite(out.ActualState).all()
+        if "rk4" in name:
+            assert identical(out, ref) and np.array_equal(att, ratt)
+            continue
+        err = rel_err(out.ActualState.astype(np.float64), ref.ActualState.astype(np.float64)).max(axis=0)
+        assert np.median(err) < tol, (name, strict, np.median(err))
+        assert np.abs(att - ratt).max() <= max(4, 0.1 * ratt.max())
