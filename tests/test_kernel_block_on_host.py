@@ -18,6 +18,8 @@ import subprocess
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.timeout(900)      # thread-per-CUDA-thread emulation: a protocol error would otherwise hang the suite
+
 from cases import make_coupled_cases, random_coupled_options, COUPLED_RESULT_FIELDS
 
 HERE = os.path.dirname(os.path.abspath(__file__))

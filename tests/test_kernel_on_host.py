@@ -19,6 +19,8 @@ import subprocess
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.timeout(900)      # thread-per-CUDA-thread emulation: a protocol error would otherwise hang the suite
+
 from cases import make_cases, random_options, RESULT_FIELDS
 
 HERE = os.path.dirname(os.path.abspath(__file__))

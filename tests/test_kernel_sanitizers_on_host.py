@@ -14,6 +14,8 @@ import sys
 
 import pytest
 
+pytestmark = pytest.mark.timeout(900)      # thread-per-CUDA-thread emulation: a protocol error would otherwise hang the suite
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 KOH = os.path.join(HERE, "kernel_on_host")
 TSANCXX = os.environ.get("TSANCXX", "/usr/bin/g++")

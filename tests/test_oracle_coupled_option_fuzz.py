@@ -9,6 +9,8 @@ import os
 import numpy as np
 import pytest
 
+pytestmark = pytest.mark.timeout(900)      # thread-per-CUDA-thread emulation: a protocol error would otherwise hang the suite
+
 from cases import make_coupled_cases, random_coupled_options, COUPLED_RESULT_FIELDS
 
 NAMES = ["ring_b1c1_rkck45", "ring_b1c0_rkck45", "ring_b0c0_rkck45", "ring_b0c1_rk4", "bubble_u8_rkck45", "ring_b1c1_rkck45_f32"]
