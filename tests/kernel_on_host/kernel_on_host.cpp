@@ -14,8 +14,31 @@
 #include <vector>
 
 using P = KOH_PREC;
+#ifdef KOH_USER_SYSDEF
+// A user's system definition, unmodified: the six PerThread_* callbacks of a reference tutorial, included where it lies under
+// /root/reference at build time (never copied), bound exactly as include/SingleSystem_PerThread_Interface.cuh binds them
+// (mpgos_b200::UserCallbacks; that header also holds the host object, which needs nvcc and the runtime library).
+#include KOH_USER_SYSDEF
+struct Sys
+{
+	static inline void OdeFunction(int tid, int NT, P* F, P* X, P T, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_OdeFunction(tid, NT, F, X, T, cPAR, sPAR, sPARi, ACC, ACCi); }
+	static inline void EventFunction(int tid, int NT, P* EF, P T, P dT, P* TD, P* X, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_EventFunction(tid, NT, EF, T, dT, TD, X, cPAR, sPAR, sPARi, ACC, ACCi); }
+	static inline void ActionAfterEventDetection(int tid, int NT, int IDX, int& UDT, P& T, P& dT, P* TD, P* X, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_ActionAfterEventDetection(tid, NT, IDX, UDT, T, dT, TD, X, cPAR, sPAR, sPARi, ACC, ACCi); }
+	static inline void ActionAfterSuccessfulTimeStep(int tid, int NT, int& UDT, P& T, P& dT, P* TD, P* X, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_ActionAfterSuccessfulTimeStep(tid, NT, UDT, T, dT, TD, X, cPAR, sPAR, sPARi, ACC, ACCi); }
+	static inline void Initialization(int tid, int NT, int& DOIDX, P& T, P& dT, P* TD, P* X, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_Initialization(tid, NT, DOIDX, T, dT, TD, X, cPAR, sPAR, sPARi, ACC, ACCi); }
+	static inline void Finalization(int tid, int NT, int& DOIDX, P& T, P& dT, P* TD, P* X, P* cPAR, P* sPAR, int* sPARi, P* ACC, int* ACCi)
+	{ PerThread_Finalization(tid, NT, DOIDX, T, dT, TD, X, cPAR, sPAR, sPARi, ACC, ACCi); }
+};
+enum { SD = KOH_SD, NCP = KOH_NCP, NSP = KOH_NSP, NISP = KOH_NISP, NE = KOH_NE, NA = KOH_NA, NIA = KOH_NIA };
+#else
 using Sys = mpgos_b200::builtin::KOH_SYSTEM;
 enum { SD = Sys::SD, NCP = Sys::NCP, NSP = Sys::NSP, NISP = Sys::NISP, NE = Sys::NE, NA = Sys::NA, NIA = Sys::NIA };
+#endif
 
 extern "C" void ref_perthread_shape(oracle_perthread_shape* s)
 {

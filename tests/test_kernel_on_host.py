@@ -226,3 +226,36 @@ def test_fp32_kernel_source_of_the_other_systems(name, koh, workloads, oracle):
         err = rel_err(out.ActualState.astype(np.float64), ref.ActualState.astype(np.float64)).max(axis=0)
         assert np.median(err) < tol, (name, strict, np.median(err))
         assert np.abs(att - ratt).max() <= max(4, 0.1 * ratt.max())
+
+
+USER_CASES = ["lorenz_rk4_f64", "lorenz_rkck45_f64", "duffing_rk4_f64", "duffing_rkck45_f64", "poincare_rk4_f64", "poincare_rkck45_f64",
+              "impact_rkck45_f64", "kellermiksis_rkck45_f64"]
+
+
+@pytest.mark.parametrize("name", USER_CASES)
+def test_reference_tutorial_system_definitions_unmodified_through_our_kernel(name, koh, cases, oracle):
+    """The drop-in claim at its most literal, on the CPU: the reference's own *_SystemDefinition.cuh files (included from
+    /root/reference at build time, not copied; bound to the kernel as the drop-in header's UserCallbacks binds them) run through
+    OUR kernel body, against the same files run through the REFERENCE's kernel (oracle/_ref).  Fixed step: bit for bit.  Adaptive:
+    the same step sequence on every instance, endpoints to 1e-9."""
+    tut = "/root/reference/Tutorials_SingleSystem_PerThread"
+    wl, phases = cases[name]
+    if not os.path.isdir(tut) or not oracle.ref_available(wl):
+        pytest.skip("needs /root/reference (development container only)")
+    r = subprocess.run(["make", "-j8", "-C", koh, "user"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    ref, ratt, racc = oracle.run_ref(wl, phases=phases)
+    lib = C.CDLL(os.path.join(koh, "_build", f"libkoh_user_{name}.so"))
+    shape = oracle._Shape()
+    lib.ref_perthread_shape(C.byref(shape))
+    oracle._check_shape(shape, wl)
+    out = wl.buffers.copy()
+    cb, co, att, acc, _keep = oracle._pack(wl, out, phases, 1)
+    lib.ref_perthread_run.restype = C.c_int
+    assert lib.ref_perthread_run(C.byref(cb), C.byref(co)) == 0
+    assert np.array_equal(att, ratt) and np.array_equal(acc, racc)
+    assert np.array_equal(out.IntegerAccessories, ref.IntegerAccessories) and np.array_equal(out.DenseIndex, ref.DenseIndex)
+    if "rk4" in name:
+        assert identical(out, ref)
+    else:
+        assert rel_err(out.ActualState, ref.ActualState).max() < 1e-9
