@@ -12,9 +12,34 @@
 #include <vector>
 
 using P = KOH_PREC;
+#ifdef KOH_USER_SYSDEF
+// A user's coupled system definition, unmodified: the CoupledSystems_PerBlock_* callbacks of a reference tutorial, included where it
+// lies under /root/reference at build time (never copied), bound as include/CoupledSystems_PerBlock_Interface.cuh binds them
+// (mpgos_b200::UserCoupledCallbacks).  -DKOH_SHAPE=UD,NC,NUP,NSP,NGP,NiGP,NUA,NiUA,NSA,NiSA,NE
+#include KOH_USER_SYSDEF
+struct Sys
+{
+	static inline void OdeFunction(int sid, int uid, P* F, P* X, P T, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC, P* CPT, P* CPF)
+	{ CoupledSystems_PerBlock_OdeFunction(sid, uid, F, X, T, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC, CPT, CPF); }
+	static inline void EventFunction(int sid, int uid, P* EF, P T, P dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC)
+	{ CoupledSystems_PerBlock_EventFunction(sid, uid, EF, T, dT, TD, X, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC); }
+	static inline void ActionAfterEventDetection(int sid, int uid, int IDX, int& UDT, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC)
+	{ CoupledSystems_PerBlock_ActionAfterEventDetection(sid, uid, IDX, UDT, T, dT, TD, X, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC); }
+	static inline void ActionAfterSuccessfulTimeStep(int sid, int uid, int& UDT, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC)
+	{ CoupledSystems_PerBlock_ActionAfterSuccessfulTimeStep(sid, uid, UDT, T, dT, TD, X, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC); }
+	static inline void Initialization(int sid, int uid, int& DOIDX, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC)
+	{ CoupledSystems_PerBlock_Initialization(sid, uid, DOIDX, T, dT, TD, X, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC); }
+	static inline void Finalization(int sid, int uid, int& DOIDX, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC)
+	{ CoupledSystems_PerBlock_Finalization(sid, uid, DOIDX, T, dT, TD, X, uPAR, sPAR, gPAR, igPAR, uACC, iuACC, sACC, isACC); }
+};
+static constexpr int kShape[11] = { KOH_SHAPE };
+enum { UPS = KOH_UPS, CBW = KOH_CBW, CCI = KOH_CCI, UD = kShape[0], NC = kShape[1], NUP = kShape[2], NSP = kShape[3], NGP = kShape[4], NiGP = kShape[5],
+       NUA = kShape[6], NiUA = kShape[7], NSA = kShape[8], NiSA = kShape[9], NE = kShape[10], UPSP = ((UPS + 31) / 32) * 32 };
+#else
 using Sys = mpgos_b200::builtin::KOH_SYSTEM<P>;
 enum { UPS = KOH_UPS, CBW = KOH_CBW, CCI = KOH_CCI, UD = Sys::UD, NC = Sys::NC, NUP = Sys::NUP, NSP = Sys::NSP, NGP = Sys::NGP, NiGP = Sys::NiGP,
        NUA = Sys::NUA, NiUA = Sys::NiUA, NSA = Sys::NSA, NiSA = Sys::NiSA, NE = Sys::NE, UPSP = ((UPS + 31) / 32) * 32 };
+#endif
 #ifndef KOH_BLOCKS
 #define KOH_BLOCKS 2
 #endif

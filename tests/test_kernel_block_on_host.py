@@ -42,8 +42,8 @@ def WC(pkg):
     return importlib.import_module(pkg.__name__ + ".workloads_coupled")
 
 
-def run_block_kernel_on_host(koh, oracle, build, wl, phases, pilot_slice=False):
-    lib = C.CDLL(os.path.join(koh, "_build", f"libkohb_{build}.so"))
+def run_block_kernel_on_host(koh, oracle, build, wl, phases, pilot_slice=False, user=False):
+    lib = C.CDLL(os.path.join(koh, "_build", f"libkohb_{'user_' if user else ''}{build}.so"))
     s = oracle._CShape()
     lib.ref_coupled_shape(C.byref(s))
     oracle._ccheck(s, wl)
@@ -217,3 +217,28 @@ def test_single_precision_tensor_core_variant_3xtf32(koh, WC, oracle):
         assert out.ActualState.dtype == np.float32 and np.array_equal(out.ActualTime, ref.ActualTime)
         assert np.abs(att - ratt).max() <= 1 and np.abs(acc - racc).max() <= 1
         assert rel_err(out.ActualState, ref.ActualState) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["ring_b1c1_rkck45", "ring_b0c1_rk4", "ring_b0c0_rkck45", "bubble_u16_rkck45", "bubble_u16_rk4"])
+def test_reference_coupled_tutorial_definitions_unmodified_through_our_kernel(name, koh, WC, oracle):
+    """The reference's own coupled *_SystemDefinition.cuh files (ring of Duffing oscillators, bubble ensemble; included from
+    /root/reference at build time, not copied; bound as the drop-in header's UserCoupledCallbacks binds them) through OUR block
+    kernel, against the same files through the REFERENCE's coupled kernels run on the host (oracle/_ref): fixed step bit for bit,
+    adaptive with the same step sequence of every system."""
+    tag, wl0, phases = make_coupled_cases(WC)[name]
+    if not os.path.isdir("/root/reference/Tutorials_CoupledSystems_PerBlock") or not os.path.exists(oracle.coupled_ref_library_path(tag)):
+        pytest.skip("needs /root/reference (development container only)")
+    r = subprocess.run(["make", "-j8", "-C", koh, "user"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    wl = copy.copy(wl0)
+    wl.buffers = wl0.buffers.take(np.arange(min(3, wl0.buffers.NS)))
+    ref = oracle.run_coupled_ref(tag, wl, phases=1)
+    chk, catt, cacc = oracle.run_coupled_oracle(wl, phases=1)        # step counts (the reference keeps none); bit-identical to `ref`
+    assert identical(chk, ref)
+    out, att, acc = run_block_kernel_on_host(koh, oracle, name, wl, 1, user=True)
+    assert np.array_equal(att, catt) and np.array_equal(acc, cacc)
+    assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories) and np.array_equal(out.DenseIndex, ref.DenseIndex)
+    if "rk4" in name:
+        assert identical(out, ref)
+    else:
+        assert rel_err(out.ActualState, ref.ActualState) < 1e-9 and rel_err(out.ActualTime, ref.ActualTime) < 1e-12
