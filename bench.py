@@ -71,7 +71,7 @@ def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int
         if world > 1:
             import copy
             wl = copy.copy(full)
-            wl.buffers = full.buffers.take(sharding.shard_indices(n, rank, world, COUPLED_TILE))
+            wl.buffers = full.buffers.take(sharding.shard_indices(n, rank, world, COUPLED_TILE if n % COUPLED_TILE == 0 else 1))
             return wl
         return full
     single = (lambda wl: W.single_precision(wl)) if precision == "f32" else (lambda wl: wl)     # our FP32 settings: tolerances 1e-5
@@ -230,6 +230,279 @@ class Arm:
         self.ps.close()
 
 
+EXTRA_CONFIGS = (      # key, workload, precision, phases per step  -- run after the headline, same timing rules, fewer steps
+    ("C1_duffing_rk4_f64", "duffing", "f64", 8),
+    ("C2_lorenz_rkck45_f32", "lorenz", "f32", 1),
+    ("C3_impact_rkck45_f64", "impact", "f64", 8),
+    ("C4_kellermiksis_dense_rkck45_f64", "kellermiksis_dense", "f64", 2),
+    ("C5_coupled_bubbles_rkck45_f64", "coupled", "f64", 1),
+)
+
+
+def reference_gpu_baseline(kind, wl, N, precision, phases, per_rank_attempted_per_launch, kmean):
+    """Reported baseline, not a target: the reference MPGOS compiled unmodified for sm_100a (oracle/_ref), same inputs, same
+    event bracket -- both without a register cap and at the -maxrregcount of the reference's own tutorial makefile ("stock"),
+    over 64 / 128 / 256 threads per block; the best setting is the baseline, every setting tried is listed."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    tried = {}
+    if kind == "coupled":
+        if not (N == 8192 and precision == "f64"):
+            return None
+        for tag in ("bubble_ensemble_u64_s1", "bubble_ensemble_u64_s2", "bubble_ensemble_u64_s1_stock", "bubble_ensemble_u64_s2_stock", "bubble_ensemble_u64_s4_stock"):
+            if not os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
+                continue
+            for shared in (0, 1):
+                try:
+                    with quiet_stdout():
+                        _, ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=phases, shared_matrices=shared, repeats=2)
+                    tried[f"{tag.replace('bubble_ensemble_u64_', '')},SharedCouplingMatrices={shared}"] = ms / phases
+                except Exception as e:
+                    tried[f"{tag},SharedCouplingMatrices={shared}"] = None
+        what = ("reference MPGOS CoupledSystems_PerBlock kernel compiled unmodified by nvcc for sm_100a; settings: s1/s2/s4 = SPB 1/2/4 with TPB = 64 SPB, "
+                "'stock' = -maxrregcount=128 as in the reference's T2_BubbleEnsemble/makefile, SharedCouplingMatrices 0/1")
+    else:
+        for variant in ("", "stock"):
+            if not oracle_py.ref_gpu_available(wl, variant):
+                continue
+            for tpb in (64, 128, 256):
+                try:
+                    with quiet_stdout():
+                        _, ms = oracle_py.run_ref_gpu(wl, phases=phases, threads_per_block=tpb, repeats=2, variant=variant)
+                    tried[f"{variant or 'nocap'},tpb={tpb}"] = ms / phases
+                except Exception as e:
+                    tried[f"{variant or 'nocap'},tpb={tpb}"] = None
+        what = ("reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a; settings: 'nocap' = no register cap, "
+                "'stock' = the -maxrregcount of the reference's own tutorial makefile (T2_Lorenz 64, T1_Reference / T6_ImpactDynamics 80, T5 128), ThreadsPerBlock 64/128/256")
+    ok = {k: v for k, v in tried.items() if v}
+    if not ok:
+        return None
+    best = min(ok, key=ok.get)
+    ref_ms = ok[best]
+    return {"kernel_ms": ref_ms, "value": per_rank_attempted_per_launch / (ref_ms * 1e-3), "unit": "system-steps/s", "speedup_kernel": ref_ms / kmean,
+            "best_setting": best, "kernel_ms_by_setting": tried,
+            "what": what + " (oracle/_ref); best of 2 per setting, the fastest setting is the baseline; same inputs; step count taken from our counters"}
+
+
+_PEAKS = {}
+
+
+def measured_peak(pkg, device, precision_bytes):
+    """FMA peak of this GPU in TFLOP/s, measured in this process: FP64 = max(DFMA probe, DMMA probe), FP32 = FFMA probe."""
+    key = (device, precision_bytes)
+    if key not in _PEAKS:
+        fma = pkg.probe_fma_peak(device, precision_bytes)
+        if precision_bytes == 8:
+            mma = pkg.probe_dmma_peak(device)
+            _PEAKS[key] = (max(fma, mma), {"dfma_probe": fma, "dmma_probe": mma})
+        else:
+            _PEAKS[key] = (fma, {"ffma_probe": fma})
+    return _PEAKS[key]
+
+
+def measure(pkg, args, workload, precision, N, phases, steps, warmup, rank, local_rank, world, full):
+    """One configuration through the product: device-resident `value`, `e2e` through the public API with host buffers, roofline,
+    clocks, and (N = 1) the two reported baselines.  Returns the result dict on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    kind, cfg_name, n_default, flops_per_step, alg = WORKLOADS[workload]
+    unit = "systems" if kind == "coupled" else "instances"
+    metric = "system-steps/sec (%s %s)" % ("FP64" if precision == "f64" else "FP32", alg)
+    config = {"workload": f"{workload}: {N} {unit} per GPU x {world} GPU(s), {phases} integration phase(s) per step (BASELINE {cfg_name})",
+              f"{unit}_per_gpu": N, "phases_per_step": phases,
+              "sharding": "tile-cyclic, no collective on the data path",
+              "l2": "flushed between timed iterations (a 256 MiB buffer is overwritten on the solver's stream, outside the summed event brackets); state is restored device-to-device from a snapshot before every step; the kernel is bound by instruction issue (an FP64 instruction takes two issue slots), its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
+              "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
+
+    wl = build_workload(pkg, workload, precision, N, rank, world)
+    arm = Arm(pkg, wl, kind, local_rank, args)
+    ps = arm.ps
+    ps.SaveState()
+    stream = torch.cuda.ExternalStream(ps.stream, device=local_rank)
+
+    for _ in range(warmup):
+        ps.RestoreState()
+        for _ in range(phases):
+            ps.Solve()
+    ps.SynchroniseDevice()
+    ps.ResetStepCounters()
+
+    # ---- value: device-resident ---------------------------------------------------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 2)]
+    ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    # L2 (126 MB) is flushed between timed iterations by overwriting a 256 MiB buffer on the solver's stream; the flush itself is
+    # outside the event brackets that are summed into the step time
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.25)
+    barrier(); torch.cuda.synchronize()
+    t_host0 = time.time()
+    ev[0].record(stream)
+    for k in range(steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(k & 0xff)
+        ev_step[k].record(stream)
+        ps.RestoreState()
+        ev[2 + 2 * k].record(stream)
+        for _ in range(phases):
+            ps.Solve()
+        ev[3 + 2 * k].record(stream)
+    ev[1].record(stream)
+    torch.cuda.synchronize(); barrier()
+    t_host1 = time.time()
+    clocks = sampler.stop(t_host0, t_host1)
+    region_ms = sum(ev_step[k].elapsed_time(ev[3 + 2 * k]) for k in range(steps))      # K x (restore + phases), flushes excluded
+    kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) / phases for k in range(steps)]
+    attempted, accepted = arm.total_steps()
+    dense_samples = None
+    if kind == "perthread" and wl.shape.NDO > 0:
+        # points stored by the last phase (the built-in dense systems restart the index every phase) x phases per step
+        ps.SynchroniseFromDeviceToHost(arm.V.DenseIndex)
+        ps.SynchroniseDevice()
+        dense_samples = int(np.minimum(ps.host(arm.V.DenseIndex), wl.shape.NDO).sum()) * phases
+    del flush
+
+    # ---- e2e: host buffers through the public API, double-buffered over `chunks` solver objects ----
+    chunks = max(1, args.e2e_chunks)
+    while N % chunks or (kind == "perthread" and N // chunks < 1):
+        chunks -= 1
+    if chunks == 1:
+        e2e_arms = [arm]
+    else:
+        import copy
+        sharding = importlib.import_module(pkg.__name__ + ".sharding")
+        e2e_arms = []
+        for c in range(chunks):
+            w = copy.copy(wl)
+            w.buffers = wl.buffers.take(sharding.shard_indices(N // chunks, c, chunks, 1))
+            e2e_arms.append(Arm(pkg, w, kind, local_rank, args))
+    h2d = d2h = 0
+    for a in e2e_arms:
+        hi, do = a.make_host_buffers(torch)
+        h2d += hi
+        d2h += do
+
+    def step_e2e():
+        # T7's loop: wait for a solver object (its previous sweep is then in the caller's arrays), refill it and launch it again,
+        # while the other objects compute -- so the copies of one step also overlap the kernels of its neighbours
+        for a in e2e_arms:
+            a.finish_e2e()
+            a.enqueue_e2e(phases)
+
+    def drain_e2e():
+        for a in e2e_arms:
+            a.finish_e2e()
+
+    for _ in range(2):
+        step_e2e()
+    drain_e2e()
+    for a in e2e_arms:
+        a.ps.ResetStepCounters()
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    drain_e2e()
+    torch.cuda.synchronize(); barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_attempted = sum(a.total_steps()[0] for a in e2e_arms)
+    final_state_checksum = float(sum(a.user_out[a.V.ActualState].double().sum() for a in e2e_arms))
+
+    # ---- reduce over ranks -------------------------------------------------------------------------
+    sharding = importlib.import_module(pkg.__name__ + ".sharding")
+    (region_ms, e2e_s, kmean), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms))],
+                                                                   [attempted, accepted, e2e_attempted], device="cuda")
+    attempted, accepted, e2e_attempted = [int(x) for x in counts]
+
+    out = None
+    if rank == 0:
+        value = attempted / (region_ms * 1e-3)
+        precision_bytes = 8 if precision == "f64" else 4
+        peak_tf, peak_probes = measured_peak(pkg, local_rank, precision_bytes)
+        per_rank_attempted_per_launch = attempted / world / steps / phases
+        achieved_tf = per_rank_attempted_per_launch * flops_per_step / (kmean * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{workload}_{precision}")
+        # solver kernels of the timed region, plus the three ordering kernels in front of every phase that has a cost history
+        # (second and later phases of a step; per-thread module: only launches of more than 16 blocks per SM, coupled module: queues
+        # longer than two rounds of slots, and there the first phase too: pilot slice + ordered continuation)
+        tpb = (args.threads_per_block or getattr(wl.options, "ThreadsPerBlock", None) or 128) if kind == "perthread" else 1
+        tiles = (N + tpb - 1) // tpb
+        ordered = (tiles > 16 * 148) if kind == "perthread" else (N > 2 * 148 * 8)
+        if kind == "coupled":      # every phase is cost-ordered (3 kernels); the first one of a step after a pilot slice (one more solver launch)
+            ordering_kernels = (3 * phases + 1) if ordered else 0
+        else:
+            ordering_kernels = 3 * (phases - 1) if (ordered and args.lane_refill <= 0) else 0
+        out = {"metric": metric, "value": value, "unit": "system-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": region_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": precision, "data": "synthetic", "config": config,
+               "accepted_steps_per_s": accepted / (region_ms * 1e-3),
+               "system_steps_per_step": attempted / steps,
+               "roofline": {"bound": "fp64_fma" if precision_bytes == 8 else "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": achieved_tf / peak_tf, "traffic": traffic,
+                            "peak_source": "measured on this GPU in this process (~10 ms register-resident chains, 256 FMAs per loop trip, CUDA events): FP64 = max of the DFMA probe and the FP64 tensor-core (DMMA) probe, FP32 = FFMA probe; MEASURED_PEAKS.json carries no FP64/FP32 FMA figure. The issue-rate bound is one DFMA per 2 cycles per SM sub-partition = 32 flop/clk x 592 x SM clock (37.2 TFLOP/s at 1965 MHz)",
+                            "peak_probes": peak_probes,
+                            "kernel_ms": kmean, "algorithmic_flops_per_launch": per_rank_attempted_per_launch * flops_per_step,
+                            "fp64_pipe_utilisation_ncu": NCU_PIPE.get(f"{workload}_{precision}")},
+               "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_s / steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
+               "gpu_launches": steps * (phases + ordering_kernels), "clocks": clocks}
+        if dense_samples is not None:
+            # the only HBM stream that matters on this path: (SD + 1) words per stored point (SURVEY.md 8d: 24 B for Keller-Miksis)
+            bytes_per_sample = (wl.shape.SD + 1) * precision_bytes
+            hbm_peak = None
+            mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(mp):
+                hbm_peak = json.load(open(mp)).get("hbm_gbs")
+            gbs = dense_samples * bytes_per_sample / (kmean * phases * 1e-3) / 1e9
+            out["dense_output"] = {"stored_points_per_step_per_gpu": dense_samples, "bytes_per_point": bytes_per_sample, "achieved_gbs": gbs,
+                                   "hbm_peak_gbs": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None,
+                                   "note": "rank 0; algorithmic bytes of the dense-output stream over the kernel time -- the kernel is issue-bound (FP64), the stream is far from the HBM roof"}
+        if world == 1 and not args.no_reference_gpu:
+            try:
+                r = reference_gpu_baseline(kind, wl, N, precision, phases, per_rank_attempted_per_launch, kmean)
+                if r is not None:
+                    out["reference_gpu"] = r
+            except Exception as e:   # the baseline must never break the bench line
+                out["reference_gpu"] = {"unavailable": str(e)[:200]}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            big = threads >= 16
+            if full:
+                sample = args.cpu_sample or {"coupled": 512 if big else 128, "kellermiksis": 1 << 15, "kellermiksis_dense": 1 << 15,
+                                             "duffing": 10000, "impact": 1 << 17 if big else 1 << 15}.get(workload, 1 << 19 if big else 1 << 17)
+            else:       # the extra configurations: a couple of seconds each
+                sample = {"coupled": 256 if big else 64, "kellermiksis_dense": 1 << 14, "duffing": 10000, "impact": 1 << 15}.get(workload, 1 << 17)
+            sample = min(sample, N)
+            n, s, kind_cpu, nt = cpu_reference_run(pkg, workload, precision, sample, threads, phases)
+            out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind_cpu,
+                                   "sample": f"every {max(N // nt, 1)}-th {unit[:-1]} of the sweep ({nt} {unit}), {phases} phase(s), {threads} host threads, {s:.1f} s"}
+    for a in e2e_arms:
+        if a is not arm:
+            a.close()
+    arm.close()
+    return out
+
+
+# FP64-pipe activity of the solver kernel as ncu reports it (sm__inst_executed_pipe_fp64 / pipe_fp64_cycles_active, from the
+# committed captures under profiles/; not measured live -- a number taken under a profiler is not a bench value): the honest
+# utilisation figure for right-hand sides whose transcendentals count 0 algorithmic flops.
+NCU_PIPE = {}
+_np = os.path.join(ROOT, "profiles", "ncu_pipe_utilisation.json")
+if os.path.exists(_np):
+    try:
+        NCU_PIPE = json.load(open(_np))
+    except Exception:
+        NCU_PIPE = {}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -247,6 +520,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--configs", default="auto", help="'auto': after the default headline workload also run the other BASELINE configurations (C1, C2-FP32, C3, C4, C5) "
+                                                      "and report them in the line's `configs` object; 'none'; or a comma list of their keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -258,16 +533,13 @@ def main():
     N = args.instances or n_default
     unit = "systems" if kind == "coupled" else "instances"
     metric = "system-steps/sec (%s %s)" % ("FP64" if args.precision == "f64" else "FP32", alg)
-    config = {"workload": f"{args.workload}: {N} {unit} per GPU x {world} GPU(s), {args.phases} integration phase(s) per step (BASELINE {cfg_name})",
-              f"{unit}_per_gpu": N, "phases_per_step": args.phases,
-              "sharding": "tile-cyclic, no collective on the data path",
-              "l2": "flushed between timed iterations (a 256 MiB buffer is overwritten on the solver's stream, outside the summed event brackets); state is restored device-to-device from a snapshot before every step; the kernel is bound by instruction issue (an FP64 instruction takes two issue slots), its HBM traffic takes < 1% of its time (profiles/traffic.json), so cache residency between steps does not enter the timing",
-              "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
 
     # ------------------------------------------------------------------ reference arm (CPU) ------
     if args.impl == "reference":
         if rank != 0:
             return
+        config = {"workload": f"{args.workload}: {N} {unit} per GPU x {world} GPU(s), {args.phases} integration phase(s) per step (BASELINE {cfg_name})",
+                  f"{unit}_per_gpu": N, "phases_per_step": args.phases, "flops_per_system_step": flops_per_step, "flops_convention": FLOPS_NOTE}
         threads = os.cpu_count() or 1
         sample = args.cpu_sample or {"coupled": 256, "kellermiksis": 1 << 14, "kellermiksis_dense": 1 << 14, "duffing": 10000}.get(args.workload, 1 << 16)
         sample = min(sample, N)
@@ -297,189 +569,28 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    out = measure(pkg, args, args.workload, args.precision, N, args.phases, args.steps, args.warmup, rank, local_rank, world, full=True)
 
-    wl = build_workload(pkg, args.workload, args.precision, N, rank, world)
-    arm = Arm(pkg, wl, kind, local_rank, args)
-    ps = arm.ps
-    ps.SaveState()
-    stream = torch.cuda.ExternalStream(ps.stream, device=local_rank)
-
-    for _ in range(args.warmup):
-        ps.RestoreState()
-        for _ in range(args.phases):
-            ps.Solve()
-    ps.SynchroniseDevice()
-    ps.ResetStepCounters()
-
-    # ---- value: device-resident ---------------------------------------------------------------
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
-    ev_step = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    # L2 (126 MB) is flushed between timed iterations by overwriting a 256 MiB buffer on the solver's stream; the flush itself is
-    # outside the event brackets that are summed into the step time
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
-    sampler = ClockSampler(local_rank)
-    time.sleep(0.25)
-    barrier(); torch.cuda.synchronize()
-    t_host0 = time.time()
-    ev[0].record(stream)
-    for k in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(k & 0xff)
-        ev_step[k].record(stream)
-        ps.RestoreState()
-        ev[2 + 2 * k].record(stream)
-        for _ in range(args.phases):
-            ps.Solve()
-        ev[3 + 2 * k].record(stream)
-    ev[1].record(stream)
-    torch.cuda.synchronize(); barrier()
-    t_host1 = time.time()
-    clocks = sampler.stop(t_host0, t_host1)
-    region_ms = sum(ev_step[k].elapsed_time(ev[3 + 2 * k]) for k in range(args.steps))      # K x (restore + phases), flushes excluded
-    kernel_ms = [ev[2 + 2 * k].elapsed_time(ev[3 + 2 * k]) / args.phases for k in range(args.steps)]
-    attempted, accepted = arm.total_steps()
-    dense_samples = None
-    if kind == "perthread" and wl.shape.NDO > 0:
-        # points stored by the last phase (the built-in dense systems restart the index every phase) x phases per step
-        ps.SynchroniseFromDeviceToHost(arm.V.DenseIndex)
-        ps.SynchroniseDevice()
-        dense_samples = int(np.minimum(ps.host(arm.V.DenseIndex), wl.shape.NDO).sum()) * args.phases
-
-    # ---- e2e: host buffers through the public API, double-buffered over `chunks` solver objects ----
-    chunks = max(1, args.e2e_chunks)
-    while N % chunks or (kind == "perthread" and N // chunks < 1):
-        chunks -= 1
-    if chunks == 1:
-        e2e_arms = [arm]
-    else:
-        import copy
-        sharding = importlib.import_module(pkg.__name__ + ".sharding")
-        e2e_arms = []
-        for c in range(chunks):
-            w = copy.copy(wl)
-            w.buffers = wl.buffers.take(sharding.shard_indices(N // chunks, c, chunks, 1))
-            e2e_arms.append(Arm(pkg, w, kind, local_rank, args))
-    h2d = d2h = 0
-    for a in e2e_arms:
-        hi, do = a.make_host_buffers(torch)
-        h2d += hi
-        d2h += do
-
-    def step_e2e():
-        # T7's loop: wait for a solver object (its previous sweep is then in the caller's arrays), refill it and launch it again,
-        # while the other objects compute -- so the copies of one step also overlap the kernels of its neighbours
-        for a in e2e_arms:
-            a.finish_e2e()
-            a.enqueue_e2e(args.phases)
-
-    def drain_e2e():
-        for a in e2e_arms:
-            a.finish_e2e()
-
-    for _ in range(2):
-        step_e2e()
-    drain_e2e()
-    for a in e2e_arms:
-        a.ps.ResetStepCounters()
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    drain_e2e()
-    torch.cuda.synchronize(); barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_attempted = sum(a.total_steps()[0] for a in e2e_arms)
-    final_state_checksum = float(sum(a.user_out[a.V.ActualState].double().sum() for a in e2e_arms))
-
-    # ---- reduce over ranks -------------------------------------------------------------------------
-    sharding = importlib.import_module(pkg.__name__ + ".sharding")
-    (region_ms, e2e_s, kmean), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms))],
-                                                                   [attempted, accepted, e2e_attempted], device="cuda")
-    attempted, accepted, e2e_attempted = [int(x) for x in counts]
-
+    # ---- the other BASELINE configurations, after the headline (whose timing they cannot disturb) ----
+    default_headline = (args.workload == "lorenz" and args.precision == "f64" and not args.instances and args.phases == 1
+                        and args.lane_refill < 0 and not args.threads_per_block)
+    wanted = [] if args.configs == "none" else ([c for c in EXTRA_CONFIGS] if args.configs == "auto" else [c for c in EXTRA_CONFIGS if c[0] in args.configs.split(",")])
+    if args.configs == "auto" and not default_headline:
+        wanted = []
+    configs = {}
+    for key, wname, prec, phases in wanted:
+        try:
+            r = measure(pkg, args, wname, prec, WORKLOADS[wname][2], phases, min(args.steps, 5), 3, rank, local_rank, world, full=False)
+        except Exception as e:      # an extra configuration must never break the headline line
+            r = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if world > 1:
+                raise
+        if rank == 0 and r is not None:
+            configs[key] = r
     if rank == 0:
-        value = attempted / (region_ms * 1e-3)
-        precision_bytes = 8 if args.precision == "f64" else 4
-        peak_tf = pkg.probe_fma_peak(local_rank, precision_bytes)
-        per_rank_attempted_per_launch = attempted / world / args.steps / args.phases
-        achieved_tf = per_rank_attempted_per_launch * flops_per_step / (kmean * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"{args.workload}_{args.precision}")
-        # solver kernels of the timed region, plus the three ordering kernels in front of every phase that has a cost history
-        # (second and later phases of a step; per-thread module: only launches of more than 16 blocks per SM, coupled module: queues
-        # longer than two rounds of slots, and there the first phase too: pilot slice + ordered continuation)
-        tpb = (args.threads_per_block or getattr(wl.options, "ThreadsPerBlock", None) or 128) if kind == "perthread" else 1
-        tiles = (N + tpb - 1) // tpb
-        ordered = (tiles > 16 * 148) if kind == "perthread" else (N > 2 * 148 * 8)
-        if kind == "coupled":      # every phase is cost-ordered (3 kernels); the first one of a step after a pilot slice (one more solver launch)
-            ordering_kernels = (3 * args.phases + 1) if ordered else 0
-        else:
-            ordering_kernels = 3 * (args.phases - 1) if (ordered and args.lane_refill <= 0) else 0
-        out = {"metric": metric, "value": value, "unit": "system-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": region_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": args.precision, "data": "synthetic", "config": config,
-               "accepted_steps_per_s": accepted / (region_ms * 1e-3),
-               "system_steps_per_step": attempted / args.steps,
-               "roofline": {"bound": "fp64_fma" if precision_bytes == 8 else "fp32_fma", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                            "frac": achieved_tf / peak_tf, "traffic": traffic,
-                            "peak_source": "measured on this GPU by mpgos_probe_fma_peak (register-resident FMA chains, CUDA events); MEASURED_PEAKS.json carries no FP64/FP32 FMA figure",
-                            "kernel_ms": kmean, "algorithmic_flops_per_launch": per_rank_attempted_per_launch * flops_per_step},
-               "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e2e_s / args.steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
-               "gpu_launches": args.steps * (args.phases + ordering_kernels), "clocks": clocks}
-        if dense_samples is not None:
-            # the only HBM stream that matters on this path: (SD + 1) words per stored point (24 B for Keller-Miksis)
-            bytes_per_sample = (wl.shape.SD + 1) * precision_bytes
-            hbm_peak = None
-            mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
-            if os.path.exists(mp):
-                hbm_peak = json.load(open(mp)).get("hbm_gbs")
-            gbs = dense_samples * bytes_per_sample / (kmean * args.phases * 1e-3) / 1e9
-            out["dense_output"] = {"stored_points_per_step_per_gpu": dense_samples, "bytes_per_point": bytes_per_sample, "achieved_gbs": gbs,
-                                   "hbm_peak_gbs": hbm_peak, "frac": (gbs / hbm_peak) if hbm_peak else None,
-                                   "note": "rank 0; algorithmic bytes of the dense-output stream over the kernel time -- the kernel is issue-bound (FP64), the stream is far from the HBM roof"}
-        if world == 1 and not args.no_reference_gpu:
-            # reported baseline, not a target: the reference MPGOS compiled for sm_100a, same inputs, same event bracket
-            try:
-                sys.path.insert(0, os.path.join(ROOT, "oracle"))
-                import oracle_py
-                ref_ms = None
-                if kind == "coupled":
-                    tag = "bubble_ensemble_u64_s2"
-                    if N == 8192 and args.precision == "f64" and os.path.exists(oracle_py.coupled_ref_library_path(tag, gpu=True)):
-                        with quiet_stdout():
-                            _, ref_ms = oracle_py.run_coupled_ref_gpu(tag, wl, phases=args.phases, shared_matrices=1, repeats=3)
-                        what = "reference MPGOS CoupledSystems_PerBlock kernel (TPB 128, SPB 2, SharedCouplingMatrices 1: its fastest setting here) compiled unmodified by nvcc for sm_100a"
-                elif oracle_py.ref_gpu_available(wl):
-                    with quiet_stdout():
-                        _, ref_ms = oracle_py.run_ref_gpu(wl, phases=args.phases, threads_per_block=64, repeats=3)
-                    what = "reference MPGOS SingleSystem_PerThread kernel compiled unmodified by nvcc for sm_100a, 64 threads/block"
-                if ref_ms is not None:
-                    ref_ms /= args.phases
-                    out["reference_gpu"] = {"kernel_ms": ref_ms, "value": per_rank_attempted_per_launch / (ref_ms * 1e-3), "unit": "system-steps/s",
-                                            "speedup_kernel": ref_ms / kmean,
-                                            "what": what + " (oracle/_ref), best of 3, same inputs; step count taken from our counters"}
-            except Exception as e:   # the baseline must never break the bench line
-                out["reference_gpu"] = {"unavailable": str(e)[:200]}
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            big = threads >= 16
-            sample = args.cpu_sample or {"coupled": 512 if big else 128, "kellermiksis": 1 << 15, "kellermiksis_dense": 1 << 15,
-                                         "duffing": 10000, "impact": 1 << 17 if big else 1 << 15}.get(args.workload, 1 << 19 if big else 1 << 17)
-            sample = min(sample, N)
-            n, s, kind_cpu, nt = cpu_reference_run(pkg, args.workload, args.precision, sample, threads, args.phases)
-            out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind_cpu,
-                                   "sample": f"every {max(N // nt, 1)}-th {unit[:-1]} of the sweep ({nt} {unit}), {args.phases} phase(s), {threads} host threads, {s:.1f} s"}
+        if wanted:
+            out["configs"] = configs
         print(json.dumps(out))
-    for a in e2e_arms:
-        if a is not arm:
-            a.close()
-    arm.close()
     if world > 1:
         dist.destroy_process_group()
 

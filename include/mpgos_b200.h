@@ -208,6 +208,9 @@ mpgos_perthread_launcher mpgos_perthread_builtin_launcher(const char* system, in
  * micro-benchmark of independent FMA chains timed with CUDA events.  This is the denominator of
  * the roofline the bench reports. */
 int   mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops);
+/* The same for the FP64 tensor-core instruction (mma.sync.m8n8k4.f64, 256 FMAs per warp instruction).  On B200 it has the FP64
+ * pipe's FMA rate, no more; the bench takes the larger of the two probes as the FP64 peak. */
+int   mpgos_probe_dmma_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

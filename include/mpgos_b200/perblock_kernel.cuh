@@ -13,8 +13,9 @@
 //  * every thread evaluates the step-size controller redundantly from the reduced values (no thread-0 serial section,
 //    no broadcast barrier); its pow/division are replaced by the division-free Newton root of perthread_kernel.cuh;
 //  * the coupling matrices live in shared memory once per block, coupling terms are double-buffered (one barrier per
-//    stage instead of two), the column sum runs in ascending order with a single accumulator exactly like
-//    ComputeCouplingValue_* (Steppers.cuh:2551-2713), so results track the reference to rounding;
+//    stage instead of two); the column sum of a dense matrix runs over MPGOS_B200_COUPLING_ACCUMULATORS (default 4)
+//    interleaved partial sums -- same terms as ComputeCouplingValue_* (Steppers.cuh:2551-2713), different summation order,
+//    results track the reference to rounding; 1 accumulator reproduces the reference's ascending single chain bit for bit;
 //  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid);
 //  * TENSOR-CORE COUPLING (MMA variant; dense matrices shared by all systems, FP64, UPS = 32, 64 or 128): the column sums of the
 //    8 systems of a block (4 for UPS = 128) are ONE matrix product  V[UPS x 8] = M[UPS x UPS] . CPT[UPS x 8]  per stage, issued as
@@ -610,7 +611,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			// every thread evaluates the controller (ErrorControllers.cuh:504-539) from the reduced values
 			const bool at_minimum = dt < a.MinimumTimeStepGuard;
 			P mult;
-			const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 <= q < 2^30 (and q > 1e-30: the reference's initial 1e30)
+			const unsigned qt = Num<P>::top(q) - Num<P>::kLow;       // 2^-100 (7.9e-31) <= q < 2^30; below that the exact path applies the reference's cap rel = min(1e30, 1/q)
 			if (finite && qt < Num<P>::kSpan)
 				mult = P(0.8) * inverse_root_fast<P>(q, update);
 			else if (MMA && !have)

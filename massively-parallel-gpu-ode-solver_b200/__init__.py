@@ -8,7 +8,7 @@ anywhere (so that CPU-only checks can inspect the library's symbols), but creati
 without a CUDA device raises.
 """
 from .solver import (ProblemSolver, MpgosError, load_library, library_path, build_library,
-                     Variables, Options, Algorithms, run_workload, ABI_SYMBOLS, probe_fma_peak,
+                     Variables, Options, Algorithms, run_workload, ABI_SYMBOLS, probe_fma_peak, probe_dmma_peak,
                      apply_workload, read_back)
 from . import workloads
 from . import workloads_coupled
@@ -16,4 +16,4 @@ from .solver_coupled import (CoupledProblemSolver, CoupledVariables, CoupledOpti
                              apply_coupled_workload, read_back_coupled)
 
 __all__ = ["ProblemSolver", "MpgosError", "load_library", "library_path", "build_library", "Variables",
-           "Options", "Algorithms", "run_workload", "workloads", "ABI_SYMBOLS", "probe_fma_peak", "apply_workload", "read_back"]
+           "Options", "Algorithms", "run_workload", "workloads", "ABI_SYMBOLS", "probe_fma_peak", "probe_dmma_peak", "apply_workload", "read_back"]

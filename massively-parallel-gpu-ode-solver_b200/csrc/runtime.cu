@@ -73,22 +73,78 @@ __global__ void reduce_step_counters(const unsigned long long* __restrict__ atte
 	if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], a); atomicAdd(&out[1], b); }
 }
 
-// independent FMA chains held in registers; 16 chains x 2 flops x iters per thread
+// Peak probes (the roofline denominators).  Independent FMA chains held in registers: 16 chains x 16 unrolled trips = 256
+// FMAs per loop trip, so that the loop's own counter/branch instructions (which cost issue slots the FP64 pipe cannot hide:
+// an FP64 instruction takes two issue cycles per sub-partition and other instructions do not overlap with it) are < 1 % of
+// the stream.  Round 1's probe had 16 FMAs per trip and read 33.7 TFLOP/s, 9 % below the issue rate the cycle-accurate
+// micro-benchmark proves (one DFMA per 2.00 cycles per sub-partition = 37.2 TFLOP/s at 1965 MHz, tools/microbench_fp64.cu).
 template <class P>
-__global__ void fma_peak_kernel(P* out, int iters, P a, P b)
+__global__ void __launch_bounds__(256) fma_peak_kernel(P* out, int trips, P a, P b)
 {
 	P x[16];
 	#pragma unroll
 	for (int i = 0; i < 16; i++) x[i] = (P)(threadIdx.x + i);
-	for (int it = 0; it < iters; it++)
+	for (int it = 0; it < trips; it++)
 	{
 		#pragma unroll
-		for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+		for (int u = 0; u < 16; u++)
+		{
+			#pragma unroll
+			for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+		}
 	}
 	P s = 0;
 	#pragma unroll
 	for (int i = 0; i < 16; i++) s += x[i];
 	if (s == (P)123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
+// FP64 tensor-core instruction (mma.sync.m8n8k4.f64, DMMA): 256 FMAs per warp instruction, 4 accumulator pairs in flight
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int trips)
+{
+	double c0[4], c1[4];
+	const double a = threadIdx.x * 1e-3, b = 1.0 - threadIdx.x * 1e-4;
+	#pragma unroll
+	for (int i = 0; i < 4; i++) { c0[i] = i; c1[i] = -i; }
+	for (int it = 0; it < trips; it++)
+	{
+		#pragma unroll
+		for (int u = 0; u < 16; u++)
+		{
+			#pragma unroll
+			for (int i = 0; i < 4; i++)
+				asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+		}
+	}
+	double s = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; i++) s += c0[i] + c1[i];
+	if (s == 123.456) out[0] = s;
+}
+
+// Times `launch(trips)` (best of 5 after one warm-up launch, CUDA events; each launch lasts ~10 ms so that the clocks are at
+// their load level and launch overhead is < 0.1 %) and returns flops / second / 1e12.
+template <class Launch>
+int time_probe(Launch launch, double flops_per_trip_total, int trips, double* tflops)
+{
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0));  CUDA_TRY(cudaEventCreate(&e1));
+	double best = 0;
+	for (int rep = 0; rep < 6; rep++)
+	{
+		CUDA_TRY(cudaEventRecord(e0));
+		launch(trips);
+		CUDA_TRY(cudaEventRecord(e1));
+		CUDA_TRY(cudaEventSynchronize(e1));
+		CUDA_TRY(cudaGetLastError());
+		float ms = 0;
+		CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+		const double tf = flops_per_trip_total * trips / (ms * 1e-3) / 1e12;
+		if (rep > 0 && tf > best) best = tf;
+	}
+	cudaEventDestroy(e0);  cudaEventDestroy(e1);
+	*tflops = best;
+	return MPGOS_OK;
 }
 
 template <class P>
@@ -99,24 +155,27 @@ int probe_fma_peak(double* tflops)
 	cudaDeviceProp prop;  int dev = 0;
 	CUDA_TRY(cudaGetDevice(&dev));
 	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
-	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
-	cudaEvent_t e0, e1;
-	CUDA_TRY(cudaEventCreate(&e0));  CUDA_TRY(cudaEventCreate(&e1));
-	double best = 0;
-	for (int rep = 0; rep < 6; rep++)
-	{
-		CUDA_TRY(cudaEventRecord(e0));
-		fma_peak_kernel<P><<<blocks, threads>>>(d, iters, (P)0.999999, (P)1e-7);
-		CUDA_TRY(cudaEventRecord(e1));
-		CUDA_TRY(cudaEventSynchronize(e1));
-		float ms = 0;
-		CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-		const double tf = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
-		if (rep > 0 && tf > best) best = tf;
-	}
-	cudaEventDestroy(e0);  cudaEventDestroy(e1);  cudaFree(d);
-	*tflops = best;
-	return MPGOS_OK;
+	const int blocks = prop.multiProcessorCount * 8, threads = 256;
+	const int trips = sizeof(P) == 8 ? 1536 : 3072;          // ~10 ms per launch
+	const int rc = time_probe([&](int n) { fma_peak_kernel<P><<<blocks, threads>>>(d, n, (P)0.999999, (P)1e-7); },
+	                          2.0 * 256.0 * (double)blocks * threads, trips, tflops);
+	cudaFree(d);
+	return rc;
+}
+
+int probe_dmma_peak(double* tflops)
+{
+	double* d = nullptr;
+	CUDA_TRY(cudaMalloc(&d, sizeof(double)));
+	cudaDeviceProp prop;  int dev = 0;
+	CUDA_TRY(cudaGetDevice(&dev));
+	CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256;
+	// one DMMA = 8 x 8 x 4 FMAs per warp; 64 DMMAs per trip and warp
+	const int rc = time_probe([&](int n) { dmma_peak_kernel<<<blocks, threads>>>(d, n); },
+	                          2.0 * 256.0 * 64.0 * (double)blocks * (threads / 32), 768, tflops);
+	cudaFree(d);
+	return rc;
 }
 
 } // namespace
@@ -574,6 +633,13 @@ int mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops)
 	return precision_bytes == 8 ? probe_fma_peak<double>(tflops) : probe_fma_peak<float>(tflops);
 }
 
+int mpgos_probe_dmma_peak(int device, double* tflops)
+{
+	if (!tflops) return fail(MPGOS_ERR_ARGUMENT, "probe_dmma_peak: bad argument");
+	CUDA_TRY(cudaSetDevice(device));
+	return probe_dmma_peak(tflops);
+}
+
 // ---- built-in systems -------------------------------------------------------------------------
 
 static void collect(std::vector<mpgos_b200::BuiltinEntry>& all)
@@ -588,9 +654,8 @@ static void collect(std::vector<mpgos_b200::BuiltinEntry>& all)
 
 static const std::vector<mpgos_b200::BuiltinEntry>& entries()
 {
-	static std::vector<mpgos_b200::BuiltinEntry> all;
-	static bool done = false;
-	if (!done) { collect(all); done = true; }
+	// function-local static with an initialiser: constructed once, thread-safe (C++11)
+	static const std::vector<mpgos_b200::BuiltinEntry> all = [] { std::vector<mpgos_b200::BuiltinEntry> v; collect(v); return v; }();
 	return all;
 }
 

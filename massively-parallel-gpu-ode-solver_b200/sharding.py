@@ -20,7 +20,10 @@ TILE = 4096
 
 
 def shard_indices(instances_per_rank: int, rank: int, world: int, tile: int = TILE) -> np.ndarray:
-    """Global instance ids owned by ``rank``: tiles of ``tile`` consecutive instances dealt round-robin."""
+    """Global instance ids owned by ``rank``: tiles of ``tile`` consecutive instances dealt round-robin.
+    Every rank owns whole tiles: ``instances_per_rank`` must be a multiple of ``tile`` (callers fall back to tile = 1)."""
+    if instances_per_rank % tile != 0:
+        raise ValueError(f"shard_indices: {instances_per_rank} instances per rank is not a multiple of the tile ({tile})")
     i = np.arange(instances_per_rank, dtype=np.int64)
     return (i // tile) * (world * tile) + rank * tile + (i % tile)
 

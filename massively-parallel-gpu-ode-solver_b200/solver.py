@@ -80,7 +80,7 @@ ABI_SYMBOLS = (
     "mpgos_perthread_stream", "mpgos_perthread_device", "mpgos_perthread_device_ptr", "mpgos_perthread_solve_timed",
     "mpgos_perthread_builtin_count", "mpgos_perthread_builtin_name", "mpgos_perthread_builtin_desc",
     "mpgos_perthread_builtin_launcher", "mpgos_probe_fma_peak", "mpgos_perthread_save_state", "mpgos_perthread_restore_state",
-    "mpgos_perthread_upload", "mpgos_perthread_download",
+    "mpgos_perthread_upload", "mpgos_perthread_download", "mpgos_probe_dmma_peak",
 )
 
 
@@ -146,6 +146,7 @@ def load_library(strict: bool = False):
     lib.mpgos_perthread_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.mpgos_perthread_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.mpgos_probe_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.mpgos_probe_dmma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _LIBS[strict] = lib
     return lib
 
@@ -155,6 +156,14 @@ def probe_fma_peak(device: int = 0, precision_bytes: int = 8) -> float:
     lib = load_library()
     v = C.c_double()
     _check(lib, lib.mpgos_probe_fma_peak(device, precision_bytes, C.byref(v)))
+    return v.value
+
+
+def probe_dmma_peak(device: int = 0) -> float:
+    """Measured throughput of the FP64 tensor-core instruction (mma.sync.m8n8k4.f64) in TFLOP/s."""
+    lib = load_library()
+    v = C.c_double()
+    _check(lib, lib.mpgos_probe_dmma_peak(device, C.byref(v)))
     return v.value
 
 

@@ -140,22 +140,23 @@ def run_oracle(wl, buffers=None, phases: Optional[int] = None, host_threads: int
 
 # ---- the reference compiled by nvcc for sm_100a (oracle/_ref/libref_gpu_*.so) -------------------------
 
-def ref_gpu_library_path(wl) -> str:
+def ref_gpu_library_path(wl, variant: str = "") -> str:
+    """variant "": compiled without a register cap; "stock": with the -maxrregcount of the reference's own tutorial makefile."""
     algo = {0: "rk4", 1: "rkck45"}[wl.shape.Algorithm]
-    return os.path.join(HERE, "_ref", f"libref_gpu_{wl.name}_{algo}_{_prec_tag(wl.shape.dtype)}.so")
+    return os.path.join(HERE, "_ref", f"libref_gpu_{wl.name}_{algo}_{_prec_tag(wl.shape.dtype)}{'_' + variant if variant else ''}.so")
 
 
-def ref_gpu_available(wl) -> bool:
-    return os.path.exists(ref_gpu_library_path(wl))
+def ref_gpu_available(wl, variant: str = "") -> bool:
+    return os.path.exists(ref_gpu_library_path(wl, variant))
 
 
 _REFGPU = {}
 
 
-def run_ref_gpu(wl, buffers=None, phases: Optional[int] = None, threads_per_block: int = 64, repeats: int = 1):
+def run_ref_gpu(wl, buffers=None, phases: Optional[int] = None, threads_per_block: int = 64, repeats: int = 1, variant: str = ""):
     """Run the REFERENCE MPGOS kernel on the GPU; returns (buffers_after, kernel_ms) -- kernel_ms is the best
     device time of the Solve() calls of one run over `repeats` runs (CUDA events, copies excluded)."""
-    path = ref_gpu_library_path(wl)
+    path = ref_gpu_library_path(wl, variant)
     lib = _REFGPU.get(path)
     if lib is None:
         lib = _REFGPU[path] = C.CDLL(path)

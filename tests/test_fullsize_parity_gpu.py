@@ -1,0 +1,119 @@
+"""Parity at the sizes and sweeps the bench actually runs (BASELINE.json configs at full size).
+
+Each test launches the FULL configuration once through the public API -- the same workload object bench.py builds -- and then
+compares a strided sample of its instances (first and last included) with the CPU checker run on exactly those instances:
+instances (systems) are independent, so the checker on the sample is the checker on the launch.  This pins the regions of the
+sweeps the small parity cases never visit (Lorenz near rho = 21, the impact oscillator at large q, Keller-Miksis at 20 kHz,
+and the coupled bubbles driven at up to 5 bar, where collapses are violent and the controller's exact-pow fallback and the
+forced minimum step are most likely to be reached).
+
+Tolerances (stated per north_star): adaptive RKCK45 endpoints relative 1e-6 (Lorenz, Keller-Miksis), 1e-5 (impact, event-terminated),
+1e-7 (coupled bubbles); step counts identical on the fraction of instances written at each assert, the rest within a few steps
+(GPU and CPU differ by FMA contraction, CUDA-vs-glibc libm and the Newton root of the controller, i.e. O(1e-16) per step, which
+flips an accept/reject decision only when err and tol agree to ~1e-15)."""
+import copy
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1.0)
+
+
+def strided(n_total, n_sample):
+    return np.unique(np.linspace(0, n_total - 1, n_sample).round().astype(np.int64))
+
+
+def sample_of(wl, idx):
+    sub = copy.copy(wl)
+    sub.buffers = wl.buffers.take(idx)
+    return sub
+
+
+def report(name, **kw):
+    print(f"[fullsize {name}] " + "  ".join(f"{k}={v}" for k, v in kw.items()))
+
+
+def test_c2_lorenz_full_launch_strided_sample_against_checker(pkg, workloads, oracle):
+    """C2: 2^20 instances, rho = linspace(0, 21), RKCK45 1e-8 (bench.py's default workload); 512 strided instances."""
+    wl = workloads.lorenz(NT=1 << 20, algorithm=workloads.RKCK45)
+    out, att, acc = pkg.run_workload(wl, phases=1)
+    idx = strided(wl.NT, 512)
+    ref, ratt, racc = oracle.run_oracle(sample_of(wl, idx), phases=1, host_threads=8)
+    err = rel_err(out.ActualState[:, idx], ref.ActualState)
+    same = (att[idx] == ratt).mean()
+    report("C2", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()))
+    assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
+    assert err.max() < 1e-6
+    assert same >= 0.95 and np.abs(att[idx] - ratt).max() <= 3
+    assert (acc[idx] == racc).mean() >= 0.95 and np.abs(acc[idx] - racc).max() <= 3
+
+
+def test_c3_impact_full_launch_strided_sample_against_checker(pkg, workloads, oracle):
+    """C3: 2^20 instances, q = linspace(0.2, 10), 8 phases (as benched), events + impact law + user termination; 384 strided instances.
+    Event counters (IntegerAccessories) must be identical on every instance."""
+    wl = workloads.impact_t6(NT=1 << 20)
+    out, att, acc = pkg.run_workload(wl, phases=8)
+    idx = strided(wl.NT, 384)
+    ref, ratt, racc = oracle.run_oracle(sample_of(wl, idx), phases=8, host_threads=8)
+    err = rel_err(out.ActualState[:, idx], ref.ActualState)
+    same = (att[idx] == ratt).mean()
+    report("C3", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()),
+           time_err=f"{rel_err(out.ActualTime[idx], ref.ActualTime).max():.2e}")
+    assert np.array_equal(out.IntegerAccessories[:, idx], ref.IntegerAccessories)
+    assert err.max() < 1e-5
+    assert rel_err(out.ActualTime[idx], ref.ActualTime).max() < 1e-6
+    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-5
+    assert same >= 0.80 and np.abs(att[idx] - ratt).max() <= 12
+
+
+def test_c4_kellermiksis_dense_full_launch_strided_sample_against_checker(pkg, workloads, oracle):
+    """C4: 2^18 instances, f = logspace(20, 1000) kHz, dense output of 200 points, 2 phases (as benched); 256 strided instances,
+    every stored dense-output point of the instances whose index agrees."""
+    wl = workloads.keller_miksis_t5(NT=1 << 18, ndo=200)
+    out, att, acc = pkg.run_workload(wl, phases=2)
+    idx = strided(wl.NT, 256)
+    ref, ratt, racc = oracle.run_oracle(sample_of(wl, idx), phases=2, host_threads=8)
+    err = rel_err(out.ActualState[:, idx], ref.ActualState)
+    same = (att[idx] == ratt).mean()
+    same_di = out.DenseIndex[idx] == ref.DenseIndex
+    report("C4", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()),
+           same_dense_index=f"{same_di.mean():.4f}")
+    assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
+    assert err.max() < 1e-6
+    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-6
+    assert same >= 0.90 and np.abs(att[idx] - ratt).max() <= 8
+    assert same_di.mean() >= 0.90
+    n = int(ref.DenseIndex.min())
+    cols = np.where(same_di)[0]
+    assert rel_err(out.DenseTime[:n][:, idx[cols]], ref.DenseTime[:n][:, cols]).max() < 1e-5
+    assert rel_err(out.DenseState[:n][:, :, idx[cols]], ref.DenseState[:n][:, :, cols]).max() < 1e-4
+
+
+@pytest.mark.parametrize("path", ["tensor_core", "scalar", "pilot_slice_forced"])
+def test_c5_bench_sweep_0_to_5_bar_strided_sample_against_checker(path, pkg, oracle):
+    """C5 exactly as bench.py runs it: bubble_ensemble(NS=8192, UPS=64), pressure amplitude linspace(0, 5) bar -- through the FP64
+    tensor-core (DMMA) coupling with the default pilot slice + cost-ordered continuation, through the scalar coupling, and with the
+    pilot-slice mechanism forced (DispatchOrder = 2).  48 strided systems including the last one (5 bar, the most violent collapse)
+    against the CPU checker.  Tolerance: endpoints 1e-7 relative, step counts within 1 on every system (the matrix product sums in
+    a different order than the reference's single accumulator)."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.bubble_ensemble(NS=8192, UPS=64)
+    kw = {"tensor_core": dict(tensor_core_coupling=1), "scalar": dict(tensor_core_coupling=0),
+          "pilot_slice_forced": dict(tensor_core_coupling=1, dispatch_order=2)}[path]
+    out, att, acc = pkg.run_coupled_workload(wl, phases=1, **kw)
+    idx = strided(8192, 48)
+    assert idx[-1] == 8191
+    ref, ratt, racc = oracle.run_coupled_oracle(sample_of(wl, idx), phases=1, host_threads=8)
+    err = rel_err(out.ActualState[:, idx, :], ref.ActualState)
+    report(f"C5/{path}", systems=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{(att[idx] == ratt).mean():.4f}",
+           max_step_diff=int(np.abs(att[idx] - ratt).max()), steps_last=int(att[-1]), steps_first=int(att[0]))
+    assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
+    assert np.isfinite(out.ActualState).all()
+    assert err.max() < 1e-7
+    assert np.abs(att[idx] - ratt).max() <= 1 and np.abs(acc[idx] - racc).max() <= 1
+    assert (att[idx] == ratt).mean() >= 0.9
