@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MPGOS_B200_ABI_VERSION 2
+#define MPGOS_B200_ABI_VERSION 3
 
 typedef enum mpgos_status
 {
@@ -98,6 +98,8 @@ typedef struct mpgos_perthread_launch
 	mpgos_perthread_desc desc;
 	void*  d_TimeDomain;  void* d_ActualState;  void* d_ActualTime;  void* d_ControlParameters;
 	void*  d_SharedParameters;  int* d_IntegerSharedParameters;
+	const double* SharedParameterValues;          /* host [NSP]: the values of the last host-to-device copy (small sets travel by value) */
+	const int*    IntegerSharedParameterValues;   /* host [NISP] */
 	void*  d_Accessories;  int* d_IntegerAccessories;
 	int*   d_DenseOutputIndex;  void* d_DenseOutputTimeInstances;  void* d_DenseOutputStates;
 	unsigned long long* d_StepsAttempted;   /* [NT] accumulated stepper invocations, never NULL */

@@ -59,11 +59,19 @@ constexpr int kAlgRK4 = 0, kAlgRKCK45 = 1;
 #define MPGOS_B200_NEWTON_F64 1
 #endif
 
+#ifndef MPGOS_B200_ACCEPT_FROM_LIMITING
+#define MPGOS_B200_ACCEPT_FROM_LIMITING 1
+#endif
+
 template <int N> struct AtLeastOne { static constexpr int value = (N > 0 ? N : 1); };
 
 // By-value kernel argument (constant bank).  Role of the reference's Struct_GlobalVariables +
 // Struct_SolverOptions + Struct_ThreadConfiguration (Interface.cuh:72-115).
-template <class P, int SD, int NE>
+// shared parameters travel by value (constant bank -> uniform registers) when there are at most this many of each kind
+constexpr int kSharedByValueLimit = 8;
+__host__ __device__ constexpr int shared_by_value_count(int n, int other) { return (n <= kSharedByValueLimit && other <= kSharedByValueLimit && n > 0) ? n : 1; }
+
+template <class P, int SD, int NE, int NSP = 0, int NISP = 0>
 struct PerThreadArgs
 {
 	P*   TimeDomain;  P* ActualState;  P* ActualTime;  P* ControlParameters;
@@ -83,6 +91,8 @@ struct PerThreadArgs
 	int  DenseOutputSaveFrequency;
 	int  DeviceMessages;
 	int  RefillThreshold;    // LaneRefill: idle lanes per warp that trigger a refill (1..32)
+	int  EventScreen;        // 1: every EventTolerance >= 0, so an event whose value keeps its sign and stays outside the band cannot fire
+	int  SharedInGlobal;     // more shared parameters than fit by value: 0 = staged in dynamic shared memory, 1 = read from global memory
 	P    InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit;
 	P    DenseOutputMinimumTimeStep;
 	P    MinimumTimeStepGuard;    // MinimumTimeStep * 1.01 (ErrorControllers.cuh:63,72), formed once on the host in P
@@ -93,6 +103,11 @@ struct PerThreadArgs
 	P    AbsoluteTolerance[SD];
 	P    EventTolerance[AtLeastOne<NE>::value];
 	int  EventDirection[AtLeastOne<NE>::value];
+	// Shared parameters by value (at most kSharedByValueLimit of each kind; values as of the last host-to-device copy): in the
+	// constant bank they cost neither vector registers nor shared-memory loads -- FP64 instructions take them as uniform-register
+	// operands.  The impact oscillator (4 shared parameters) lost its 68-byte register spill to this.
+	P    SharedValues[shared_by_value_count(NSP, NISP)];
+	int  IntegerSharedValues[shared_by_value_count(NISP, NSP)];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -305,6 +320,85 @@ struct Vec<float, N, true>
 	}
 };
 
+// device-side warnings of the step loop (the reference's texts), out of line: a printf call inside the loop body costs the
+// ordinary step register moves and flag bookkeeping around it even when it never runs
+static __device__ __noinline__ void device_message(int which, int gid)
+{   // [cold>
+	if (which == 0) printf("Error: State is not a finite number. Try to use smaller step size. (thread id: %d)\n", gid);
+	else            printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (thread id: %d)\n", gid);
+}   // <cold]
+
+// ---------------------------------------------------------------------------------------------
+// The cold half of the RKCK45 controller (ErrorControllers.cuh:38-85), out of line: every step that is near a step-size limit, at
+// the minimum step, or whose tolerances / error estimates leave the fast path's operand range (including every NaN / Inf) comes
+// here.  `fast`: the step-size factor of the fast path is valid and only the limits remain; otherwise the exact reference
+// arithmetic (division, pow, isfinite flags) decides everything anew.  Returns bit 0: accept, bit 1: terminate.
+template <class P, int SD>
+struct ControllerCold
+{
+	P x[SD], xn[SD], err[SD];
+	P dt, mult, dt_new;
+	int gid;
+	bool fast, update;
+};
+
+template <class P, int SD, int NE, int NSP, int NISP>
+__device__ __noinline__ int controller_exact(const PerThreadArgs<P, SD, NE, NSP, NISP>* ap, ControllerCold<P, SD>* c)
+{   // [cold>
+	const PerThreadArgs<P, SD, NE, NSP, NISP>& a = *ap;
+	const P dt = c->dt;
+	const int gid = c->gid;
+	P mult = c->mult;
+	bool update = c->update, terminate = false, finite = true;
+	const bool at_minimum = dt < a.MinimumTimeStepGuard;
+	if (c->fast)
+	{
+		if (at_minimum)
+		{
+			if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
+			update = true;
+		}
+	}
+	else
+	{
+		// exact reference arithmetic (division, pow) for exotic operand ranges and non-finite states
+		P rel = P(1e30);
+		update = true;
+		for (int i = 0; i < SD; i++)
+		{
+			finite = finite && Num<P>::finite(c->xn[i]) && Num<P>::finite(c->err[i]);
+			const P tol_i = fmax(a.RelativeTolerance[i] * fmax(fabs(c->xn[i]), fabs(c->x[i])), a.AbsoluteTolerance[i]);
+			update = update && (c->err[i] < tol_i);
+			rel = fmin(rel, tol_i / c->err[i]);
+		}
+		mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+		if (!Num<P>::finite(mult)) finite = false;
+		if (!finite)
+		{
+			mult = a.TimeStepShrinkLimit;
+			update = false;
+			if (at_minimum)
+			{
+				if (a.DeviceMessages) printf("Error: State is not a finite number even with the minimal step size. Try to use less stringent tolerances. (thread id: %d)\n", gid);
+				terminate = true;
+			}
+		}
+		else if (at_minimum)
+		{
+			if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
+			update = true;
+		}
+	}
+	// all operands positive: plain compare-selects instead of fmin/fmax
+	mult = (mult > a.TimeStepGrowLimit) ? a.TimeStepGrowLimit : mult;
+	mult = (mult < a.TimeStepShrinkLimit) ? a.TimeStepShrinkLimit : mult;
+	P dt_new = dt * mult;
+	dt_new = (dt_new > a.MaximumTimeStep) ? a.MaximumTimeStep : dt_new;
+	dt_new = (dt_new < a.MinimumTimeStep) ? a.MinimumTimeStep : dt_new;
+	c->dt_new = dt_new;
+	return (update ? 1 : 0) | (terminate ? 2 : 0);
+}   // <cold]
+
 // ---------------------------------------------------------------------------------------------
 // One instance's registers.
 
@@ -332,33 +426,41 @@ struct LaneState
 
 template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA, int NIA, bool DENSE, int ALG, bool REFILL, int MINB>
 __global__ void __launch_bounds__(launch_bound_threads(MINB), MINB)
-perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
+perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE, NSP, NISP> a)
 {
-	// shared parameters: staged once per block (Solver.cuh:66-88); unlike the reference we
-	// synchronise before the first use.
-	__shared__ P   s_par[AtLeastOne<NSP>::value];
-	__shared__ int s_pari[AtLeastOne<NISP>::value];
-	if (NSP > 0 || NISP > 0)
+	// Shared parameters (Solver.cuh:66-88).  Up to kSharedByValueLimit of each kind arrive by value in the kernel argument and
+	// are copied into a thread-local array: as long as the callbacks only read them the compiler forwards the constant-bank
+	// values (uniform registers), a callback that writes one gets a private copy (in the reference such a write goes to the
+	// block's shared memory, unsynchronised).  Larger sets are staged in dynamic shared memory once per block -- with the
+	// __syncthreads() the reference omits -- or, when they do not fit or PreferSharedMemory = 0, read from global memory.
+	constexpr bool kSharedByValue = (NSP <= kSharedByValueLimit && NISP <= kSharedByValueLimit);
+	P   r_par[kSharedByValue ? AtLeastOne<NSP>::value : 1];
+	int r_pari[kSharedByValue ? AtLeastOne<NISP>::value : 1];
+	P*   p_par  = r_par;
+	int* p_pari = r_pari;
+	if (kSharedByValue)
 	{
+		#pragma unroll
+		for (int i = 0; i < NSP; i++)  r_par[i]  = a.SharedValues[i];
+		#pragma unroll
+		for (int i = 0; i < NISP; i++) r_pari[i] = a.IntegerSharedValues[i];
+	}
+	else if (a.SharedInGlobal)
+	{
+		p_par  = a.SharedParameters;
+		p_pari = a.IntegerSharedParameters;
+	}
+	else
+	{
+		MPGOS_B200_DYNAMIC_SHARED_MEMORY(dyn_smem);
+		P*   s_par  = reinterpret_cast<P*>(dyn_smem);
+		int* s_pari = reinterpret_cast<int*>(s_par + NSP);
 		for (int i = threadIdx.x; i < NSP; i += blockDim.x)  s_par[i]  = a.SharedParameters[i];
 		for (int i = threadIdx.x; i < NISP; i += blockDim.x) s_pari[i] = a.IntegerSharedParameters[i];
 		__syncthreads();
+		p_par  = s_par;
+		p_pari = s_pari;
 	}
-
-	// A handful of shared parameters is copied on into registers: the volatile tableau loads of the step loop keep the
-	// compiler from hoisting shared-memory reads out of it (13 LDS + address arithmetic per step for the impact system).
-	constexpr bool kSharedInRegisters = (NSP <= 8 && NISP <= 8);
-	P   r_par[kSharedInRegisters ? AtLeastOne<NSP>::value : 1];
-	int r_pari[kSharedInRegisters ? AtLeastOne<NISP>::value : 1];
-	if (kSharedInRegisters)
-	{
-		#pragma unroll
-		for (int i = 0; i < NSP; i++)  r_par[i]  = s_par[i];
-		#pragma unroll
-		for (int i = 0; i < NISP; i++) r_pari[i] = s_pari[i];
-	}
-	P*   const p_par  = kSharedInRegisters ? r_par  : s_par;
-	int* const p_pari = kSharedInRegisters ? r_pari : s_pari;
 
 	const int NTG    = a.GlobalInstances;
 	const int stride = a.Stride;
@@ -447,7 +549,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			// ErrorControllers.cuh:6-20: never rejects; a non-finite state ends the phase, committed
 			if (!finite)
 			{
-				if (a.DeviceMessages) printf("Error: State is not a finite number. Try to use smaller step size. (thread id: %d)\n", gid);
+				if (a.DeviceMessages) device_message(0, gid);
 				terminate = true;
 			}
 			s.dt_new = a.InitialTimeStep;
@@ -593,7 +695,6 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			// The selects are ordered so that a NaN/Inf in xn or err reaches tol/err unchanged; the
 			// range test below then routes the step to the exact path, which also sets `finite`.
 			P tol[SD];
-			unsigned outside = 0;      // max over all tol_i, err_i of (top - kLow); >= kSpan means "leave the fast path"
 			#pragma unroll
 			for (int i = 0; i < SD; i++)
 			{
@@ -602,8 +703,6 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				const P m  = (fabs(s.x[i]) > fabs(xn[i])) ? s.x[i] : xn[i];
 				const P t  = a.RelativeTolerance[i] * fabs(m);
 				tol[i] = (a.AbsoluteTolerance[i] > t) ? a.AbsoluteTolerance[i] : t;
-				update = update && (err[i] < tol[i]);
-				outside = max(outside, max(Num<P>::top(tol[i]) - Num<P>::kLow, Num<P>::top(err[i]) - Num<P>::kLow));
 			}
 			// component with the smallest tol/err: tol_a/err_a < tol_b/err_b  <=>  tol_a err_b < tol_b err_a
 			P tsel = tol[0], esel = err[0];
@@ -614,7 +713,28 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				tsel = less ? tol[i] : tsel;
 				esel = less ? err[i] : esel;
 			}
-			const bool fast = (outside < Num<P>::kSpan) &&
+#if MPGOS_B200_ACCEPT_FROM_LIMITING
+			// "every err_i < tol_i" is "the largest err_i/tol_i is below 1": one comparison on the limiting pair instead of one per
+			// component.  The pair is found by cross-multiplication, whose two roundings can misorder components only when their
+			// ratios agree to an ulp; the decision could then differ from the component-wise one only if, in addition, those ratios
+			// straddle 1 within that ulp (err_i == tol_i to the last bit for one of them).  The parity build tests every component.
+			update = esel < tsel;
+#else
+			#pragma unroll
+			for (int i = 0; i < SD; i++) update = update && (err[i] < tol[i]);
+#endif
+			// Operand range of the fast path: every tol_i and err_i positive, finite and in [2^-100, 2^30) (in single precision
+			// [2^-60, 2^30)), tested on the words that hold sign and exponent: the largest of them (as unsigned integers: a negative
+			// number, an infinity or a NaN is larger than any admissible value) and the smallest tolerance (err_i carries the
+			// 1e-18 floor and cannot be small).  3-input integer min/max: 4 instructions for 6 operands.
+			unsigned top_max = 0u, top_min = 0xffffffffu;
+			#pragma unroll
+			for (int i = 0; i < SD; i++)
+			{
+				top_max = max(top_max, max(Num<P>::top(tol[i]), Num<P>::top(err[i])));
+				top_min = min(top_min, Num<P>::top(tol[i]));
+			}
+			const bool fast = (top_max < Num<P>::kLow + Num<P>::kSpan) && (top_min >= Num<P>::kLow) &&
 			                  ((unsigned)((int)(Num<P>::top(tsel) - Num<P>::top(esel)) + Num<P>::kRatioFloor) < (unsigned)(Num<P>::kRatioLimit + Num<P>::kRatioFloor));
 			// ErrorControllers.cuh:60-85 -- forced acceptance at the minimum step, limits on the factor and on the new step.
 			// None of them is active in an ordinary step, and whether one CAN be active is decided in single precision with a
@@ -638,61 +758,37 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 			if (plain)
 				s.dt_new = dt * mult;
 			else
-			{
-				const bool at_minimum = dt < a.MinimumTimeStepGuard;
-				if (fast)
-				{
-					if (at_minimum)
-					{
-						if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
-						update = true;
-					}
-				}
-				else
-				{
-					// exact reference arithmetic (division, pow) for exotic operand ranges and non-finite states
-					P rel = P(1e30);
-					#pragma unroll
-					for (int i = 0; i < SD; i++)
-					{
-						finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
-						rel = fmin(rel, fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(s.x[i])), a.AbsoluteTolerance[i]) / err[i]);
-					}
-					mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
-					if (!Num<P>::finite(mult)) finite = false;
-					if (!finite)
-					{
-						mult = a.TimeStepShrinkLimit;
-						update = false;
-						if (at_minimum)
-						{
-							if (a.DeviceMessages) printf("Error: State is not a finite number even with the minimal step size. Try to use less stringent tolerances. (thread id: %d)\n", gid);
-							terminate = true;
-						}
-					}
-					else if (at_minimum)
-					{
-						if (a.DeviceMessages) printf("Warning: Minimum step size reached! Continue with fixed minimum step size! Tolerance cannot be guaranteed!, thread id: %d, time step: %+6.5e, min step size: %+6.5e \n", gid, (double)dt, (double)a.MinimumTimeStep);
-						update = true;
-					}
-				}
-				// all operands positive: plain compare-selects instead of fmin/fmax
-				mult = (mult > a.TimeStepGrowLimit) ? a.TimeStepGrowLimit : mult;
-				mult = (mult < a.TimeStepShrinkLimit) ? a.TimeStepShrinkLimit : mult;
-				P dt_new = dt * mult;
-				dt_new = (dt_new > a.MaximumTimeStep) ? a.MaximumTimeStep : dt_new;
-				dt_new = (dt_new < a.MinimumTimeStep) ? a.MinimumTimeStep : dt_new;
-				s.dt_new = dt_new;
-			}
+			{   // [cold>
+				// the rest of the controller is cold and lives out of line (controller_exact): the ordinary step neither holds its
+				// temporaries in registers nor keeps the accept / terminate flags out of predicates because of it
+				ControllerCold<P, SD> c;
+				#pragma unroll
+				for (int i = 0; i < SD; i++) { c.x[i] = s.x[i];  c.xn[i] = xn[i];  c.err[i] = err[i]; }
+				c.dt = dt;  c.mult = mult;  c.fast = fast;  c.update = update;  c.gid = gid;
+				const int r = controller_exact<P, SD, NE, NSP, NISP>(&a, &c);
+				s.dt_new = c.dt_new;
+				update = (r & 1) != 0;
+				terminate = (r & 2) != 0;
+			}   // <cold]
 		}
 
 		// ---- events: step-size control (EventHandling.cuh:6-45) ------------------------------
+		// Both scans -- the secant step-size control here and the detection after the commit -- can only fire for an event whose
+		// value changes sign over the step or ends inside the tolerance band (tolerances >= 0, checked on the host:
+		// EventScreen).  That is one integer test and one comparison per event; a lane without such an event skips both scans
+		// (a warp without such a lane jumps over them; the conditions inside are the reference's, unchanged).
 		P evn[AtLeastOne<NE>::value];
+		bool scan = true;
 		if (NE > 0)
 		{
 			Sys::EventFunction(gid, NTG, evn, s.t + dt, dt, s.td, xn, s.cpar, p_par, p_pari, s.acc, s.acci);
-			if (update && !terminate)
-			{
+			bool near = false;
+			#pragma unroll
+			for (int i = 0; i < NE; i++)
+				near = near || ((int)(Num<P>::top(s.ev[i]) ^ Num<P>::top(evn[i])) < 0) || !(fabs(evn[i]) >= a.EventTolerance[i]);
+			scan = (a.EventScreen == 0) || near;
+			if (scan && update && !terminate)
+			{   // [rare>
 				P dt_event = dt;
 				bool corrected = false;
 				#pragma unroll
@@ -710,11 +806,11 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 				{
 					if (dt_event < a.MinimumTimeStep)
 					{
-						if (a.DeviceMessages) printf("Warning: Event cannot be detected without reducing the step size below the minimum! Event detection omitted!, (thread id: %d)\n", gid);
+						if (a.DeviceMessages) device_message(1, gid);
 					}
 					else { s.dt_new = dt_event; update = false; }
 				}
-			}
+			}   // <rare]
 		}
 
 		// ---- accepted step (Solver.cuh:302-392) ------------------------------------------------
@@ -730,14 +826,17 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE> a)
 
 			if (NE > 0)
 			{
-				#pragma unroll
-				for (int i = 0; i < NE; i++)
-				{
-					const P et = a.EventTolerance[i];
-					if (((s.ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) ||
-					    ((s.ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
-						Sys::ActionAfterEventDetection(gid, NTG, i, user_terminate, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
-				}
+				if (scan)
+				{   // [rare>
+					#pragma unroll
+					for (int i = 0; i < NE; i++)
+					{
+						const P et = a.EventTolerance[i];
+						if (((s.ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) ||
+						    ((s.ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
+							Sys::ActionAfterEventDetection(gid, NTG, i, user_terminate, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
+					}
+				}   // <rare]
 				Sys::EventFunction(gid, NTG, s.ev, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 			}
 
@@ -900,9 +999,19 @@ template <class Sys, class P, int SD, int NCP, int NSP, int NISP, int NE, int NA
 struct PerThreadLauncher
 {
 	template <bool REFILL>
-	static cudaError_t enqueue(const mpgos_perthread_launch* L, PerThreadArgs<P, SD, NE>& args, cudaStream_t stream)
+	static cudaError_t enqueue(const mpgos_perthread_launch* L, PerThreadArgs<P, SD, NE, NSP, NISP>& args, cudaStream_t stream)
 	{
 		auto kernel = perthread_kernel<Sys, P, SD, NCP, NSP, NISP, NE, NA, NIA, DENSE, ALG, REFILL, MINB>;
+		// shared parameters that do not travel by value: dynamic shared memory (opt-in above 48 KB), or global memory when they
+		// do not fit next to the launch's other needs or the user asked for it (PreferSharedMemory = 0, as in the reference)
+		constexpr bool kSharedByValue = (NSP <= kSharedByValueLimit && NISP <= kSharedByValueLimit);
+		size_t smem = kSharedByValue ? 0 : sizeof(P) * (size_t)NSP + sizeof(int) * (size_t)NISP;
+		if (smem > 200 * 1024 || (!kSharedByValue && L->PreferSharedMemory == 0)) { smem = 0;  args.SharedInGlobal = 1; }
+		if (smem > 48 * 1024)
+		{
+			cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return e;
+		}
 		int block = L->ThreadsPerBlock;
 		if (block < 32) block = 32;
 		if (block > launch_bound_threads(MINB)) block = launch_bound_threads(MINB);
@@ -914,7 +1023,7 @@ struct PerThreadLauncher
 		{
 			// persistent grid: as many blocks as are resident at once, a multiple of the SM count
 			int per_sm = 0;
-			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
 			if (e != cudaSuccess) return e;
 			if (per_sm < 1) per_sm = 1;
 			const int resident = per_sm * (L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148);
@@ -939,7 +1048,7 @@ struct PerThreadLauncher
 				args.DispatchOrder = L->d_DispatchOrder;
 			}
 		}
-		kernel<<<grid, block, 0, stream>>>(args);
+		kernel<<<grid, block, smem, stream>>>(args);
 		return cudaGetLastError();
 	}
 
@@ -951,7 +1060,7 @@ struct PerThreadLauncher
 		    d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
 			return (int)cudaErrorInvalidValue;
 
-		PerThreadArgs<P, SD, NE> a;
+		PerThreadArgs<P, SD, NE, NSP, NISP> a;
 		a.TimeDomain = (P*)L->d_TimeDomain;  a.ActualState = (P*)L->d_ActualState;  a.ActualTime = (P*)L->d_ActualTime;
 		a.ControlParameters = (P*)L->d_ControlParameters;  a.SharedParameters = (P*)L->d_SharedParameters;
 		a.IntegerSharedParameters = L->d_IntegerSharedParameters;  a.Accessories = (P*)L->d_Accessories;
@@ -981,6 +1090,15 @@ struct PerThreadLauncher
 		{
 			a.EventTolerance[i] = (i < NE) ? (P)L->EventTolerance[i] : P(0);
 			a.EventDirection[i] = (i < NE) ? L->EventDirection[i] : 0;
+		}
+		a.EventScreen = 1;
+		for (int i = 0; i < NE; i++) if (!(a.EventTolerance[i] >= P(0))) a.EventScreen = 0;
+		constexpr bool kSharedByValue = (NSP <= kSharedByValueLimit && NISP <= kSharedByValueLimit);
+		a.SharedValues[0] = P(0);  a.IntegerSharedValues[0] = 0;  a.SharedInGlobal = 0;
+		if (kSharedByValue)
+		{
+			for (int i = 0; i < NSP; i++)  a.SharedValues[i] = (P)L->SharedParameterValues[i];
+			for (int i = 0; i < NISP; i++) a.IntegerSharedValues[i] = L->IntegerSharedParameterValues[i];
 		}
 		return (int)(L->LaneRefill ? enqueue<true>(L, a, stream) : enqueue<false>(L, a, stream));
 	}

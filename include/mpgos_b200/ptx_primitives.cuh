@@ -24,6 +24,11 @@ __device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, un
 __device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b)
 { unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// true if `p` holds on any lane of the warp that executes this call together with the caller.  Used only to decide whether the
+// warp enters a cold region at all (inside it every lane tests its own condition again), so the result may depend on which lanes
+// happen to be converged here without any lane's arithmetic depending on it (the host stand-in simply returns `p`).
+__device__ __forceinline__ bool warp_any(bool p) { return __any_sync(__activemask(), p) != 0; }
+
 // ---- block-per-system kernel (perblock_kernel.cuh) ----------------------------------------------------------------------
 // named barrier over `count` threads (a slot of the block synchronises on its own, never with __syncthreads())
 __device__ __forceinline__ void named_barrier_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }

@@ -209,6 +209,9 @@ struct mpgos_perthread_solver
 	int    DispatchOrder = 1;
 	std::vector<double> rtol, atol, evtol;
 	std::vector<int>    evdir;
+	// shared parameters as of the last host-to-device copy: small sets reach the kernel by value (perthread_kernel.cuh)
+	std::vector<double> shared_values;
+	std::vector<int>    integer_shared_values;
 };
 
 extern "C" {
@@ -264,6 +267,7 @@ int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_sol
 	s->ActiveNumberOfThreads = d.NT;
 	s->rtol.assign(d.SD, 1e-8);  s->atol.assign(d.SD, 1e-8);
 	s->evtol.assign(d.NE > 0 ? d.NE : 1, 1e-6);  s->evdir.assign(d.NE > 0 ? d.NE : 1, 0);
+	s->shared_values.assign(d.NSP > 0 ? d.NSP : 1, 0.0);  s->integer_shared_values.assign(d.NISP > 0 ? d.NISP : 1, 0);
 
 	int rc = MPGOS_OK;
 	auto A = [&](int v, size_t elements, size_t elem) { if (rc == MPGOS_OK) rc = alloc_mirror(s->var[v], elements, elem); };
@@ -423,6 +427,16 @@ int mpgos_perthread_get_option(mpgos_perthread_solver* s, int option, int index,
 	return MPGOS_OK;
 }
 
+// what the device copy of the shared parameters holds once the copy enqueued now has run
+static void shadow_shared(mpgos_perthread_solver* s, int variable, const void* src)
+{
+	if (variable == MPGOS_VAR_SharedParameters)
+		for (int i = 0; i < s->desc.NSP; i++)
+			s->shared_values[i] = s->desc.PrecisionBytes == 8 ? ((const double*)src)[i] : (double)((const float*)src)[i];
+	if (variable == MPGOS_VAR_IntegerSharedParameters)
+		for (int i = 0; i < s->desc.NISP; i++) s->integer_shared_values[i] = ((const int*)src)[i];
+}
+
 static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
@@ -444,7 +458,7 @@ static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device
 	{
 		Mirror& m = s->var[list[i]];
 		if (m.bytes == 0) continue;
-		if (to_device) CUDA_TRY(cudaMemcpyAsync(m.dev, m.host, m.bytes, cudaMemcpyHostToDevice, s->stream));
+		if (to_device) { CUDA_TRY(cudaMemcpyAsync(m.dev, m.host, m.bytes, cudaMemcpyHostToDevice, s->stream));  shadow_shared(s, list[i], m.host); }
 		else           CUDA_TRY(cudaMemcpyAsync(m.host, m.dev, m.bytes, cudaMemcpyDeviceToHost, s->stream));
 	}
 	return MPGOS_OK;
@@ -461,6 +475,7 @@ int mpgos_perthread_upload(mpgos_perthread_solver* s, int variable, const void* 
 	if (bytes == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
+	shadow_shared(s, variable, host_src);
 	s->history_valid = false;
 	return MPGOS_OK;
 }
@@ -483,6 +498,7 @@ static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
 	L.d_ActualTime = s->var[MPGOS_VAR_ActualTime].dev;  L.d_ControlParameters = s->var[MPGOS_VAR_ControlParameters].dev;
 	L.d_SharedParameters = s->var[MPGOS_VAR_SharedParameters].dev;
 	L.d_IntegerSharedParameters = (int*)s->var[MPGOS_VAR_IntegerSharedParameters].dev;
+	L.SharedParameterValues = s->shared_values.data();  L.IntegerSharedParameterValues = s->integer_shared_values.data();
 	L.d_Accessories = s->var[MPGOS_VAR_Accessories].dev;  L.d_IntegerAccessories = (int*)s->var[MPGOS_VAR_IntegerAccessories].dev;
 	L.d_DenseOutputIndex = (int*)s->var[MPGOS_VAR_DenseIndex].dev;
 	L.d_DenseOutputTimeInstances = s->var[MPGOS_VAR_DenseTime].dev;  L.d_DenseOutputStates = s->var[MPGOS_VAR_DenseState].dev;

@@ -146,7 +146,8 @@ def load_library(strict: bool = False):
     lib.mpgos_perthread_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.mpgos_perthread_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     lib.mpgos_probe_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
-    lib.mpgos_probe_dmma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    if hasattr(lib, "mpgos_probe_dmma_peak"):      # absent from A/B builds of older revisions (MPGOS_B200_LIBRARY)
+        lib.mpgos_probe_dmma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _LIBS[strict] = lib
     return lib
 

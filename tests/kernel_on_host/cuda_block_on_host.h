@@ -25,6 +25,9 @@
 #undef __grid_constant__
 #endif
 #define __grid_constant__
+#ifndef __noinline__
+#define __noinline__
+#endif
 #ifdef __shared__
 #undef __shared__
 #endif
@@ -146,6 +149,7 @@ static inline int      min(int a, int b) { return a < b ? a : b; }
 #define MPGOS_B200_PTX_PRIMITIVES_CUH
 #define MPGOS_B200_DYNAMIC_SHARED_MEMORY(name) unsigned char* const name = g_dynamic_shared
 namespace mpgos_b200 {
+static inline bool warp_any(bool p) { return p; }      // a lane's own condition is a valid answer (see ptx_primitives.cuh)
 static inline float sfu_lg2(float x) { return std::log2(x); }
 static inline float sfu_ex2(float x) { return std::exp2(x); }
 static inline float sfu_rcp(float x) { return 1.0f / x; }

@@ -19,6 +19,9 @@
 #undef __grid_constant__
 #endif
 #define __grid_constant__
+#ifndef __noinline__
+#define __noinline__
+#endif
 
 // built-in variables
 struct host_dim3 { unsigned x, y, z; };
@@ -35,6 +38,8 @@ static inline int  __float_as_int(float x) { int b; std::memcpy(&b, &x, 4); retu
 static inline float __double2float_rn(double x) { return (float)x; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int  __any_sync(unsigned, int p) { return p != 0; }
+static unsigned char host_dynamic_shared[1 << 16];
+#define MPGOS_B200_DYNAMIC_SHARED_MEMORY(name) unsigned char* const name = host_dynamic_shared
 static inline int  __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int  __ffs(unsigned v) { return __builtin_ffs((int)v); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
@@ -59,6 +64,7 @@ static inline int      min(int a, int b) { return a < b ? a : b; }
 // calls (more accurate than the hardware's 2^-22; the controller's Newton steps absorb either), the packed FP32 pair two floats.
 #define MPGOS_B200_PTX_PRIMITIVES_CUH
 namespace mpgos_b200 {
+static inline bool warp_any(bool p) { return p; }      // a lane's own condition is a valid answer (see ptx_primitives.cuh)
 static inline float sfu_lg2(float x) { return std::log2(x); }
 static inline float sfu_ex2(float x) { return std::exp2(x); }
 static inline float sfu_rcp(float x) { return 1.0f / x; }

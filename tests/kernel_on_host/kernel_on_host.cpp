@@ -53,7 +53,7 @@ extern "C" int ref_perthread_run(const oracle_perthread_buffers* b, const oracle
 	std::vector<unsigned long long> att(NT, 0), acc(NT, 0);
 	std::vector<unsigned int> last(NT, 0);
 	unsigned int queue = 0;
-	PerThreadArgs<P, SD, NE> a;
+	PerThreadArgs<P, SD, NE, NSP, NISP> a;
 	std::memset(&a, 0, sizeof(a));
 	a.TimeDomain = (P*)b->TimeDomain;  a.ActualState = (P*)b->ActualState;  a.ActualTime = (P*)b->ActualTime;
 	a.ControlParameters = (P*)b->ControlParameters;  a.SharedParameters = (P*)b->SharedParameters;
@@ -74,6 +74,13 @@ extern "C" int ref_perthread_run(const oracle_perthread_buffers* b, const oracle
 	a.MaximumBelow = (float)((double)a.MaximumTimeStep * (1.0 - 1e-4));
 	for (int i = 0; i < SD; i++) { a.RelativeTolerance[i] = ((const P*)b->RelativeTolerance)[i];  a.AbsoluteTolerance[i] = ((const P*)b->AbsoluteTolerance)[i]; }
 	for (int i = 0; i < NE; i++) { a.EventTolerance[i] = ((const P*)b->EventTolerance)[i];  a.EventDirection[i] = b->EventDirection[i]; }
+	a.EventScreen = 1;
+	for (int i = 0; i < NE; i++) if (!(a.EventTolerance[i] >= P(0))) a.EventScreen = 0;
+	if (NSP <= kSharedByValueLimit && NISP <= kSharedByValueLimit)
+	{
+		for (int i = 0; i < NSP; i++)  a.SharedValues[i] = ((const P*)b->SharedParameters)[i];
+		for (int i = 0; i < NISP; i++) a.IntegerSharedValues[i] = b->IntegerSharedParameters[i];
+	}
 
 #ifdef KOH_REFILL
 	// LaneRefill = KOH_REFILL idle lanes per warp trigger a refill; 2 blocks of 64 threads (2 warps each) share the instance queue

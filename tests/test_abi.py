@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/mpgos_b200.h but not exported"
     assert sorted(pkg.ABI_SYMBOLS) == declared
-    assert lib.mpgos_abi_version() == 2
+    assert lib.mpgos_abi_version() == 3
 
 
 def test_library_exports_every_declared_coupled_symbol(pkg):
