@@ -243,16 +243,17 @@ class ProblemSolver
 		}
 	}
 
-public:
-	explicit ProblemSolver(int Device)
+	void Construct(const int* Devices, int DeviceCount, int Tile)
 	{
+		const int Device = Devices[0];
 		mpgos_coupled_desc d;
 		std::memset(&d, 0, sizeof(d));
 		d.NS = NS; d.UPS = UPS; d.UD = UD; d.TPB = TPB; d.SPB = SPB; d.NC = NC; d.CBW = CBW; d.CCI = CCI; d.NUP = NUP; d.NSP = NSP; d.NGP = NGP; d.NiGP = NiGP;
 		d.NUA = NUA; d.NiUA = NiUA; d.NSA = NSA; d.NiSA = NiSA; d.NE = NE; d.NDO = NDO;
 		d.Algorithm = (int)Algorithm; d.PrecisionBytes = (int)sizeof(Precision); d.Device = Device;
 		Handle = nullptr;
-		Check(mpgos_coupled_create(&d, &Handle), "ProblemSolver (constructor)");
+		if (DeviceCount == 1) Check(mpgos_coupled_create(&d, &Handle), "ProblemSolver (constructor)");
+		else                  Check(mpgos_coupled_create_sharded(&d, Devices, DeviceCount, Tile, &Handle), "ProblemSolver (constructor)");
 		h_TimeDomain = Mirror<Precision>(TimeDomain);  h_ActualState = Mirror<Precision>(ActualState);  h_ActualTime = Mirror<Precision>(ActualTime);
 		h_UnitParameters = Mirror<Precision>(UnitParameters);  h_SystemParameters = Mirror<Precision>(SystemParameters);
 		h_GlobalParameters = Mirror<Precision>(GlobalParameters);  h_IntegerGlobalParameters = Mirror<int>(IntegerGlobalParameters);
@@ -260,8 +261,22 @@ public:
 		h_SystemAccessories = Mirror<Precision>(SystemAccessories);  h_IntegerSystemAccessories = Mirror<int>(IntegerSystemAccessories);
 		h_CouplingStrength = Mirror<Precision>(CouplingStrength);  h_CouplingIndex = Mirror<int>(CouplingIndex);
 		h_DenseOutputIndex = Mirror<int>(DenseIndex);  h_DenseOutputTimeInstances = Mirror<Precision>(DenseTime);  h_DenseOutputStates = Mirror<Precision>(DenseState);
-		std::cout << "Object for Parameters scan is successfully created on device " << Device << " (B200-native coupled solver, " << NS << " systems x "
+		std::cout << "Object for Parameters scan is successfully created on device " << Device;
+		for (int i = 1; i < DeviceCount; i++) std::cout << ", " << Devices[i];
+		std::cout << " (B200-native coupled solver, " << NS << " systems x "
 		          << UPS << " units, " << (Algorithm == RK4 ? "RK4" : "RKCK45") << (sizeof(Precision) == 8 ? ", double)" : ", float)") << std::endl << std::endl;
+	}
+
+public:
+	explicit ProblemSolver(int Device) { Construct(&Device, 1, 0); }
+
+	// Addition of this implementation: ONE object over several devices of the node; the NS systems are dealt to them in tiles of
+	// `Tile` systems (0: 64), coupling matrices and global parameters are replicated, the host side is unchanged (one mirror over
+	// all systems), callbacks receive the system's id in the whole sweep.  A single system is never split.
+	explicit ProblemSolver(const std::vector<int>& Devices, int Tile = 0)
+	{
+		if (Devices.empty()) { std::cerr << "ERROR: In solver member function ProblemSolver (constructor)!" << std::endl << "       empty device list" << std::endl; exit(EXIT_FAILURE); }
+		Construct(Devices.data(), (int)Devices.size(), Tile);
 	}
 
 	~ProblemSolver() { mpgos_coupled_destroy(Handle); std::cout << "Object for Parameters scan is deleted! Every memory have been deallocated!" << std::endl << std::endl; }

@@ -192,23 +192,37 @@ class ProblemSolver
 		}
 	}
 
-public:
-	explicit ProblemSolver(int Device)
+	void Construct(const int* Devices, int DeviceCount, int Tile)
 	{
 		mpgos_perthread_desc d;
 		std::memset(&d, 0, sizeof(d));
 		d.NT = NT; d.SD = SD; d.NCP = NCP; d.NSP = NSP; d.NISP = NISP; d.NE = NE; d.NA = NA; d.NIA = NIA; d.NDO = NDO;
-		d.Algorithm = (int)Algorithm; d.PrecisionBytes = (int)sizeof(Precision); d.Device = Device;
+		d.Algorithm = (int)Algorithm; d.PrecisionBytes = (int)sizeof(Precision); d.Device = Devices[0];
 		Handle = nullptr;
-		Check(mpgos_perthread_create(&d, &Handle), "ProblemSolver (constructor)");
+		if (DeviceCount == 1) Check(mpgos_perthread_create(&d, &Handle), "ProblemSolver (constructor)");
+		else                  Check(mpgos_perthread_create_sharded(&d, Devices, DeviceCount, Tile, &Handle), "ProblemSolver (constructor)");
 		h_TimeDomain = Mirror<Precision>(TimeDomain);  h_ActualState = Mirror<Precision>(ActualState);  h_ActualTime = Mirror<Precision>(ActualTime);
 		h_ControlParameters = Mirror<Precision>(ControlParameters);  h_SharedParameters = Mirror<Precision>(SharedParameters);
 		h_IntegerSharedParameters = Mirror<int>(IntegerSharedParameters);  h_Accessories = Mirror<Precision>(Accessories);
 		h_IntegerAccessories = Mirror<int>(IntegerAccessories);  h_DenseOutputIndex = Mirror<int>(DenseIndex);
 		h_DenseOutputTimeInstances = Mirror<Precision>(DenseTime);  h_DenseOutputStates = Mirror<Precision>(DenseState);
 		// the reference launches 64-thread blocks from its tutorials; our default is the runtime's
-		std::cout << "Object for Parameters scan is successfully created on device " << Device << " (B200-native solver, "
-		          << NT << " instances, " << (Algorithm == RK4 ? "RK4" : "RKCK45") << ", " << (sizeof(Precision) == 8 ? "double" : "float") << ")" << std::endl << std::endl;
+		std::cout << "Object for Parameters scan is successfully created on device " << Devices[0];
+		for (int i = 1; i < DeviceCount; i++) std::cout << ", " << Devices[i];
+		std::cout << " (B200-native solver, " << NT << " instances, " << (Algorithm == RK4 ? "RK4" : "RKCK45") << ", " << (sizeof(Precision) == 8 ? "double" : "float") << ")" << std::endl << std::endl;
+	}
+
+public:
+	explicit ProblemSolver(int Device) { Construct(&Device, 1, 0); }
+
+	// Addition of this implementation: ONE object over several devices of the node.  The NT instances are dealt to the devices in
+	// tiles of `Tile` consecutive instances (0: 4096); the host side (SetHost / GetHost / Print, one mirror in the sweep's layout)
+	// and every other member work as for one device; callbacks receive the instance's id in the whole sweep and NT.  The
+	// reference needs one object per device, filled and driven by hand (T8_MultiGPUSingleNode/MultiGPUSingleNode.cu:85-135).
+	explicit ProblemSolver(const std::vector<int>& Devices, int Tile = 0)
+	{
+		if (Devices.empty()) { std::cerr << "ERROR: In solver member function ProblemSolver (constructor)!" << std::endl << "       empty device list" << std::endl; exit(EXIT_FAILURE); }
+		Construct(Devices.data(), (int)Devices.size(), Tile);
 	}
 
 	~ProblemSolver() { mpgos_perthread_destroy(Handle); std::cout << "Object for Parameters scan is deleted! Every memory have been deallocated!" << std::endl << std::endl; }

@@ -88,6 +88,12 @@ typedef struct mpgos_perthread_desc
 	int Device;             /* CUDA device ordinal (ctor argument, ST/Interface.cuh:309) */
 	int InstanceOffset;     /* global id of local instance 0 (0 for an unsharded solver) */
 	int GlobalInstances;    /* NT seen by the callbacks (0 = same as NT) */
+	/* Tile-cyclic shard of a sweep (filled in by mpgos_perthread_create_sharded for the per-device parts of a multi-device
+	 * solver; all 0 for an ordinary solver): the sweep is cut into tiles of ShardTile consecutive instances, tile t belongs to
+	 * shard t % ShardCount, and local instance i of shard ShardIndex has the global id
+	 *     ((i / ShardTile) * ShardCount + ShardIndex) * ShardTile + i % ShardTile  (+ InstanceOffset),
+	 * which is what the callbacks receive as `tid` (ST/Solver.cuh:148-160 passes tid and NT to every callback). */
+	int ShardIndex, ShardCount, ShardTile;
 } mpgos_perthread_desc;
 
 /* What a kernel launcher receives: device pointers in the run's precision and the resolved
@@ -95,6 +101,7 @@ typedef struct mpgos_perthread_desc
  * (ST/Interface.cuh:72-115). */
 typedef struct mpgos_perthread_launch
 {
+	int    AbiVersion;      /* MPGOS_B200_ABI_VERSION of the runtime that filled the struct; a launcher built against another one refuses */
 	mpgos_perthread_desc desc;
 	void*  d_TimeDomain;  void* d_ActualState;  void* d_ActualTime;  void* d_ControlParameters;
 	void*  d_SharedParameters;  int* d_IntegerSharedParameters;
@@ -140,6 +147,29 @@ int   mpgos_device_count(void);                                   /* ListCUDADev
 int   mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_solver** out);
 /* ~ProblemSolver, ST/Interface.cuh:522-555 */
 int   mpgos_perthread_destroy(mpgos_perthread_solver* s);
+
+/* One solver object over SEVERAL devices of one node (the reference's only multi-GPU mechanism is one ProblemSolver per device,
+ * filled and driven by hand: Tutorials_SingleSystem_PerThread/T8_MultiGPUSingleNode/MultiGPUSingleNode.cu:55-56, 85-135).
+ * desc->NT is the size of the whole sweep; desc->Device is ignored.  The handle behaves like an ordinary one for every call
+ * below: ONE pinned host mirror per variable in the reference layout (stride NT, so SetHost/GetHost index arithmetic is
+ * unchanged); the instances are dealt to the devices in tiles of `tile` consecutive instances, round-robin (cost varies
+ * smoothly along a sweep, so contiguous slabs would leave most devices idle behind the most expensive one; tile <= 0 picks
+ * 4096, a multiple of 32 is required); SynchroniseFromHostToDevice / FromDeviceToHost become strided 2-D copies per device
+ * on that device's stream, Solve() enqueues one launch per device from the calling thread, SynchroniseSolver waits for all of
+ * them, step counters are gathered in sweep order.  Callbacks receive the global instance id and the global NT.  There is no
+ * collective and no device-to-device traffic: instances are independent.  mpgos_perthread_device_ptr and _stream refer to the
+ * part on the first device. */
+int   mpgos_perthread_create_sharded(const mpgos_perthread_desc* desc, const int* devices, int device_count, int tile,
+                                     mpgos_perthread_solver** out);
+/* Number of devices behind a handle (1 for an ordinary solver) and, for part `shard`, its device, its number of instances and
+ * the global id of its local instance `local`. */
+int   mpgos_perthread_shard_count(mpgos_perthread_solver* s);
+int   mpgos_perthread_shard_info(mpgos_perthread_solver* s, int shard, int* device, int* instances);
+int   mpgos_perthread_shard_global_id(mpgos_perthread_solver* s, int shard, int local);
+/* The tile map itself (no device needed): instances of part `index` of `count` in a sweep of NT, and the global id of its local
+ * instance `local`; -1 on a bad argument. */
+int   mpgos_shard_instances(int NT, int tile, int count, int index);
+int   mpgos_shard_global_id(int tile, int count, int index, int local);
 
 /* Pinned host mirror of a variable (SetHost/GetHost do their index arithmetic on it inline,
  * ST/Interface.cuh:708-876, 1009-1081); *elements receives its length.  Variables:
@@ -197,7 +227,8 @@ void* mpgos_perthread_device_ptr(mpgos_perthread_solver* s, int variable, size_t
 int   mpgos_perthread_solve_timed(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher, int phases, float* elapsed_ms);
 
 /* Systems compiled into the library (the tutorial systems the BASELINE configurations use):
- * "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense".
+ * "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", and "tidprobe" (a test system whose
+ * right-hand side depends on the instance id).
  * mpgos_perthread_builtin_desc fills SD..NIA for the named system (NT, NDO, Device are the
  * caller's); mpgos_perthread_builtin_launcher returns NULL for an unknown combination. */
 int   mpgos_perthread_builtin_count(void);

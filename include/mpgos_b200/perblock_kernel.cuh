@@ -58,6 +58,7 @@ struct PerBlockArgs
 	// counts give; systems that ended inside the pilot are skipped.  0: the whole phase in one launch.
 	int SliceMode;  P SliceFraction;
 	P* SliceDt;  P* SliceLastDt;  P* SliceDenseNext;  int* SliceSkipped;  int* SlicePaused;
+	int ShardIndex, ShardCount, ShardTile;      // tile-cyclic shard of a multi-device solver (mpgos_b200_coupled.h); ShardCount <= 1: none
 	int NS, Active, SystemOffset, DenseCapacity, DenseOutputSaveFrequency, DeviceMessages;
 	P   InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep, MinimumTimeStepGuard;
 	P   RelativeTolerance[UD];  P AbsoluteTolerance[UD];
@@ -367,7 +368,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			}
 			if (!dry && !(resumed && a.SlicePaused[sys] == 0))      // continuation: a system that ended inside the pilot is skipped
 			{
-				gsys = sys + a.SystemOffset;
+				gsys = (a.ShardCount > 1 ? ((sys / a.ShardTile) * a.ShardCount + a.ShardIndex) * a.ShardTile + sys % a.ShardTile : sys) + a.SystemOffset;
 				ug   = (size_t)sys * UPS + (is_unit ? unit : 0);
 				// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
 				if (unit == 0)
@@ -863,6 +864,7 @@ struct PerBlockLauncher
 	static int launch(const mpgos_coupled_launch* L, void* stream_v)
 	{
 		cudaStream_t stream = (cudaStream_t)stream_v;
+		if (L->AbiVersion != MPGOS_B200_ABI_VERSION) return (int)cudaErrorInvalidValue;      // translation unit built against another header
 		const mpgos_coupled_desc& d = L->desc;
 		if (d.UPS != UPS || d.UD != UD || d.NC != NC || d.CBW != CBW || d.CCI != CCI || d.NUP != NUP || d.NSP != NSP || d.NGP != NGP || d.NiGP != NiGP ||
 		    d.NUA != NUA || d.NiUA != NiUA || d.NSA != NSA || d.NiSA != NiSA || d.NE != NE || d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
@@ -876,6 +878,7 @@ struct PerBlockLauncher
 		a.DenseOutputStates = (P*)L->d_DenseOutputStates;  a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
 		a.LastPhaseSteps = L->d_LastPhaseSteps;  a.DispatchOrder = nullptr;
 		a.SliceMode = 0;  a.SliceFraction = P(0);  a.SliceDt = a.SliceLastDt = a.SliceDenseNext = nullptr;  a.SliceSkipped = a.SlicePaused = nullptr;
+		a.ShardIndex = d.ShardIndex;  a.ShardCount = d.ShardCount;  a.ShardTile = d.ShardTile > 0 ? d.ShardTile : 1;
 		a.NS = d.NS;  a.Active = L->ActiveSystems < d.NS ? L->ActiveSystems : d.NS;  a.SystemOffset = d.SystemOffset;  a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;  a.DeviceMessages = L->DeviceMessages;
 		a.InitialTimeStep = (P)L->InitialTimeStep;  a.MaximumTimeStep = (P)L->MaximumTimeStep;  a.MinimumTimeStep = (P)L->MinimumTimeStep;

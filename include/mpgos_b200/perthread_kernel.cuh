@@ -87,6 +87,7 @@ struct PerThreadArgs
 	int  Active;             // instances [0, Active) are integrated
 	int  InstanceOffset;     // global id of local instance 0
 	int  GlobalInstances;    // NT as the callbacks see it
+	int  ShardIndex, ShardCount, ShardTile;      // tile-cyclic shard of a multi-device solver (mpgos_b200.h); ShardCount <= 1: none
 	int  DenseCapacity;      // NDO
 	int  DenseOutputSaveFrequency;
 	int  DeviceMessages;
@@ -416,6 +417,7 @@ struct LaneState
 	P   dense_next_time;
 	int dense_index;
 	int dense_skipped;
+	int gid;                             // the instance's id in the whole sweep: what the callbacks receive as `tid`
 	unsigned attempted, accepted;
 };
 
@@ -489,7 +491,9 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE, NSP, NISP> a)
 		s.attempted = 0;  s.accepted = 0;
 
 		P dt0 = a.InitialTimeStep;
-		const int gid = inst + a.InstanceOffset;
+		// global id: the instance's own index, or its place in the sweep a multi-device solver deals out in tiles
+		s.gid = (a.ShardCount > 1 ? ((inst / a.ShardTile) * a.ShardCount + a.ShardIndex) * a.ShardTile + inst % a.ShardTile : inst) + a.InstanceOffset;
+		const int gid = s.gid;
 		Sys::Initialization(gid, NTG, s.dense_index, s.t, dt0, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 		if (NE > 0)
 			Sys::EventFunction(gid, NTG, s.ev, s.t, dt0, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
@@ -512,7 +516,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE, NSP, NISP> a)
 	auto step = [&](const int inst, P& dt) -> bool
 	{
 		// ======================== one attempted step (Solver.cuh:197-394) =====================
-		const int gid = inst + a.InstanceOffset;
+		const int gid = s.gid;
 		bool update = true, finite = true, terminate = false, end_reached = false;
 		dt = s.dt_new;
 		{
@@ -747,17 +751,28 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE, NSP, NISP> a)
 			{
 				float yf;
 				mult = ck<P>(CK_SAFETY) * ratio_root_fast<P>(tsel, esel, update, yf);
-				if (sizeof(P) == 8)      // in FP32 the exact compares cost the same as the screening (measured: 0.896 vs 0.917 ms on C2 FP32)
+				if (sizeof(P) == 8)
 				{
 					const float df = Num<P>::narrow(dt);
 					const float mf = 0.9f * yf;
 					const float nf = df * mf;
 					plain = (df > a.GuardAbove) && (mf > a.ShrinkAbove) && (mf < a.GrowBelow) && (nf > a.MinimumAbove) && (nf < a.MaximumBelow);
+					if (plain) s.dt_new = dt * mult;
+				}
+				else if (!(dt < a.MinimumTimeStepGuard))
+				{
+					// in FP32 the exact limits cost the same as the screening (measured: 0.896 vs 0.917 ms on C2 FP32): applied in place;
+					// only the forced acceptance at the minimum step goes out of line
+					mult = (mult > a.TimeStepGrowLimit) ? a.TimeStepGrowLimit : mult;
+					mult = (mult < a.TimeStepShrinkLimit) ? a.TimeStepShrinkLimit : mult;
+					P dt_new = dt * mult;
+					dt_new = (dt_new > a.MaximumTimeStep) ? a.MaximumTimeStep : dt_new;
+					dt_new = (dt_new < a.MinimumTimeStep) ? a.MinimumTimeStep : dt_new;
+					s.dt_new = dt_new;
+					plain = true;
 				}
 			}
-			if (plain)
-				s.dt_new = dt * mult;
-			else
+			if (!plain)
 			{   // [cold>
 				// the rest of the controller is cold and lives out of line (controller_exact): the ordinary step neither holds its
 				// temporaries in registers nor keeps the accept / terminate flags out of predicates because of it
@@ -866,7 +881,7 @@ perthread_kernel(const __grid_constant__ PerThreadArgs<P, SD, NE, NSP, NISP> a)
 	// ---- end of the phase for this instance (Solver.cuh:398-435) ------------------------------------
 	auto store = [&](const int inst, P& dt)
 	{
-		const int gid = inst + a.InstanceOffset;
+		const int gid = s.gid;
 		Sys::Finalization(gid, NTG, s.dense_index, s.t, dt, s.td, s.x, s.cpar, p_par, p_pari, s.acc, s.acci);
 		#pragma unroll
 		for (int i = 0; i < 2; i++)   a.TimeDomain[inst + i * stride] = s.td[i];
@@ -1055,6 +1070,7 @@ struct PerThreadLauncher
 	static int launch(const mpgos_perthread_launch* L, void* stream_v)
 	{
 		cudaStream_t stream = (cudaStream_t)stream_v;
+		if (L->AbiVersion != MPGOS_B200_ABI_VERSION) return (int)cudaErrorInvalidValue;      // translation unit built against another mpgos_b200.h
 		const mpgos_perthread_desc& d = L->desc;
 		if (d.SD != SD || d.NCP != NCP || d.NSP != NSP || d.NISP != NISP || d.NE != NE || d.NA != NA || d.NIA != NIA ||
 		    d.Algorithm != ALG || d.PrecisionBytes != (int)sizeof(P) || (d.NDO > 0) != DENSE)
@@ -1071,6 +1087,7 @@ struct PerThreadLauncher
 		a.Stride = d.NT;
 		a.Active = L->ActiveNumberOfThreads < d.NT ? L->ActiveNumberOfThreads : d.NT;
 		a.InstanceOffset = d.InstanceOffset;
+		a.ShardIndex = d.ShardIndex;  a.ShardCount = d.ShardCount;  a.ShardTile = d.ShardTile > 0 ? d.ShardTile : 1;
 		a.GlobalInstances = d.GlobalInstances > 0 ? d.GlobalInstances : d.NT;
 		a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;

@@ -61,10 +61,15 @@ typedef struct mpgos_coupled_desc
 	int PrecisionBytes;   /* 8 (4 is not built yet) */
 	int Device;
 	int SystemOffset;     /* global id of local system 0 when a sweep is sharded over several solver objects */
+	/* tile-cyclic shard of a multi-device solver (mpgos_coupled_create_sharded; all 0 otherwise): tiles of ShardTile consecutive
+	 * systems, tile t on part t % ShardCount; local system i of part ShardIndex is system
+	 * ((i / ShardTile) * ShardCount + ShardIndex) * ShardTile + i % ShardTile (+ SystemOffset) of the sweep -- the `sid` the callbacks get */
+	int ShardIndex, ShardCount, ShardTile;
 } mpgos_coupled_desc;
 
 typedef struct mpgos_coupled_launch
 {
+	int    AbiVersion;      /* MPGOS_B200_ABI_VERSION of the runtime that filled the struct; a launcher built against another one refuses */
 	mpgos_coupled_desc desc;
 	void* d_TimeDomain;  void* d_ActualState;  void* d_ActualTime;  void* d_UnitParameters;  void* d_SystemParameters;
 	void* d_GlobalParameters;  int* d_IntegerGlobalParameters;  void* d_UnitAccessories;  int* d_IntegerUnitAccessories;
@@ -92,6 +97,12 @@ typedef struct mpgos_coupled_solver mpgos_coupled_solver;
 /* ProblemSolver(int) / ~ProblemSolver, CP/Interface.cuh:353-657, 661-700 */
 int   mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** out);
 int   mpgos_coupled_destroy(mpgos_coupled_solver* s);
+/* One solver object over several devices of the node, the twin of mpgos_perthread_create_sharded (mpgos_b200.h): desc->NS systems
+ * are dealt to the devices in tiles of `tile` systems (<= 0: 64), one pinned host mirror per variable in the reference layout over
+ * all NS systems, strided copies per device, one launch per device from the calling thread, coupling matrices / global parameters /
+ * coupling indices replicated.  A single system is never split.  Every other entry point takes the handle as usual. */
+int   mpgos_coupled_create_sharded(const mpgos_coupled_desc* desc, const int* devices, int device_count, int tile, mpgos_coupled_solver** out);
+int   mpgos_coupled_shard_count(mpgos_coupled_solver* s);
 /* pinned host mirror of a variable (CouplingMatrix: the PACKED matrix) and its length */
 void* mpgos_coupled_host_ptr(mpgos_coupled_solver* s, int variable, size_t* elements);
 /* SetHost(CouplingNumber, CouplingMatrix, Row, Col, Value), CP/Interface.cuh:993-1081: packs by matrix type; entries outside

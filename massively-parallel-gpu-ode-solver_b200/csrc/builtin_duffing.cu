@@ -22,6 +22,8 @@ static const BuiltinEntry kEntries[] = {
 	MPGOS_BUILTIN_ENTRY("duffing", Duffing, double, kAlgRKCK45, false, MPGOS_MINB_DUFFING),
 	MPGOS_BUILTIN_ENTRY("duffing", Duffing, float, kAlgRKCK45, true, MPGOS_MINB_DUFFING),
 	MPGOS_BUILTIN_ENTRY("duffing", Duffing, float, kAlgRK4, true, MPGOS_MINB_DUFFING),
+	MPGOS_BUILTIN_ENTRY("tidprobe", TidProbe, double, kAlgRKCK45, false, MPGOS_MINB_DUFFING),
+	MPGOS_BUILTIN_ENTRY("tidprobe", TidProbe, double, kAlgRK4, false, MPGOS_MINB_DUFFING),
 };
 const BuiltinEntry* builtin_entries_duffing(int* n) { *n = (int)(sizeof(kEntries) / sizeof(kEntries[0])); return kEntries; }
 }

@@ -43,6 +43,19 @@ struct Lorenz : Empty<P>
 	}
 };
 
+// Not a tutorial system: relaxation towards tid / NT.  The only built-in system whose right-hand side and accessories depend on
+// the instance id and on NT as the callbacks see them (ST/Solver.cuh:148-160 hands both to every callback; README.md:35 of the
+// reference advertises indexing by them) -- used to check that a sweep dealt out over several solver parts / devices still
+// shows every callback the instance's id in the WHOLE sweep.
+template <class P>
+struct TidProbe : Empty<P>
+{
+	enum { SD = 1, NCP = 1, NSP = 0, NISP = 0, NE = 0, NA = 1, NIA = 2 };
+	MPGOS_DEV OdeFunction(MPGOS_ODE_ARGS(P)) { F[0] = cPAR[0] * ((P)tid / (P)NT - X[0]); }
+	MPGOS_DEV Initialization(MPGOS_INIT_ARGS(P)) { T = TD[0];  ACCi[0] = tid; }
+	MPGOS_DEV Finalization(MPGOS_INIT_ARGS(P)) { ACCi[1] = NT;  ACC[0] = (P)tid / (P)NT; }
+};
+
 // T3_PoincareSection/Poincare_SystemDefinition.cuh:6-13, 44-51 -- Duffing without events
 template <class P>
 struct Poincare : Empty<P>

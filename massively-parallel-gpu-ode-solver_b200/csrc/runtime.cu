@@ -212,7 +212,85 @@ struct mpgos_perthread_solver
 	// shared parameters as of the last host-to-device copy: small sets reach the kernel by value (perthread_kernel.cuh)
 	std::vector<double> shared_values;
 	std::vector<int>    integer_shared_values;
+	// multi-device solver (mpgos_perthread_create_sharded): the parent owns the host mirrors (global layout) and no device
+	// memory; each part is an ordinary solver object on its device without host mirrors
+	std::vector<mpgos_perthread_solver*> shards;
+	int  tile = 0;
+	bool has_host_mirrors = true;
 };
+
+namespace {
+
+// ---- tile-cyclic shard map (mpgos_b200.h): tile t of `tile` consecutive instances belongs to shard t % count ----
+int shard_instances(int NT, int tile, int count, int index)
+{
+	const int ntiles = (NT + tile - 1) / tile;
+	if (index >= ntiles) return 0;
+	const int mine = (ntiles - index + count - 1) / count;
+	int n = mine * tile;
+	if ((ntiles - 1) % count == index) n -= ntiles * tile - NT;      // the sweep's last tile may be short
+	return n;
+}
+long long shard_global_id(int tile, int count, int index, int local) { return ((long long)(local / tile) * count + index) * tile + local % tile; }
+// local instances of the shard whose global id is below `limit`
+int shard_instances_below(int NT, int tile, int count, int index, int limit)
+{
+	return shard_instances(limit < NT ? (limit > 0 ? limit : 0) : NT, tile, count, index);
+}
+
+// elements per instance of a per-instance variable (0: not per instance)
+int serials_of(const mpgos_perthread_desc& d, int v)
+{
+	switch (v)
+	{
+		case MPGOS_VAR_TimeDomain: return 2;            case MPGOS_VAR_ActualState: return d.SD;        case MPGOS_VAR_ActualTime: return 1;
+		case MPGOS_VAR_ControlParameters: return d.NCP; case MPGOS_VAR_Accessories: return d.NA;        case MPGOS_VAR_IntegerAccessories: return d.NIA;
+		case MPGOS_VAR_DenseIndex: return 1;            case MPGOS_VAR_DenseTime: return d.NDO;         case MPGOS_VAR_DenseState: return d.NDO * d.SD;
+		default: return 0;
+	}
+}
+size_t element_size_of(const mpgos_perthread_desc& d, int v)
+{
+	return (v == MPGOS_VAR_IntegerSharedParameters || v == MPGOS_VAR_IntegerAccessories || v == MPGOS_VAR_DenseIndex) ? 4 : (size_t)d.PrecisionBytes;
+}
+
+// Strided copy between a host array in the sweep's layout (element (g, serial) at [g + serial * NT]) and one part's device
+// buffer (element (i, serial) at [i + serial * n]): one 2-D copy for the whole variable when the sweep is a whole number of
+// rounds of tiles, else one per serial plus the short last tile.  Asynchronous on the part's stream.
+int copy_shard(mpgos_perthread_solver* parent, int index, int v, unsigned char* host, bool to_device)
+{
+	mpgos_perthread_solver* c = parent->shards[index];
+	const mpgos_perthread_desc& pd = parent->desc;
+	const int count = (int)parent->shards.size(), tile = parent->tile, NT = pd.NT, n = c->desc.NT;
+	const int serials = serials_of(pd, v);
+	const size_t es = element_size_of(pd, v);
+	unsigned char* dev = (unsigned char*)c->var[v].dev;
+	if (n == 0 || serials == 0 || !dev) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(c->desc.Device));
+	auto copy2d = [&](size_t dev_off, size_t host_off, size_t width, size_t rows) -> cudaError_t
+	{
+		if (rows == 0 || width == 0) return cudaSuccess;
+		return to_device ? cudaMemcpy2DAsync(dev + dev_off, (size_t)tile * es, host + host_off, (size_t)tile * count * es, width, rows, cudaMemcpyHostToDevice, c->stream)
+		                 : cudaMemcpy2DAsync(host + host_off, (size_t)tile * count * es, dev + dev_off, (size_t)tile * es, width, rows, cudaMemcpyDeviceToHost, c->stream);
+	};
+	const size_t first = (size_t)index * tile * es;       // host offset of the part's first tile
+	if (NT % (tile * count) == 0)
+	{
+		// rows (serial, local tile) have a uniform pitch on both sides
+		CUDA_TRY(copy2d(0, first, (size_t)tile * es, (size_t)serials * (n / tile)));
+		return MPGOS_OK;
+	}
+	const int full = n / tile, rest = n % tile;
+	for (int k = 0; k < serials; k++)
+	{
+		CUDA_TRY(copy2d((size_t)k * n * es, (size_t)k * NT * es + first, (size_t)tile * es, (size_t)full));
+		if (rest) CUDA_TRY(copy2d(((size_t)k * n + (size_t)full * tile) * es, (size_t)k * NT * es + first + (size_t)full * tile * count * es, (size_t)rest * es, 1));
+	}
+	return MPGOS_OK;
+}
+
+} // namespace
+
 
 extern "C" {
 
@@ -226,19 +304,26 @@ int mpgos_device_count(void)
 	return n;
 }
 
-static int alloc_mirror(Mirror& m, size_t elements, size_t elem_size)
+static int alloc_mirror(Mirror& m, size_t elements, size_t elem_size, bool host, bool device)
 {
 	m.elements = elements;
 	m.bytes = elements * elem_size;
 	if (m.bytes == 0) return MPGOS_OK;
-	CUDA_TRY(cudaMallocHost(&m.host, m.bytes));
-	std::memset(m.host, 0, m.bytes);
-	CUDA_TRY(cudaMalloc(&m.dev, m.bytes));
-	CUDA_TRY(cudaMemset(m.dev, 0, m.bytes));
+	if (host)
+	{
+		CUDA_TRY(cudaMallocHost(&m.host, m.bytes));
+		std::memset(m.host, 0, m.bytes);
+	}
+	if (device)
+	{
+		CUDA_TRY(cudaMalloc(&m.dev, m.bytes));
+		CUDA_TRY(cudaMemset(m.dev, 0, m.bytes));
+	}
 	return MPGOS_OK;
 }
 
-int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_solver** out)
+// host_mirrors = false: a part of a multi-device solver (its parent owns the host side)
+static int create_impl(const mpgos_perthread_desc* desc, bool host_mirrors, mpgos_perthread_solver** out)
 {
 	if (!desc || !out) return fail(MPGOS_ERR_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -268,9 +353,10 @@ int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_sol
 	s->rtol.assign(d.SD, 1e-8);  s->atol.assign(d.SD, 1e-8);
 	s->evtol.assign(d.NE > 0 ? d.NE : 1, 1e-6);  s->evdir.assign(d.NE > 0 ? d.NE : 1, 0);
 	s->shared_values.assign(d.NSP > 0 ? d.NSP : 1, 0.0);  s->integer_shared_values.assign(d.NISP > 0 ? d.NISP : 1, 0);
+	s->has_host_mirrors = host_mirrors;
 
 	int rc = MPGOS_OK;
-	auto A = [&](int v, size_t elements, size_t elem) { if (rc == MPGOS_OK) rc = alloc_mirror(s->var[v], elements, elem); };
+	auto A = [&](int v, size_t elements, size_t elem) { if (rc == MPGOS_OK) rc = alloc_mirror(s->var[v], elements, elem, host_mirrors, true); };
 	A(MPGOS_VAR_TimeDomain, 2 * NT, P);
 	A(MPGOS_VAR_ActualState, d.SD * NT, P);
 	A(MPGOS_VAR_ActualTime, NT, P);
@@ -312,9 +398,90 @@ int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_sol
 	return MPGOS_OK;
 }
 
+int mpgos_perthread_create(const mpgos_perthread_desc* desc, mpgos_perthread_solver** out) { return create_impl(desc, true, out); }
+
+int mpgos_perthread_create_sharded(const mpgos_perthread_desc* desc, const int* devices, int device_count, int tile, mpgos_perthread_solver** out)
+{
+	if (!desc || !out || !devices || device_count < 1) return fail(MPGOS_ERR_ARGUMENT, "create_sharded: null argument or no device");
+	*out = nullptr;
+	if (tile <= 0) tile = 4096;
+	if (tile % 32 != 0) return fail(MPGOS_ERR_ARGUMENT, "create_sharded: the tile (%d) must be a multiple of 32", tile);
+	const mpgos_perthread_desc& d = *desc;
+	if (d.NT <= 0 || d.SD <= 0 || d.NCP < 0 || d.NSP < 0 || d.NISP < 0 || d.NE < 0 || d.NA < 0 || d.NIA < 0 || d.NDO < 0)
+		return fail(MPGOS_ERR_ARGUMENT, "invalid sizes in descriptor");
+	if (d.PrecisionBytes != 8 && d.PrecisionBytes != 4) return fail(MPGOS_ERR_ARGUMENT, "precision must be 8 or 4 bytes");
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	for (int i = 0; i < device_count; i++)
+		if (devices[i] < 0 || devices[i] >= ndev) return fail(MPGOS_ERR_ARGUMENT, "device %d not present (%d devices)", devices[i], ndev);
+
+	mpgos_perthread_solver* p = new (std::nothrow) mpgos_perthread_solver();
+	if (!p) return fail(MPGOS_ERR_MEMORY, "host allocation failed");
+	p->desc = d;  p->desc.Device = devices[0];  p->desc.ShardIndex = 0;  p->desc.ShardCount = device_count;  p->desc.ShardTile = tile;
+	p->tile = tile;
+	p->ActiveNumberOfThreads = d.NT;
+	p->rtol.assign(d.SD, 1e-8);  p->atol.assign(d.SD, 1e-8);
+	p->evtol.assign(d.NE > 0 ? d.NE : 1, 1e-6);  p->evdir.assign(d.NE > 0 ? d.NE : 1, 0);
+	p->shared_values.assign(d.NSP > 0 ? d.NSP : 1, 0.0);  p->integer_shared_values.assign(d.NISP > 0 ? d.NISP : 1, 0);
+	// the host side: one pinned mirror per variable, in the reference's layout over the whole sweep
+	const size_t P = (size_t)d.PrecisionBytes, NT = (size_t)d.NT;
+	int rc = MPGOS_OK;
+	auto A = [&](int v, size_t elements, size_t elem) { if (rc == MPGOS_OK) rc = alloc_mirror(p->var[v], elements, elem, true, false); };
+	A(MPGOS_VAR_TimeDomain, 2 * NT, P);  A(MPGOS_VAR_ActualState, d.SD * NT, P);  A(MPGOS_VAR_ActualTime, NT, P);
+	A(MPGOS_VAR_ControlParameters, d.NCP * NT, P);  A(MPGOS_VAR_SharedParameters, d.NSP, P);  A(MPGOS_VAR_IntegerSharedParameters, d.NISP, 4);
+	A(MPGOS_VAR_Accessories, d.NA * NT, P);  A(MPGOS_VAR_IntegerAccessories, d.NIA * NT, 4);  A(MPGOS_VAR_DenseIndex, NT, 4);
+	A(MPGOS_VAR_DenseTime, (size_t)d.NDO * NT, P);  A(MPGOS_VAR_DenseState, (size_t)d.NDO * d.SD * NT, P);
+	for (int i = 0; i < device_count && rc == MPGOS_OK; i++)
+	{
+		mpgos_perthread_desc c = d;
+		c.NT = shard_instances(d.NT, tile, device_count, i);
+		c.Device = devices[i];
+		c.GlobalInstances = d.GlobalInstances > 0 ? d.GlobalInstances : d.NT;
+		c.ShardIndex = i;  c.ShardCount = device_count;  c.ShardTile = tile;
+		if (c.NT == 0) { rc = fail(MPGOS_ERR_ARGUMENT, "create_sharded: %d instances in tiles of %d leave device %d without work; use fewer devices or a smaller tile", d.NT, tile, devices[i]); break; }
+		mpgos_perthread_solver* child = nullptr;
+		rc = create_impl(&c, false, &child);
+		if (rc == MPGOS_OK) p->shards.push_back(child);
+	}
+	if (rc != MPGOS_OK) { char keep[512]; std::memcpy(keep, g_error, sizeof(keep)); mpgos_perthread_destroy(p); std::memcpy(g_error, keep, sizeof(keep)); return rc; }
+	p->sm_count = p->shards[0]->sm_count;
+	*out = p;
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_shard_count(mpgos_perthread_solver* s) { return !s ? 0 : (s->shards.empty() ? 1 : (int)s->shards.size()); }
+
+int mpgos_perthread_shard_info(mpgos_perthread_solver* s, int shard, int* device, int* instances)
+{
+	if (!s || shard < 0 || shard >= mpgos_perthread_shard_count(s)) return fail(MPGOS_ERR_ARGUMENT, "shard_info: bad argument");
+	mpgos_perthread_solver* c = s->shards.empty() ? s : s->shards[shard];
+	if (device) *device = c->desc.Device;
+	if (instances) *instances = c->desc.NT;
+	return MPGOS_OK;
+}
+
+int mpgos_perthread_shard_global_id(mpgos_perthread_solver* s, int shard, int local)
+{
+	if (!s || shard < 0 || shard >= mpgos_perthread_shard_count(s) || local < 0) return -1;
+	if (s->shards.empty()) return local < s->desc.NT ? local + s->desc.InstanceOffset : -1;
+	if (local >= s->shards[shard]->desc.NT) return -1;
+	return (int)shard_global_id(s->tile, (int)s->shards.size(), shard, local) + s->desc.InstanceOffset;
+}
+
+// the map itself, for callers and tests without a device: instances of part `index` of `count`, and a local instance's global id
+int mpgos_shard_instances(int NT, int tile, int count, int index) { return (NT < 0 || tile <= 0 || count <= 0 || index < 0 || index >= count) ? -1 : shard_instances(NT, tile, count, index); }
+int mpgos_shard_global_id(int tile, int count, int index, int local) { return (tile <= 0 || count <= 0 || index < 0 || index >= count || local < 0) ? -1 : (int)shard_global_id(tile, count, index, local); }
+
 int mpgos_perthread_destroy(mpgos_perthread_solver* s)
 {
 	if (!s) return MPGOS_OK;
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) mpgos_perthread_destroy(c);
+		for (Mirror& m : s->var) if (m.host) cudaFreeHost(m.host);
+		delete s;
+		return MPGOS_OK;
+	}
 	cudaSetDevice(s->desc.Device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (Mirror& m : s->var) { if (m.host) cudaFreeHost(m.host); if (m.dev) cudaFree(m.dev); }
@@ -349,6 +516,7 @@ void* mpgos_perthread_host_ptr(mpgos_perthread_solver* s, int variable, size_t* 
 void* mpgos_perthread_device_ptr(mpgos_perthread_solver* s, int variable, size_t* elements)
 {
 	if (!s || !is_buffer_variable(variable)) { fail(MPGOS_ERR_ARGUMENT, "device_ptr: bad variable %d", variable); return nullptr; }
+	if (!s->shards.empty()) return mpgos_perthread_device_ptr(s->shards[0], variable, elements);
 	if (elements) *elements = s->var[variable].elements;
 	return s->var[variable].dev;
 }
@@ -356,6 +524,13 @@ void* mpgos_perthread_device_ptr(mpgos_perthread_solver* s, int variable, size_t
 int mpgos_perthread_set_option(mpgos_perthread_solver* s, int option, double value)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	for (size_t i = 0; i < s->shards.size(); i++)
+	{
+		// every part takes the option; "the first n instances are active" becomes each part's share of them
+		const double v = option == MPGOS_OPT_ActiveNumberOfThreads ? (double)shard_instances_below(s->desc.NT, s->tile, (int)s->shards.size(), (int)i, (int)value) : value;
+		const int rc = mpgos_perthread_set_option(s->shards[i], option, v);
+		if (rc != MPGOS_OK) return rc;
+	}
 	switch (option)
 	{
 		case MPGOS_OPT_ThreadsPerBlock:            s->ThreadsPerBlock = (int)value; break;
@@ -379,6 +554,11 @@ int mpgos_perthread_set_option(mpgos_perthread_solver* s, int option, double val
 int mpgos_perthread_set_option_indexed(mpgos_perthread_solver* s, int option, int index, double value)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	for (mpgos_perthread_solver* c : s->shards)
+	{
+		const int rc = mpgos_perthread_set_option_indexed(c, option, index, value);
+		if (rc != MPGOS_OK) return rc;
+	}
 	const int SD = s->desc.SD, NE = s->desc.NE;
 	switch (option)
 	{
@@ -452,6 +632,31 @@ static int copy_variable(mpgos_perthread_solver* s, int variable, bool to_device
 	else if (variable == MPGOS_VAR_DenseOutput) { list[n++] = MPGOS_VAR_DenseIndex;  list[n++] = MPGOS_VAR_DenseTime;  list[n++] = MPGOS_VAR_DenseState; }
 	else if (is_buffer_variable(variable)) list[n++] = variable;
 	else return fail(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
+	if (!s->shards.empty())
+	{
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_perthread_solver* c = s->shards[k];
+			if (to_device && variable != MPGOS_VAR_TimeDomain && variable != MPGOS_VAR_DenseOutput && variable != MPGOS_VAR_DenseIndex) c->history_valid = false;
+			for (int i = 0; i < n; i++)
+			{
+				Mirror& m = s->var[list[i]];
+				if (m.bytes == 0) continue;
+				if (serials_of(s->desc, list[i]) > 0)
+				{
+					const int rc = copy_shard(s, (int)k, list[i], (unsigned char*)m.host, to_device);
+					if (rc != MPGOS_OK) return rc;
+				}
+				else       // shared parameters: every device holds them all
+				{
+					CUDA_TRY(cudaSetDevice(c->desc.Device));
+					if (to_device) { CUDA_TRY(cudaMemcpyAsync(c->var[list[i]].dev, m.host, m.bytes, cudaMemcpyHostToDevice, c->stream));  shadow_shared(c, list[i], m.host); }
+					else if (k == 0) CUDA_TRY(cudaMemcpyAsync(m.host, c->var[list[i]].dev, m.bytes, cudaMemcpyDeviceToHost, c->stream));
+				}
+			}
+		}
+		return MPGOS_OK;
+	}
 	// new instances or parameters: the cost history no longer describes them (a new time domain alone leaves the instances what they were)
 	if (to_device && variable != MPGOS_VAR_TimeDomain && variable != MPGOS_VAR_DenseOutput && variable != MPGOS_VAR_DenseIndex) s->history_valid = false;
 	for (int i = 0; i < n; i++)
@@ -473,6 +678,22 @@ int mpgos_perthread_upload(mpgos_perthread_solver* s, int variable, const void* 
 	Mirror& m = s->var[variable];
 	if (bytes != m.bytes) return fail(MPGOS_ERR_BOUNDS, "upload: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
 	if (bytes == 0) return MPGOS_OK;
+	if (!s->shards.empty())
+	{
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_perthread_solver* c = s->shards[k];
+			c->history_valid = false;
+			if (serials_of(s->desc, variable) > 0) { const int rc = copy_shard(s, (int)k, variable, (unsigned char*)const_cast<void*>(host_src), true);  if (rc != MPGOS_OK) return rc; }
+			else
+			{
+				CUDA_TRY(cudaSetDevice(c->desc.Device));
+				CUDA_TRY(cudaMemcpyAsync(c->var[variable].dev, host_src, bytes, cudaMemcpyHostToDevice, c->stream));
+				shadow_shared(c, variable, host_src);
+			}
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
 	shadow_shared(s, variable, host_src);
@@ -486,6 +707,20 @@ int mpgos_perthread_download(mpgos_perthread_solver* s, int variable, void* host
 	Mirror& m = s->var[variable];
 	if (bytes != m.bytes) return fail(MPGOS_ERR_BOUNDS, "download: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
 	if (bytes == 0) return MPGOS_OK;
+	if (!s->shards.empty())
+	{
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_perthread_solver* c = s->shards[k];
+			if (serials_of(s->desc, variable) > 0) { const int rc = copy_shard(s, (int)k, variable, (unsigned char*)host_dst, false);  if (rc != MPGOS_OK) return rc; }
+			else if (k == 0)
+			{
+				CUDA_TRY(cudaSetDevice(c->desc.Device));
+				CUDA_TRY(cudaMemcpyAsync(host_dst, c->var[variable].dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+			}
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(host_dst, m.dev, bytes, cudaMemcpyDeviceToHost, s->stream));
 	return MPGOS_OK;
@@ -493,6 +728,7 @@ int mpgos_perthread_download(mpgos_perthread_solver* s, int variable, void* host
 
 static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
 {
+	L.AbiVersion = MPGOS_B200_ABI_VERSION;
 	L.desc = s->desc;
 	L.d_TimeDomain = s->var[MPGOS_VAR_TimeDomain].dev;  L.d_ActualState = s->var[MPGOS_VAR_ActualState].dev;
 	L.d_ActualTime = s->var[MPGOS_VAR_ActualTime].dev;  L.d_ControlParameters = s->var[MPGOS_VAR_ControlParameters].dev;
@@ -518,6 +754,12 @@ static void fill_launch(mpgos_perthread_solver* s, mpgos_perthread_launch& L)
 int mpgos_perthread_solve(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher)
 {
 	if (!s || !launcher) return fail(MPGOS_ERR_ARGUMENT, "Solve: null solver or launcher");
+	for (mpgos_perthread_solver* c : s->shards)      // one launch per device, back to back from this thread; each on its own stream
+	{
+		const int rc = mpgos_perthread_solve(c, launcher);
+		if (rc != MPGOS_OK) return rc;
+	}
+	if (!s->shards.empty()) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	mpgos_perthread_launch L;
 	fill_launch(s, L);
@@ -530,6 +772,27 @@ int mpgos_perthread_solve(mpgos_perthread_solver* s, mpgos_perthread_launcher la
 int mpgos_perthread_solve_timed(mpgos_perthread_solver* s, mpgos_perthread_launcher launcher, int phases, float* elapsed_ms)
 {
 	if (!s || !launcher || !elapsed_ms || phases < 0) return fail(MPGOS_ERR_ARGUMENT, "solve_timed: bad argument");
+	if (!s->shards.empty())
+	{
+		// all devices run concurrently; the time of the slowest one
+		for (mpgos_perthread_solver* c : s->shards)
+		{
+			CUDA_TRY(cudaSetDevice(c->desc.Device));
+			CUDA_TRY(cudaEventRecord(c->t0, c->stream));
+			for (int p = 0; p < phases; p++) { const int rc = mpgos_perthread_solve(c, launcher);  if (rc != MPGOS_OK) return rc; }
+			CUDA_TRY(cudaEventRecord(c->t1, c->stream));
+		}
+		*elapsed_ms = 0;
+		for (mpgos_perthread_solver* c : s->shards)
+		{
+			float ms = 0;
+			CUDA_TRY(cudaSetDevice(c->desc.Device));
+			CUDA_TRY(cudaEventSynchronize(c->t1));
+			CUDA_TRY(cudaEventElapsedTime(&ms, c->t0, c->t1));
+			if (ms > *elapsed_ms) *elapsed_ms = ms;
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	mpgos_perthread_launch L;
 	fill_launch(s, L);
@@ -550,6 +813,11 @@ int mpgos_perthread_solve_timed(mpgos_perthread_solver* s, mpgos_perthread_launc
 int mpgos_perthread_insert_sync_point(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_insert_sync_point(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaEventRecord(s->event, s->stream));
 	return MPGOS_OK;
@@ -558,6 +826,11 @@ int mpgos_perthread_insert_sync_point(mpgos_perthread_solver* s)
 int mpgos_perthread_sync_solver(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_sync_solver(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaEventSynchronize(s->event));
 	return MPGOS_OK;
@@ -566,6 +839,11 @@ int mpgos_perthread_sync_solver(mpgos_perthread_solver* s)
 int mpgos_perthread_sync_device(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_sync_device(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaDeviceSynchronize());
 	return MPGOS_OK;
@@ -574,6 +852,25 @@ int mpgos_perthread_sync_device(mpgos_perthread_solver* s)
 int mpgos_perthread_read_step_counters(mpgos_perthread_solver* s, unsigned long long* attempted, unsigned long long* accepted)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		// each part's counters, scattered to their places in the sweep
+		std::vector<unsigned long long> a, b;
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_perthread_solver* c = s->shards[k];
+			a.resize(c->desc.NT);  b.resize(c->desc.NT);
+			const int rc = mpgos_perthread_read_step_counters(c, attempted ? a.data() : nullptr, accepted ? b.data() : nullptr);
+			if (rc != MPGOS_OK) return rc;
+			for (int i = 0; i < c->desc.NT; i++)
+			{
+				const long long g = shard_global_id(s->tile, (int)s->shards.size(), (int)k, i);
+				if (attempted) attempted[g] = a[i];
+				if (accepted)  accepted[g] = b[i];
+			}
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	const size_t bytes = 8 * (size_t)s->desc.NT;
 	if (attempted) CUDA_TRY(cudaMemcpyAsync(attempted, s->d_attempted, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -585,6 +882,11 @@ int mpgos_perthread_read_step_counters(mpgos_perthread_solver* s, unsigned long 
 int mpgos_perthread_reset_step_counters(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_reset_step_counters(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	const size_t bytes = 8 * (size_t)s->desc.NT;
 	CUDA_TRY(cudaMemsetAsync(s->d_attempted, 0, bytes, s->stream));
@@ -595,6 +897,20 @@ int mpgos_perthread_reset_step_counters(mpgos_perthread_solver* s)
 int mpgos_perthread_total_steps(mpgos_perthread_solver* s, unsigned long long* attempted, unsigned long long* accepted)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		unsigned long long ta = 0, tb = 0;
+		for (mpgos_perthread_solver* c : s->shards)
+		{
+			unsigned long long a = 0, b = 0;
+			const int rc = mpgos_perthread_total_steps(c, &a, &b);
+			if (rc != MPGOS_OK) return rc;
+			ta += a;  tb += b;
+		}
+		if (attempted) *attempted = ta;
+		if (accepted)  *accepted = tb;
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemsetAsync(s->d_totals, 0, 16, s->stream));
 	reduce_step_counters<<<148 * 4, 256, 0, s->stream>>>(s->d_attempted, s->d_accepted, s->desc.NT, s->d_totals);
@@ -613,6 +929,11 @@ static const int kStateVariables[] = { MPGOS_VAR_TimeDomain, MPGOS_VAR_ActualSta
 int mpgos_perthread_save_state(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_save_state(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	for (int v : kStateVariables)
 	{
@@ -627,6 +948,11 @@ int mpgos_perthread_save_state(mpgos_perthread_solver* s)
 int mpgos_perthread_restore_state(mpgos_perthread_solver* s)
 {
 	if (!s) return fail(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		for (mpgos_perthread_solver* c : s->shards) { const int rc = mpgos_perthread_restore_state(c);  if (rc != MPGOS_OK) return rc; }
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	for (int v : kStateVariables)
 	{
@@ -639,7 +965,7 @@ int mpgos_perthread_restore_state(mpgos_perthread_solver* s)
 	return MPGOS_OK;
 }
 
-void* mpgos_perthread_stream(mpgos_perthread_solver* s) { return s ? (void*)s->stream : nullptr; }
+void* mpgos_perthread_stream(mpgos_perthread_solver* s) { return !s ? nullptr : (s->shards.empty() ? (void*)s->stream : (void*)s->shards[0]->stream); }
 int   mpgos_perthread_device(mpgos_perthread_solver* s) { return s ? s->desc.Device : -1; }
 
 int mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops)
@@ -675,7 +1001,7 @@ static const std::vector<mpgos_b200::BuiltinEntry>& entries()
 	return all;
 }
 
-static const char* const kBuiltinNames[] = { "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense" };
+static const char* const kBuiltinNames[] = { "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", "tidprobe" };
 
 int mpgos_perthread_builtin_count(void) { return (int)(sizeof(kBuiltinNames) / sizeof(kBuiltinNames[0])); }
 const char* mpgos_perthread_builtin_name(int i) { return (i >= 0 && i < mpgos_perthread_builtin_count()) ? kBuiltinNames[i] : nullptr; }

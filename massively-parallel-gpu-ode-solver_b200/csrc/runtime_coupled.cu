@@ -47,7 +47,23 @@ struct mpgos_coupled_solver
 	int DenseOutputSaveFrequency = 1, ActiveSystems = 0, DeviceMessages = 0, SharedGlobalVariables = 1, SharedCouplingMatrices = 0, TensorCoreCoupling = 1;
 	std::vector<double> rtol, atol, evtol;
 	std::vector<int> evdir;
+	// multi-device solver (mpgos_coupled_create_sharded): the parent owns the host mirrors over all systems and no device memory
+	std::vector<mpgos_coupled_solver*> shards;
+	int tile = 0;
 };
+
+namespace {
+// tile-cyclic shard map, as in runtime.cu
+int cshard_systems(int NS, int tile, int count, int index)
+{
+	const int ntiles = (NS + tile - 1) / tile;
+	if (index >= ntiles) return 0;
+	int n = ((ntiles - index + count - 1) / count) * tile;
+	if ((ntiles - 1) % count == index) n -= ntiles * tile - NS;
+	return n;
+}
+long long cshard_global_id(int tile, int count, int index, int local) { return ((long long)(local / tile) * count + index) * tile + local % tile; }
+}
 
 static size_t matrix_elements(const mpgos_coupled_desc& d)
 {
@@ -64,9 +80,100 @@ static bool is_int_variable(int v)
 	       v == MPGOS_CVAR_CouplingIndex || v == MPGOS_CVAR_DenseIndex;
 }
 
+// (elements per system in one serial, serials) of a per-system variable; width 0: replicated on every device
+static void scope_of(const mpgos_coupled_desc& d, int v, int* width, int* serials)
+{
+	*width = 0;  *serials = 0;
+	switch (v)
+	{
+		case MPGOS_CVAR_ActualState:             *width = d.UPS; *serials = d.UD; break;
+		case MPGOS_CVAR_UnitParameters:          *width = d.UPS; *serials = d.NUP; break;
+		case MPGOS_CVAR_UnitAccessories:         *width = d.UPS; *serials = d.NUA; break;
+		case MPGOS_CVAR_IntegerUnitAccessories:  *width = d.UPS; *serials = d.NiUA; break;
+		case MPGOS_CVAR_DenseState:              *width = d.UPS; *serials = d.UD * d.NDO; break;
+		case MPGOS_CVAR_TimeDomain:              *width = 1; *serials = 2; break;
+		case MPGOS_CVAR_ActualTime:              *width = 1; *serials = 1; break;
+		case MPGOS_CVAR_SystemParameters:        *width = 1; *serials = d.NSP; break;
+		case MPGOS_CVAR_SystemAccessories:       *width = 1; *serials = d.NSA; break;
+		case MPGOS_CVAR_IntegerSystemAccessories:*width = 1; *serials = d.NiSA; break;
+		case MPGOS_CVAR_CouplingStrength:        *width = 1; *serials = d.NC; break;
+		case MPGOS_CVAR_DenseIndex:              *width = 1; *serials = 1; break;
+		case MPGOS_CVAR_DenseTime:               *width = 1; *serials = d.NDO; break;
+		default: break;
+	}
+}
+
+// strided copy between a host array over all NS systems and one part's device buffer (see copy_shard in runtime.cu)
+static int ccopy_shard(mpgos_coupled_solver* parent, int index, int v, unsigned char* host, bool to_device)
+{
+	mpgos_coupled_solver* c = parent->shards[index];
+	const mpgos_coupled_desc& pd = parent->desc;
+	const int count = (int)parent->shards.size(), tile = parent->tile, NS = pd.NS, n = c->desc.NS;
+	int width = 0, serials = 0;
+	scope_of(pd, v, &width, &serials);
+	const size_t es = (is_int_variable(v) ? 4 : (size_t)pd.PrecisionBytes) * (size_t)width;      // bytes per system and serial
+	unsigned char* dev = (unsigned char*)c->var[v].dev;
+	if (n == 0 || serials == 0 || width == 0 || !dev) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(c->desc.Device));
+	auto copy2d = [&](size_t dev_off, size_t host_off, size_t w, size_t rows) -> cudaError_t
+	{
+		if (rows == 0 || w == 0) return cudaSuccess;
+		return to_device ? cudaMemcpy2DAsync(dev + dev_off, (size_t)tile * es, host + host_off, (size_t)tile * count * es, w, rows, cudaMemcpyHostToDevice, c->stream)
+		                 : cudaMemcpy2DAsync(host + host_off, (size_t)tile * count * es, dev + dev_off, (size_t)tile * es, w, rows, cudaMemcpyDeviceToHost, c->stream);
+	};
+	const size_t first = (size_t)index * tile * es;
+	if (NS % (tile * count) == 0) { CUDA_TRY(copy2d(0, first, (size_t)tile * es, (size_t)serials * (n / tile)));  return MPGOS_OK; }
+	const int full = n / tile, rest = n % tile;
+	for (int k = 0; k < serials; k++)
+	{
+		CUDA_TRY(copy2d((size_t)k * n * es, (size_t)k * NS * es + first, (size_t)tile * es, (size_t)full));
+		if (rest) CUDA_TRY(copy2d(((size_t)k * n + (size_t)full * tile) * es, (size_t)k * NS * es + first + (size_t)full * tile * count * es, (size_t)rest * es, 1));
+	}
+	return MPGOS_OK;
+}
+
+static int ccreate_impl(const mpgos_coupled_desc* desc, bool host_mirrors, bool device_side, mpgos_coupled_solver** out);
+
 extern "C" {
 
-int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** out)
+int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** out) { return ccreate_impl(desc, true, true, out); }
+
+int mpgos_coupled_create_sharded(const mpgos_coupled_desc* desc, const int* devices, int device_count, int tile, mpgos_coupled_solver** out)
+{
+	if (!desc || !out || !devices || device_count < 1) return CFAIL(MPGOS_ERR_ARGUMENT, "create_sharded: null argument or no device");
+	*out = nullptr;
+	if (tile <= 0) tile = 64;
+	int ndev = 0;
+	CUDA_TRY(cudaGetDeviceCount(&ndev));
+	for (int i = 0; i < device_count; i++)
+		if (devices[i] < 0 || devices[i] >= ndev) return CFAIL(MPGOS_ERR_ARGUMENT, "device %d not present (%d devices)", devices[i], ndev);
+	mpgos_coupled_desc pd = *desc;
+	pd.Device = devices[0];  pd.ShardIndex = 0;  pd.ShardCount = device_count;  pd.ShardTile = tile;
+	mpgos_coupled_solver* p = nullptr;
+	int rc = ccreate_impl(&pd, true, false, &p);      // host mirrors over all systems, nothing on a device
+	if (rc != MPGOS_OK) return rc;
+	p->tile = tile;
+	for (int i = 0; i < device_count && rc == MPGOS_OK; i++)
+	{
+		mpgos_coupled_desc c = *desc;
+		c.NS = cshard_systems(desc->NS, tile, device_count, i);
+		c.Device = devices[i];  c.ShardIndex = i;  c.ShardCount = device_count;  c.ShardTile = tile;
+		if (c.NS == 0) { rc = CFAIL(MPGOS_ERR_ARGUMENT, "create_sharded: %d systems in tiles of %d leave device %d without work; use fewer devices or a smaller tile", desc->NS, tile, devices[i]); break; }
+		mpgos_coupled_solver* child = nullptr;
+		rc = ccreate_impl(&c, false, true, &child);
+		if (rc == MPGOS_OK) p->shards.push_back(child);
+	}
+	if (rc != MPGOS_OK) { char keep[512]; std::strncpy(keep, mpgos_last_error(), sizeof(keep) - 1); keep[sizeof(keep) - 1] = 0; mpgos_coupled_destroy(p); CFAIL(rc, "%s", keep); return rc; }
+	p->sm_count = p->shards[0]->sm_count;
+	*out = p;
+	return MPGOS_OK;
+}
+
+int mpgos_coupled_shard_count(mpgos_coupled_solver* s) { return !s ? 0 : (s->shards.empty() ? 1 : (int)s->shards.size()); }
+
+} // extern "C"
+
+static int ccreate_impl(const mpgos_coupled_desc* desc, bool host_mirrors, bool device_side, mpgos_coupled_solver** out)
 {
 	if (!desc || !out) return CFAIL(MPGOS_ERR_ARGUMENT, "null argument");
 	*out = nullptr;
@@ -94,7 +201,7 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 	for (int v = 0; v < MPGOS_CVAR_COUNT; v++) need += elems[v] * (is_int_variable(v) ? 4 : P);
 	size_t free_b = 0, total_b = 0;
 	CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-	if (need >= free_b) return CFAIL(MPGOS_ERR_MEMORY, "solver needs %zu bytes of device memory, %zu free", need, free_b);
+	if (device_side && need >= free_b) return CFAIL(MPGOS_ERR_MEMORY, "solver needs %zu bytes of device memory, %zu free", need, free_b);
 
 	mpgos_coupled_solver* s = new (std::nothrow) mpgos_coupled_solver();
 	if (!s) return CFAIL(MPGOS_ERR_MEMORY, "host allocation failed");
@@ -107,9 +214,15 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 		CMirror& m = s->var[v];
 		m.elements = elems[v];  m.bytes = elems[v] * (is_int_variable(v) ? 4 : P);
 		if (!m.bytes) continue;
-		e = cudaMallocHost(&m.host, m.bytes);
-		if (e == cudaSuccess) { std::memset(m.host, 0, m.bytes); e = cudaMalloc(&m.dev, m.bytes); }
-		if (e == cudaSuccess) e = cudaMemset(m.dev, 0, m.bytes);
+		if (host_mirrors) { e = cudaMallocHost(&m.host, m.bytes);  if (e == cudaSuccess) std::memset(m.host, 0, m.bytes); }
+		if (e == cudaSuccess && device_side) e = cudaMalloc(&m.dev, m.bytes);
+		if (e == cudaSuccess && device_side) e = cudaMemset(m.dev, 0, m.bytes);
+	}
+	if (!device_side)
+	{
+		if (e != cudaSuccess) { mpgos_coupled_destroy(s); return CFAIL(MPGOS_ERR_CUDA, "coupled solver construction failed -> %s", cudaGetErrorString(e)); }
+		*out = s;
+		return MPGOS_OK;
 	}
 	cudaDeviceProp prop;
 	if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, d.Device);
@@ -133,9 +246,13 @@ int mpgos_coupled_create(const mpgos_coupled_desc* desc, mpgos_coupled_solver** 
 	return MPGOS_OK;
 }
 
+extern "C" {
+
 int mpgos_coupled_destroy(mpgos_coupled_solver* s)
 {
 	if (!s) return MPGOS_OK;
+	for (mpgos_coupled_solver* c : s->shards) mpgos_coupled_destroy(c);
+	s->shards.clear();
 	cudaSetDevice(s->desc.Device);
 	if (s->stream) cudaStreamSynchronize(s->stream);
 	for (CMirror& m : s->var) { if (m.host) cudaFreeHost(m.host); if (m.dev) cudaFree(m.dev); if (m.snap) cudaFree(m.snap); }
@@ -202,6 +319,14 @@ int mpgos_coupled_get_matrix_entry(mpgos_coupled_solver* s, int k, int row, int 
 int mpgos_coupled_set_option(mpgos_coupled_solver* s, int option, double value)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	for (size_t i = 0; i < s->shards.size(); i++)
+	{
+		// "the first n systems are active" becomes each part's share of them
+		const int lim = (int)value < s->desc.NS ? ((int)value > 0 ? (int)value : 0) : s->desc.NS;
+		const double v = option == MPGOS_COPT_ActiveSystems ? (double)cshard_systems(lim, s->tile, (int)s->shards.size(), (int)i) : value;
+		const int rc = mpgos_coupled_set_option(s->shards[i], option, v);
+		if (rc != MPGOS_OK) return rc;
+	}
 	switch (option)
 	{
 		case MPGOS_COPT_InitialTimeStep:            s->InitialTimeStep = value; break;
@@ -225,6 +350,7 @@ int mpgos_coupled_set_option(mpgos_coupled_solver* s, int option, double value)
 int mpgos_coupled_set_option_indexed(mpgos_coupled_solver* s, int option, int index, double value)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_set_option_indexed(c, option, index, value);  if (rc != MPGOS_OK) return rc; }
 	const int UD = s->desc.UD, NE = s->desc.NE;
 	switch (option)
 	{
@@ -246,6 +372,29 @@ static int ccopy(mpgos_coupled_solver* s, int variable, bool to_device)
 	else if (variable == MPGOS_CVAR_DenseOutput) { list[n++] = MPGOS_CVAR_DenseIndex; list[n++] = MPGOS_CVAR_DenseTime; list[n++] = MPGOS_CVAR_DenseState; }
 	else if (is_cbuffer(variable)) list[n++] = variable;
 	else return CFAIL(MPGOS_ERR_ARGUMENT, "Synchronise: bad variable %d", variable);
+	if (!s->shards.empty())
+	{
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_coupled_solver* c = s->shards[k];
+			if (to_device && variable != MPGOS_CVAR_TimeDomain && variable != MPGOS_CVAR_DenseOutput && variable != MPGOS_CVAR_DenseIndex) c->history_valid = false;
+			for (int i = 0; i < n; i++)
+			{
+				CMirror& m = s->var[list[i]];
+				if (!m.bytes) continue;
+				int width = 0, serials = 0;
+				scope_of(s->desc, list[i], &width, &serials);
+				if (width > 0) { const int rc = ccopy_shard(s, (int)k, list[i], (unsigned char*)m.host, to_device);  if (rc != MPGOS_OK) return rc; }
+				else       // coupling matrices, global parameters, coupling indices: every device holds them all
+				{
+					CUDA_TRY(cudaSetDevice(c->desc.Device));
+					if (to_device)   CUDA_TRY(cudaMemcpyAsync(c->var[list[i]].dev, m.host, m.bytes, cudaMemcpyHostToDevice, c->stream));
+					else if (k == 0) CUDA_TRY(cudaMemcpyAsync(m.host, c->var[list[i]].dev, m.bytes, cudaMemcpyDeviceToHost, c->stream));
+				}
+			}
+		}
+		return MPGOS_OK;
+	}
 	// new systems or parameters: the cost history no longer describes them (a new time domain alone leaves the systems what they were)
 	if (to_device && variable != MPGOS_CVAR_TimeDomain && variable != MPGOS_CVAR_DenseOutput && variable != MPGOS_CVAR_DenseIndex) s->history_valid = false;
 	for (int i = 0; i < n; i++)
@@ -266,6 +415,19 @@ int mpgos_coupled_upload(mpgos_coupled_solver* s, int variable, const void* host
 	CMirror& m = s->var[variable];
 	if (bytes != m.bytes) return CFAIL(MPGOS_ERR_BOUNDS, "upload: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
 	if (bytes == 0) return MPGOS_OK;
+	if (!s->shards.empty())
+	{
+		int width = 0, serials = 0;
+		scope_of(s->desc, variable, &width, &serials);
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_coupled_solver* c = s->shards[k];
+			c->history_valid = false;
+			if (width > 0) { const int rc = ccopy_shard(s, (int)k, variable, (unsigned char*)const_cast<void*>(host_src), true);  if (rc != MPGOS_OK) return rc; }
+			else { CUDA_TRY(cudaSetDevice(c->desc.Device));  CUDA_TRY(cudaMemcpyAsync(c->var[variable].dev, host_src, bytes, cudaMemcpyHostToDevice, c->stream)); }
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(m.dev, host_src, bytes, cudaMemcpyHostToDevice, s->stream));
 	s->history_valid = false;
@@ -278,6 +440,18 @@ int mpgos_coupled_download(mpgos_coupled_solver* s, int variable, void* host_dst
 	CMirror& m = s->var[variable];
 	if (bytes != m.bytes) return CFAIL(MPGOS_ERR_BOUNDS, "download: variable %d holds %zu bytes, caller passed %zu", variable, m.bytes, bytes);
 	if (bytes == 0) return MPGOS_OK;
+	if (!s->shards.empty())
+	{
+		int width = 0, serials = 0;
+		scope_of(s->desc, variable, &width, &serials);
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_coupled_solver* c = s->shards[k];
+			if (width > 0) { const int rc = ccopy_shard(s, (int)k, variable, (unsigned char*)host_dst, false);  if (rc != MPGOS_OK) return rc; }
+			else if (k == 0) { CUDA_TRY(cudaSetDevice(c->desc.Device));  CUDA_TRY(cudaMemcpyAsync(host_dst, c->var[variable].dev, bytes, cudaMemcpyDeviceToHost, c->stream)); }
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemcpyAsync(host_dst, m.dev, bytes, cudaMemcpyDeviceToHost, s->stream));
 	return MPGOS_OK;
@@ -285,6 +459,7 @@ int mpgos_coupled_download(mpgos_coupled_solver* s, int variable, void* host_dst
 
 static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 {
+	L.AbiVersion = MPGOS_B200_ABI_VERSION;
 	L.desc = s->desc;
 	L.d_TimeDomain = s->var[MPGOS_CVAR_TimeDomain].dev;  L.d_ActualState = s->var[MPGOS_CVAR_ActualState].dev;  L.d_ActualTime = s->var[MPGOS_CVAR_ActualTime].dev;
 	L.d_UnitParameters = s->var[MPGOS_CVAR_UnitParameters].dev;  L.d_SystemParameters = s->var[MPGOS_CVAR_SystemParameters].dev;
@@ -308,6 +483,8 @@ static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 int mpgos_coupled_solve(mpgos_coupled_solver* s, mpgos_coupled_launcher launcher)
 {
 	if (!s || !launcher) return CFAIL(MPGOS_ERR_ARGUMENT, "Solve: null solver or launcher");
+	for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_solve(c, launcher);  if (rc != MPGOS_OK) return rc; }
+	if (!s->shards.empty()) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	mpgos_coupled_launch L;
 	cfill(s, L);
@@ -320,6 +497,26 @@ int mpgos_coupled_solve(mpgos_coupled_solver* s, mpgos_coupled_launcher launcher
 int mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher launcher, int phases, float* elapsed_ms)
 {
 	if (!s || !launcher || !elapsed_ms || phases < 0) return CFAIL(MPGOS_ERR_ARGUMENT, "solve_timed: bad argument");
+	if (!s->shards.empty())
+	{
+		for (mpgos_coupled_solver* c : s->shards)
+		{
+			CUDA_TRY(cudaSetDevice(c->desc.Device));
+			CUDA_TRY(cudaEventRecord(c->t0, c->stream));
+			for (int p = 0; p < phases; p++) { const int rc = mpgos_coupled_solve(c, launcher);  if (rc != MPGOS_OK) return rc; }
+			CUDA_TRY(cudaEventRecord(c->t1, c->stream));
+		}
+		*elapsed_ms = 0;
+		for (mpgos_coupled_solver* c : s->shards)
+		{
+			float ms = 0;
+			CUDA_TRY(cudaSetDevice(c->desc.Device));
+			CUDA_TRY(cudaEventSynchronize(c->t1));
+			CUDA_TRY(cudaEventElapsedTime(&ms, c->t0, c->t1));
+			if (ms > *elapsed_ms) *elapsed_ms = ms;
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	mpgos_coupled_launch L;
 	cfill(s, L);
@@ -337,13 +534,49 @@ int mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher la
 	return MPGOS_OK;
 }
 
-int mpgos_coupled_insert_sync_point(mpgos_coupled_solver* s) { if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver"); CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaEventRecord(s->event, s->stream)); return MPGOS_OK; }
-int mpgos_coupled_sync_solver(mpgos_coupled_solver* s) { if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver"); CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaEventSynchronize(s->event)); return MPGOS_OK; }
-int mpgos_coupled_sync_device(mpgos_coupled_solver* s) { if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver"); CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaDeviceSynchronize()); return MPGOS_OK; }
+int mpgos_coupled_insert_sync_point(mpgos_coupled_solver* s)
+{
+	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_insert_sync_point(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
+	CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaEventRecord(s->event, s->stream));
+	return MPGOS_OK;
+}
+int mpgos_coupled_sync_solver(mpgos_coupled_solver* s)
+{
+	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_sync_solver(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
+	CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaEventSynchronize(s->event));
+	return MPGOS_OK;
+}
+int mpgos_coupled_sync_device(mpgos_coupled_solver* s)
+{
+	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_sync_device(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
+	CUDA_TRY(cudaSetDevice(s->desc.Device)); CUDA_TRY(cudaDeviceSynchronize());
+	return MPGOS_OK;
+}
 
 int mpgos_coupled_read_step_counters(mpgos_coupled_solver* s, unsigned long long* attempted, unsigned long long* accepted)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty())
+	{
+		std::vector<unsigned long long> a, b;
+		for (size_t k = 0; k < s->shards.size(); k++)
+		{
+			mpgos_coupled_solver* c = s->shards[k];
+			a.resize(c->desc.NS);  b.resize(c->desc.NS);
+			const int rc = mpgos_coupled_read_step_counters(c, attempted ? a.data() : nullptr, accepted ? b.data() : nullptr);
+			if (rc != MPGOS_OK) return rc;
+			for (int i = 0; i < c->desc.NS; i++)
+			{
+				const long long g = cshard_global_id(s->tile, (int)s->shards.size(), (int)k, i);
+				if (attempted) attempted[g] = a[i];
+				if (accepted)  accepted[g] = b[i];
+			}
+		}
+		return MPGOS_OK;
+	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	const size_t bytes = 8 * (size_t)s->desc.NS;
 	if (attempted) CUDA_TRY(cudaMemcpyAsync(attempted, s->d_attempted, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -355,6 +588,7 @@ int mpgos_coupled_read_step_counters(mpgos_coupled_solver* s, unsigned long long
 int mpgos_coupled_reset_step_counters(mpgos_coupled_solver* s)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_reset_step_counters(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	CUDA_TRY(cudaMemsetAsync(s->d_attempted, 0, 8 * (size_t)s->desc.NS, s->stream));
 	CUDA_TRY(cudaMemsetAsync(s->d_accepted, 0, 8 * (size_t)s->desc.NS, s->stream));
@@ -367,6 +601,7 @@ static const int kCState[] = { MPGOS_CVAR_TimeDomain, MPGOS_CVAR_ActualTime, MPG
 int mpgos_coupled_save_state(mpgos_coupled_solver* s)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_save_state(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	for (int v : kCState)
 	{
@@ -381,6 +616,7 @@ int mpgos_coupled_save_state(mpgos_coupled_solver* s)
 int mpgos_coupled_restore_state(mpgos_coupled_solver* s)
 {
 	if (!s) return CFAIL(MPGOS_ERR_ARGUMENT, "null solver");
+	if (!s->shards.empty()) { for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_restore_state(c);  if (rc != MPGOS_OK) return rc; }  return MPGOS_OK; }
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
 	for (int v : kCState)
 	{
@@ -393,7 +629,7 @@ int mpgos_coupled_restore_state(mpgos_coupled_solver* s)
 	return MPGOS_OK;
 }
 
-void* mpgos_coupled_stream(mpgos_coupled_solver* s) { return s ? (void*)s->stream : nullptr; }
+void* mpgos_coupled_stream(mpgos_coupled_solver* s) { return !s ? nullptr : (s->shards.empty() ? (void*)s->stream : (void*)s->shards[0]->stream); }
 
 int mpgos_coupled_builtin_desc(const char* system, int ups, int cbw, int cci, mpgos_coupled_desc* desc)
 {

@@ -81,12 +81,15 @@ ABI_SYMBOLS = (
     "mpgos_perthread_builtin_count", "mpgos_perthread_builtin_name", "mpgos_perthread_builtin_desc",
     "mpgos_perthread_builtin_launcher", "mpgos_probe_fma_peak", "mpgos_perthread_save_state", "mpgos_perthread_restore_state",
     "mpgos_perthread_upload", "mpgos_perthread_download", "mpgos_probe_dmma_peak",
+    "mpgos_perthread_create_sharded", "mpgos_perthread_shard_count", "mpgos_perthread_shard_info", "mpgos_perthread_shard_global_id",
+    "mpgos_shard_instances", "mpgos_shard_global_id",
 )
 
 
 class _Desc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("NT", "SD", "NCP", "NSP", "NISP", "NE", "NA", "NIA", "NDO", "Algorithm",
-                                        "PrecisionBytes", "Device", "InstanceOffset", "GlobalInstances")]
+                                        "PrecisionBytes", "Device", "InstanceOffset", "GlobalInstances",
+                                        "ShardIndex", "ShardCount", "ShardTile")]
 
 
 def library_path(strict: bool = False) -> str:
@@ -148,6 +151,13 @@ def load_library(strict: bool = False):
     lib.mpgos_probe_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     if hasattr(lib, "mpgos_probe_dmma_peak"):      # absent from A/B builds of older revisions (MPGOS_B200_LIBRARY)
         lib.mpgos_probe_dmma_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    if hasattr(lib, "mpgos_perthread_create_sharded"):
+        lib.mpgos_perthread_create_sharded.argtypes = [C.POINTER(_Desc), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        lib.mpgos_perthread_shard_count.argtypes = [C.c_void_p]
+        lib.mpgos_perthread_shard_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.mpgos_perthread_shard_global_id.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib.mpgos_shard_instances.argtypes = [C.c_int] * 4
+        lib.mpgos_shard_global_id.argtypes = [C.c_int] * 4
     _LIBS[strict] = lib
     return lib
 
@@ -179,7 +189,11 @@ class ProblemSolver:
     arguments, everything else keeps the reference's names."""
 
     def __init__(self, system: str, NT: int, NDO: int = 0, Algorithm: int = Algorithms.RKCK45, Precision=np.float64,
-                 Device: int = 0, InstanceOffset: int = 0, GlobalInstances: int = 0, strict: bool = False):
+                 Device: int = 0, InstanceOffset: int = 0, GlobalInstances: int = 0, strict: bool = False,
+                 Devices=None, Tile: int = 0):
+        """``Devices`` (a list of device ordinals): ONE solver object over several devices of the node -- the sweep is dealt to them
+        in tiles of ``Tile`` instances, everything else (host mirrors in the sweep's layout, SetHost/GetHost, synchronisation,
+        Solve) stays as for one device (mpgos_perthread_create_sharded)."""
         self._lib = lib = load_library(strict)
         self._h = None
         self.system = system
@@ -193,7 +207,11 @@ class ProblemSolver:
         if not self._launcher:
             raise MpgosError(lib.mpgos_last_error().decode())
         h = C.c_void_p()
-        _check(lib, lib.mpgos_perthread_create(C.byref(d), C.byref(h)))
+        if Devices is not None:
+            devs = (C.c_int * len(Devices))(*[int(x) for x in Devices])
+            _check(lib, lib.mpgos_perthread_create_sharded(C.byref(d), devs, len(Devices), int(Tile), C.byref(h)))
+        else:
+            _check(lib, lib.mpgos_perthread_create(C.byref(d), C.byref(h)))
         self._h = h
         self._views: Dict[int, np.ndarray] = {}
 
@@ -427,12 +445,13 @@ def read_back(ps: ProblemSolver, wl):
 
 
 def run_workload(wl, buffers=None, phases: Optional[int] = None, lane_refill: Optional[bool] = None, device: int = 0,
-                 threads_per_block: Optional[int] = None, strict: bool = False):
+                 threads_per_block: Optional[int] = None, strict: bool = False, devices=None, tile: int = 0):
     """Integrate a workload on the GPU through the public API; returns (buffers_after, attempted, accepted)
     with the same meaning as the checker's ``run_oracle`` / ``run_ref``."""
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
-    with ProblemSolver(wl.name, b.NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=device, strict=strict) as ps:
+    with ProblemSolver(wl.name, b.NT, NDO=sh.NDO, Algorithm=sh.Algorithm, Precision=sh.dtype, Device=device, strict=strict,
+                       Devices=devices, Tile=tile) as ps:
         apply_workload(ps, wl, b)
         if lane_refill is not None:
             ps.SolverOption(Options.LaneRefill, int(lane_refill))

@@ -60,13 +60,14 @@ COUPLED_ABI_SYMBOLS = (
     "mpgos_coupled_solve_timed", "mpgos_coupled_insert_sync_point", "mpgos_coupled_sync_solver", "mpgos_coupled_sync_device",
     "mpgos_coupled_read_step_counters", "mpgos_coupled_reset_step_counters", "mpgos_coupled_save_state", "mpgos_coupled_restore_state",
     "mpgos_coupled_stream", "mpgos_coupled_builtin_desc", "mpgos_coupled_builtin_launcher", "mpgos_coupled_builtin_launcher_p",
-    "mpgos_coupled_upload", "mpgos_coupled_download",
+    "mpgos_coupled_upload", "mpgos_coupled_download", "mpgos_coupled_create_sharded", "mpgos_coupled_shard_count",
 )
 
 
 class _CDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("NS", "UPS", "UD", "TPB", "SPB", "NC", "CBW", "CCI", "NUP", "NSP", "NGP", "NiGP", "NUA", "NiUA", "NSA", "NiSA",
-                                        "NE", "NDO", "Algorithm", "PrecisionBytes", "Device", "SystemOffset")]
+                                        "NE", "NDO", "Algorithm", "PrecisionBytes", "Device", "SystemOffset",
+                                        "ShardIndex", "ShardCount", "ShardTile")]
 
 
 _BOUND = False
@@ -78,6 +79,8 @@ def _bind(lib):
         return
     v = C.c_void_p
     lib.mpgos_coupled_create.argtypes = [C.POINTER(_CDesc), C.POINTER(v)]
+    lib.mpgos_coupled_create_sharded.argtypes = [C.POINTER(_CDesc), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(v)]
+    lib.mpgos_coupled_shard_count.argtypes = [v]
     lib.mpgos_coupled_destroy.argtypes = [v]
     lib.mpgos_coupled_host_ptr.restype = v
     lib.mpgos_coupled_host_ptr.argtypes = [v, C.c_int, C.POINTER(C.c_size_t)]
@@ -108,7 +111,8 @@ class CoupledProblemSolver:
     """``ProblemSolver<NS,UPS,UD,TPB,SPB,NC,CBW,CCI,NUP,...,Algorithm,Precision>`` for a built-in coupled system."""
 
     def __init__(self, system: str, NS: int, UPS: int, CBW: int = 0, CCI: int = 0, NDO: int = 0, Algorithm: int = 1,
-                 Device: int = 0, TPB: int = 64, SPB: int = 1, SystemOffset: int = 0, Precision=np.float64):
+                 Device: int = 0, TPB: int = 64, SPB: int = 1, SystemOffset: int = 0, Precision=np.float64, Devices=None, Tile: int = 0):
+        """``Devices``: one solver object over several devices (systems dealt out in tiles of ``Tile``; mpgos_coupled_create_sharded)."""
         self._lib = lib = load_library()
         _bind(lib)
         self._h = None
@@ -121,7 +125,11 @@ class CoupledProblemSolver:
         if not self._launcher:
             raise MpgosError(lib.mpgos_last_error().decode())
         h = C.c_void_p()
-        _check(lib, lib.mpgos_coupled_create(C.byref(d), C.byref(h)))
+        if Devices is not None:
+            devs = (C.c_int * len(Devices))(*[int(x) for x in Devices])
+            _check(lib, lib.mpgos_coupled_create_sharded(C.byref(d), devs, len(Devices), int(Tile), C.byref(h)))
+        else:
+            _check(lib, lib.mpgos_coupled_create(C.byref(d), C.byref(h)))
         self._h = h
         self._views: Dict[int, np.ndarray] = {}
 
@@ -288,12 +296,12 @@ def read_back_coupled(ps: CoupledProblemSolver, wl):
 
 
 def run_coupled_workload(wl, buffers=None, phases: Optional[int] = None, device: int = 0, tensor_core_coupling: Optional[int] = None,
-                         dispatch_order: Optional[int] = None):
+                         dispatch_order: Optional[int] = None, devices=None, tile: int = 0):
     """Integrate a coupled workload on the GPU through the public API; returns (buffers_after, attempted, accepted)."""
     b = wl.buffers if buffers is None else buffers
     sh = wl.shape
     with CoupledProblemSolver(wl.name, b.NS, sh.UPS, CBW=sh.CBW, CCI=sh.CCI, NDO=sh.NDO, Algorithm=sh.Algorithm, Device=device,
-                              TPB=sh.TPB, SPB=sh.SPB, Precision=sh.dtype) as ps:
+                              TPB=sh.TPB, SPB=sh.SPB, Precision=sh.dtype, Devices=devices, Tile=tile) as ps:
         apply_coupled_workload(ps, wl, b)
         if tensor_core_coupling is not None:
             ps.SolverOption(CoupledOptions.TensorCoreCoupling, tensor_core_coupling)

@@ -277,6 +277,16 @@ def keller_miksis_t5(NT: int = 1 << 18, phases: int = 32, ndo: int = 200) -> Wor
     return Workload(name, shape, opt, b, phases, 413, "T5 Keller-Miksis frequency sweep")
 
 
+def tidprobe(NT: int = 4096, algorithm: int = RKCK45) -> Workload:
+    """Test system "tidprobe" (csrc/builtin_systems.cuh): x' = k (tid / NT - x); accessories record the id and NT the callbacks saw."""
+    shape = Shape(SD=1, NCP=1, NA=1, NIA=2, Algorithm=algorithm)
+    b = Buffers(shape, NT)
+    b.TimeDomain[1, :] = 3.0
+    b.ActualState[0, :] = linspace(-1.0, 1.0, NT)
+    b.ControlParameters[0, :] = linspace(0.5, 4.0, NT)
+    return Workload("tidprobe", shape, Options(InitialTimeStep=1e-2), b, 1, 0, "instance-id probe")
+
+
 def vanderpol_example(NT: int = 1536, algorithm: int = RKCK45, phases: int = 2) -> Workload:
     """The user-written system of examples/vanderpol (drop-in test; not a BASELINE configuration):
     same options and initial data as examples/vanderpol/vanderpol_dropin.cu."""
