@@ -19,6 +19,7 @@ static const BuiltinEntry kEntries[] = {
 	MPGOS_BUILTIN_ENTRY("impact", Impact, double, kAlgRKCK45, false, MPGOS_MINB_IMPACT),
 	MPGOS_BUILTIN_ENTRY("impact", Impact, double, kAlgRK4, false, MPGOS_MINB_IMPACT),
 	MPGOS_BUILTIN_ENTRY("impact", Impact, float, kAlgRKCK45, false, MPGOS_MINB_IMPACT_F32),
+	MPGOS_BUILTIN_ENTRY("impact", Impact, double, kAlgRKCK45, true, MPGOS_MINB_IMPACT),      // with dense output: lanes drift apart at the impacts (store-efficiency probe)
 };
 const BuiltinEntry* builtin_entries_impact(int* n) { *n = (int)(sizeof(kEntries) / sizeof(kEntries[0])); return kEntries; }
 }

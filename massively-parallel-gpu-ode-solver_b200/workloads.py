@@ -222,10 +222,10 @@ def poincare_t3(NT: int = 10000, algorithm: int = RK4, phases: int = 8) -> Workl
     return Workload("poincare", shape, opt, b, phases, flops, "T3 Duffing without events")
 
 
-def impact_t6(NT: int = 1 << 20, phases: int = 128) -> Workload:
+def impact_t6(NT: int = 1 << 20, phases: int = 128, ndo: int = 0) -> Workload:
     """C3: T6_ImpactDynamics/ImpactDynamics.cu:38,58-66,166-186 -- pressure relief valve with
     impact law; q = Linspace(0.2, 10, NT); each phase ends at the first Poincare crossing."""
-    shape = Shape(SD=3, NCP=1, NSP=4, NE=2, NA=3, NIA=2, Algorithm=RKCK45)
+    shape = Shape(SD=3, NCP=1, NSP=4, NE=2, NA=3, NIA=2, NDO=ndo, Algorithm=RKCK45)      # ndo > 0: not a tutorial setting (store-efficiency probe)
     b = Buffers(shape, NT)
     b.TimeDomain[0, :] = 0.0
     b.TimeDomain[1, :] = 1.0e10
