@@ -57,6 +57,9 @@ WORKLOADS = {
     "kellermiksis_dense": ("perthread", "configs[3] T5 Keller-Miksis + dense output (200 points)", 1 << 18, 413, "RKCK45"),
     "duffing":            ("perthread", "configs[0] T1_Reference Duffing, RK4", 10000, 58, "RK4"),
     "coupled":            ("coupled", "configs[4] T2_BubbleEnsemble, 64 units, dense coupling matrix", 8192, 78857, "RKCK45"),
+    # the same two configurations with the opt-in transcendentals of include/mpgos_b200/fast_math.cuh (pow / sincospi / sin / cos <= 3 ulp)
+    "kellermiksis_dense_fm": ("perthread", "configs[3] T5 Keller-Miksis + dense output, opt-in fast_math.cuh transcendentals", 1 << 18, 413, "RKCK45"),
+    "coupled_fm":         ("coupled", "configs[4] T2_BubbleEnsemble, 64 units, opt-in fast_math.cuh transcendentals", 8192, 78857, "RKCK45"),
 }
 COUPLED_TILE = 64
 
@@ -66,8 +69,8 @@ def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int
     W = pkg.workloads
     sharding = importlib.import_module(pkg.__name__ + ".sharding")
     dtype = np.float64 if precision == "f64" else np.float32
-    if name == "coupled":
-        full = pkg.workloads_coupled.bubble_ensemble(NS=n * world, UPS=64, dtype=dtype)
+    if name in ("coupled", "coupled_fm"):
+        full = pkg.workloads_coupled.bubble_ensemble(NS=n * world, UPS=64, dtype=dtype, fast_math=name.endswith("_fm"))
         if world > 1:
             import copy
             wl = copy.copy(full)
@@ -80,6 +83,7 @@ def build_workload(pkg, name: str, precision: str, n: int, rank: int, world: int
            "impact": lambda m: single(W.impact_t6(NT=m)),
            "kellermiksis": lambda m: single(W.keller_miksis_t5(NT=m, ndo=0)),
            "kellermiksis_dense": lambda m: single(W.keller_miksis_t5(NT=m, ndo=200)),
+           "kellermiksis_dense_fm": lambda m: W.keller_miksis_t5(NT=m, ndo=200, fast_math=True),
            "duffing": lambda m: single(W.duffing_t1(NT=m, algorithm=W.RK4))}[name]
     tile = sharding.TILE if n % sharding.TILE == 0 else 1
     return sharding.shard_workload(gen(n * world), n, rank, world, tile)
@@ -147,6 +151,8 @@ def cpu_reference_run(pkg, name: str, precision: str, sample: int, threads: int,
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py
+    if name.endswith("_fm"):       # the baselines run the system as the reference defines it (CUDA / C math library)
+        name = name[:-3]
     n_full = WORKLOADS[name][2]
     full = build_workload(pkg, name, precision, n_full, 0, 1)
     if name == "coupled":
@@ -236,6 +242,8 @@ EXTRA_CONFIGS = (      # key, workload, precision, phases per step  -- run after
     ("C3_impact_rkck45_f64", "impact", "f64", 8),
     ("C4_kellermiksis_dense_rkck45_f64", "kellermiksis_dense", "f64", 2),
     ("C5_coupled_bubbles_rkck45_f64", "coupled", "f64", 1),
+    ("C4_kellermiksis_dense_fastmath", "kellermiksis_dense_fm", "f64", 2),
+    ("C5_coupled_bubbles_fastmath", "coupled_fm", "f64", 1),
 )
 
 
@@ -245,6 +253,10 @@ def reference_gpu_baseline(kind, wl, N, precision, phases, per_rank_attempted_pe
     over 64 / 128 / 256 threads per block; the best setting is the baseline, every setting tried is listed."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
+    if wl.name.endswith("_fm"):      # the reference has one form of the system: its own, on the CUDA math library
+        import copy
+        wl = copy.copy(wl)
+        wl.name = wl.name[:-3]
     tried = {}
     if kind == "coupled":
         if not (N == 8192 and precision == "f64"):
@@ -479,7 +491,8 @@ def measure(pkg, args, workload, precision, N, phases, steps, warmup, rank, loca
                 sample = args.cpu_sample or {"coupled": 512 if big else 128, "kellermiksis": 1 << 15, "kellermiksis_dense": 1 << 15,
                                              "duffing": 10000, "impact": 1 << 17 if big else 1 << 15}.get(workload, 1 << 19 if big else 1 << 17)
             else:       # the extra configurations: a couple of seconds each
-                sample = {"coupled": 256 if big else 64, "kellermiksis_dense": 1 << 14, "duffing": 10000, "impact": 1 << 15}.get(workload, 1 << 17)
+                sample = {"coupled": 256 if big else 64, "coupled_fm": 256 if big else 64, "kellermiksis_dense": 1 << 14, "kellermiksis_dense_fm": 1 << 14,
+                          "duffing": 10000, "impact": 1 << 15}.get(workload, 1 << 17)
             sample = min(sample, N)
             n, s, kind_cpu, nt = cpu_reference_run(pkg, workload, precision, sample, threads, phases)
             out["cpu_baseline"] = {"value": n / s, "unit": "system-steps/s", "cores": threads, "kind": kind_cpu,

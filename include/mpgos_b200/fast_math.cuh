@@ -1,0 +1,259 @@
+// fast_math.cuh -- opt-in replacements for the double-precision transcendentals that dominate transcendental-heavy right-hand
+// sides on sm_100a (Keller-Miksis: pow + sincospi + sin + cos are ~80 % of a step's issue slots; 17 % of the executed
+// instructions are UMOV pairs that rebuild the CUDA math library's FP64 literals, because FP64 instructions take constants only
+// from the 63 uniform registers).
+//
+//   mpgos_b200::fm::sincos / sin / cos (double)   <= 1.5 ulp for |x| <= 1e6, the CUDA function beyond that and for NaN / Inf
+//   mpgos_b200::fm::sincospi (double)             <= 1.7 ulp for |x| <= 2^30, the CUDA function beyond
+//   mpgos_b200::fm::pow (double, double)          <= 3 ulp for normal positive finite x and |y log2 x| <= 1000, the CUDA function otherwise
+//                                                 (x <= 0, subnormal, Inf, NaN, over/underflowing results: all special cases are CUDA's)
+//   (errors measured against 200-bit references over the ranges of tests/test_fast_math_gpu.py; CUDA's own: sin/cos/sincospi/pow <= 2 ulp)
+//
+// What makes them cheap here: coefficient tables in __constant__ memory (one LDCU per one or two constants instead of two UMOVs per
+// literal), range reduction by adding and subtracting 1.5 * 2^52 (the integer part falls out of the low mantissa word: no FRND,
+// F2I or I2F on the FP64 pipe), no Payne-Hanek path and no double-double logarithm: pow forms y * log2(x) as a compensated
+// product of two doubles, which is enough for 3 ulp at |y log2 x| <= 1000, where CUDA's accurate pow spends ~80 FP64 instructions.
+// Instruction counts (sm_100a, per call): pow ~50 FP64 + ~15 other against ~95 + ~130; sincos ~24 + ~10 against ~50 + ~100 for
+// sin + cos of the same argument; sincospi ~23 + ~10 against ~25 + ~50.
+//
+// OPT-IN.  Nothing in the library uses these unless asked to: the built-in systems exist in both forms ("kellermiksis" /
+// "kellermiksis_fm", ...), and a user translation unit redirects the calls of its UNMODIFIED *_SystemDefinition.cuh by defining
+// MPGOS_B200_FAST_MATH before including this header ahead of the system definition (or with nvcc -include):
+//     #define MPGOS_B200_FAST_MATH
+//     #include "mpgos_b200/fast_math.cuh"
+//     #include "KellerMiksis_SystemDefinition.cuh"
+//     #include "SingleSystem_PerThread_Interface.cuh"
+// Single-precision calls are passed on to the CUDA functions unchanged.
+#ifndef MPGOS_B200_FAST_MATH_CUH
+#define MPGOS_B200_FAST_MATH_CUH
+
+#include <cuda_runtime.h>
+#include <math.h>
+#ifdef MPGOS_B200_FAST_MATH
+// everything the interface headers include, before the names below become macros
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <type_traits>
+#include <vector>
+#endif
+
+namespace mpgos_b200 {
+namespace fm {
+
+// The coefficient table, in the order of use and in PAIRS: every load below is a volatile 16-byte constant load (LDCU.128: two
+// doubles straight into uniform registers, where FP64 instructions take them from).  Volatile, because the compiler would otherwise
+// hoist all ~45 constants out of the caller's step loop, run out of the 63 uniform registers, park the rest in vector registers
+// (spilling some) and move them back with two R2UR per constant and use -- measured on the Keller-Miksis kernel: 220 R2UR, 127 LDC
+// and 49 local-memory loads per step.
+enum FmPair
+{
+	FM_S6C6, FM_S5C5, FM_S4C4, FM_S3C3, FM_S2C2, FM_S1C1,     // sin(r) = r + r^3 (S1 + r^2 (S2 + ...)), cos(r) = 1 - r^2/2 + r^4 (C1 + r^2 (C2 + ...)), |r| <= pi/4
+	FM_2OPI_PIO2A, FM_PIO2B_PIO2C,                            // 2/pi and pi/2 in three parts (Cody-Waite with FMA)
+	FM_PIHI_PILO,
+	FM_LG6_LG7, FM_LG4_LG5, FM_LG2_LG3, FM_LG1_L2EH,          // log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f / (2 + f); log2(e) hi
+	FM_L2EL_LN2H, FM_LN2L_E13,                                // log2(e) lo, ln 2 hi / lo
+	FM_E12_E11, FM_E10_E9, FM_E8_E7, FM_E6_E5, FM_E4_E3, FM_E2_PAD,      // e^t = 1 + t + t^2/2! + ... + t^13/13!, |t| <= ln2/2
+	FM_PAIRS
+};
+
+static __constant__ __align__(16) double kFm[2 * FM_PAIRS] = {
+	1.58969099521155010221e-10, -1.13596475577881948265e-11,   -2.50507602534068634195e-08, 2.08757232129817482790e-09,
+	2.75573137070700676789e-06, -2.75573143513906633035e-07,   -1.98412698298579493134e-04, 2.48015872894767294178e-05,
+	8.33333333332248946124e-03, -1.38888888888741095749e-03,   -1.66666666666666324348e-01, 4.16666666666666019037e-02,
+	0.6366197723675814, 1.5707963267948966,                    6.123233995736766e-17, -1.4973849048591698e-33,
+	3.141592653589793, 1.2246467991473532e-16,
+	1.531383769920937332e-01, 1.479819860511658591e-01,        2.222219843214978396e-01, 1.818357216161805012e-01,
+	3.999999999940941908e-01, 2.857142874366239149e-01,        6.666666666666735130e-01, 1.4426950408889634,
+	2.0355273740931033e-17, 0.6931471805599453,                2.3190468138462996e-17, 1.0 / 6227020800.0,
+	1.0 / 479001600.0, 1.0 / 39916800.0,                       1.0 / 3628800.0, 1.0 / 362880.0,
+	1.0 / 40320.0, 1.0 / 5040.0,                               1.0 / 720.0, 1.0 / 120.0,
+	1.0 / 24.0, 1.0 / 6.0,                                     1.0 / 2.0, 0.0
+};
+
+__device__ __forceinline__ void ldpair(int pair, double& a, double& b)
+{
+	asm volatile("ld.const.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(__cvta_generic_to_constant(&kFm[2 * pair])));
+}
+
+// the CUDA functions, out of line: taken only outside the ranges stated above, and kept out of the callers' loop bodies
+static __device__ __noinline__ void   cuda_sincos(double x, double* s, double* c)   { ::sincos(x, s, c); }      // [cold>
+static __device__ __noinline__ void   cuda_sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
+static __device__ __noinline__ double cuda_pow(double x, double y)                  { return ::pow(x, y); }     // <cold]
+
+// The three functions are real subroutines by default (MPGOS_B200_FM_INLINE 0).  Inlined into a step loop, their ~45 constants are
+// loop invariants: the compiler hoists the loads, runs out of the 63 uniform registers, parks the rest in vector registers and moves
+// them back with two R2UR per constant and use (measured on the Keller-Miksis kernel: 240 R2UR + 63 LDC + 47 local-memory loads per
+// step, 188 bytes of spill).  A subroutine has no loop to hoist out of: every pair of constants is one LDCU.128 where it is used, and
+// the six right-hand-side evaluations of a step share one copy of the code.
+#ifndef MPGOS_B200_FM_INLINE
+#define MPGOS_B200_FM_INLINE 0
+#endif
+#if MPGOS_B200_FM_INLINE
+#define MPGOS_FM_FN static __device__ __forceinline__
+#else
+#define MPGOS_FM_FN static __device__ __noinline__
+#endif
+
+// 1.5 * 2^52: x + kMagic - kMagic rounds x to the nearest integer (|x| < 2^51), and the low mantissa word of x + kMagic holds that
+// integer in two's complement
+#define MPGOS_FM_MAGIC 6755399441055744.0
+
+// sin and cos of r, |r| <= pi/4 (the polynomials of fdlibm's __kernel_sin / __kernel_cos), then the quadrant q (0..3):
+// (sin, cos)(r + q pi/2); sign changes on the words that hold the sign
+struct SinCos { double s, c; };      // returned by value: in registers across the subroutine boundary
+
+__device__ __forceinline__ SinCos kernel_sincos(double r, int q)
+{
+	const double z = r * r;
+	double ps, pc, a, b;
+	ldpair(FM_S6C6, ps, pc);
+	ldpair(FM_S5C5, a, b);  ps = fma(ps, z, a);  pc = fma(pc, z, b);
+	ldpair(FM_S4C4, a, b);  ps = fma(ps, z, a);  pc = fma(pc, z, b);
+	ldpair(FM_S3C3, a, b);  ps = fma(ps, z, a);  pc = fma(pc, z, b);
+	ldpair(FM_S2C2, a, b);  ps = fma(ps, z, a);  pc = fma(pc, z, b);
+	ldpair(FM_S1C1, a, b);  ps = fma(ps, z, a);  pc = fma(pc, z, b);
+	const double s = fma(r * z, ps, r);
+	const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+	const bool odd = (q & 1) != 0;
+	const double u = odd ? c : s, v = odd ? s : c;
+	const unsigned flip_s = (unsigned)(q & 2) << 30, flip_c = (unsigned)((q + 1) & 2) << 30;
+	SinCos out;
+	out.s = __hiloint2double((int)((unsigned)__double2hiint(u) ^ flip_s), __double2loint(u));
+	out.c = __hiloint2double((int)((unsigned)__double2hiint(v) ^ flip_c), __double2loint(v));
+	return out;
+}
+
+MPGOS_FM_FN SinCos sincos_core(double x)
+{
+	double two_over_pi, p1, p2, p3;
+	ldpair(FM_2OPI_PIO2A, two_over_pi, p1);
+	ldpair(FM_PIO2B_PIO2C, p2, p3);
+	const double t = fma(x, two_over_pi, MPGOS_FM_MAGIC);
+	const double n = t - MPGOS_FM_MAGIC;
+	double r = fma(-n, p1, x);
+	r = fma(-n, p2, r);
+	r = fma(-n, p3, r);
+	SinCos out = kernel_sincos(r, __double2loint(t) & 3);
+	if (!(fabs(x) <= 1.0e6)) cuda_sincos(x, &out.s, &out.c);           // large arguments, NaN, Inf: the CUDA function
+	return out;
+}
+__device__ __forceinline__ void sincos(double x, double* sn, double* cs) { const SinCos r = sincos_core(x); *sn = r.s; *cs = r.c; }
+__device__ __forceinline__ double sin(double x) { double s, c; mpgos_b200::fm::sincos(x, &s, &c); return s; }
+__device__ __forceinline__ double cos(double x) { double s, c; mpgos_b200::fm::sincos(x, &s, &c); return c; }
+
+MPGOS_FM_FN SinCos sincospi_core(double x)
+{
+	double pi_hi, pi_lo;
+	ldpair(FM_PIHI_PILO, pi_hi, pi_lo);
+	const double t = fma(x, 2.0, MPGOS_FM_MAGIC);
+	const double n = t - MPGOS_FM_MAGIC;
+	const double r = fma(n, -0.5, x);                     // exact: |r| <= 1/4
+	SinCos out = kernel_sincos(fma(r, pi_lo, r * pi_hi), __double2loint(t) & 3);
+	if (!(fabs(x) <= 1073741824.0)) cuda_sincospi(x, &out.s, &out.c);
+	return out;
+}
+__device__ __forceinline__ void sincospi(double x, double* sn, double* cs) { const SinCos r = sincospi_core(x); *sn = r.s; *cs = r.c; }
+
+// x^y for normal positive finite x and moderate |y log2 x|; everything else (including every special case of the C standard) is
+// the CUDA function's.  Straight-line: the fast path is computed unconditionally (on operands outside its range it produces
+// garbage, never a fault) and replaced at the end.
+MPGOS_FM_FN double pow(double x, double y)
+{
+	const int hx = __double2hiint(x);
+	// x = 2^e m, m in [sqrt(1/2), sqrt(2))
+	const int h2 = hx + (0x3ff00000 - 0x3fe6a09e);
+	const int e = (h2 >> 20) - 0x3ff;
+	const double m = __hiloint2double((h2 & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+	const double ke = __hiloint2double(0x43300000, 0x80000000 ^ e) - 4503601774854144.0;      // (double)e without I2F: 2^52 + 2^31 subtracted
+	// log(m): s = f / (2 + f), the reciprocal by two Newton steps on the hardware's ~20-bit one
+	const double f = m - 1.0;
+	const double den = 2.0 + f;
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));      // MUFU.RCP64H
+	r = fma(r, fma(-den, r, 1.0), r);
+	r = fma(r, fma(-den, r, 1.0), r);
+	const double s = f * r;
+	const double z = s * s, w = z * z;
+	double lg6, lg7, lg4, lg5, lg2, lg3, lg1, l2e_hi, l2e_lo, ln2_hi, ln2_lo, c13, a, b;
+	ldpair(FM_LG6_LG7, lg6, lg7);
+	ldpair(FM_LG4_LG5, lg4, lg5);
+	ldpair(FM_LG2_LG3, lg2, lg3);
+	ldpair(FM_LG1_L2EH, lg1, l2e_hi);
+	const double t1 = w * fma(w, fma(w, lg6, lg4), lg2);
+	const double t2 = z * fma(w, fma(w, fma(w, lg7, lg5), lg3), lg1);
+	const double hfsq = 0.5 * f * f;
+	const double logm = f - (hfsq - s * (hfsq + (t2 + t1)));
+	// log2(x) = e + logm * log2(e) as hi + lo, z = y * log2(x) as zh + zl
+	ldpair(FM_L2EL_LN2H, l2e_lo, ln2_hi);
+	const double hi = fma(logm, l2e_hi, ke);
+	double lo = fma(logm, l2e_hi, ke - hi);
+	lo = fma(logm, l2e_lo, lo);
+	const double zh = y * hi;
+	const double zl = fma(y, lo, fma(y, hi, -zh));
+	// 2^zh = 2^n e^t
+	const double tn = zh + MPGOS_FM_MAGIC;
+	const double n = tn - MPGOS_FM_MAGIC;
+	const double g = zh - n;
+	ldpair(FM_LN2L_E13, ln2_lo, c13);
+	const double t = fma(g, ln2_lo, g * ln2_hi);
+	double p = c13;
+	ldpair(FM_E12_E11, a, b);  p = fma(p, t, a);  p = fma(p, t, b);
+	ldpair(FM_E10_E9, a, b);   p = fma(p, t, a);  p = fma(p, t, b);
+	ldpair(FM_E8_E7, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
+	ldpair(FM_E6_E5, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
+	ldpair(FM_E4_E3, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
+	p = fma(p, t, 0.5);
+	p = fma(p, t, 1.0);        p = fma(p, t, 1.0);
+	p = fma(p, zl * ln2_hi, p);                                                   // e^(zl ln 2) = 1 + zl ln 2
+	p = p * __hiloint2double((__double2loint(tn) + 1023) << 20, 0);
+	// zero, subnormal, negative, Inf, NaN base; overflow, underflow, y = NaN / Inf
+	if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u || !(fabs(zh) <= 1000.0)) p = cuda_pow(x, y);
+	return p;
+}
+
+// single precision: the CUDA functions
+__device__ __forceinline__ void  sincos(float x, float* s, float* c)   { ::sincosf(x, s, c); }
+__device__ __forceinline__ float sin(float x)                          { return ::sinf(x); }
+__device__ __forceinline__ float cos(float x)                          { return ::cosf(x); }
+__device__ __forceinline__ void  sincospi(float x, float* s, float* c) { ::sincospif(x, s, c); }
+__device__ __forceinline__ float pow(float x, float y)                 { return ::powf(x, y); }
+
+// compile-time choice between these functions and CUDA's, for code that exists in both forms (the built-in systems)
+template <bool FAST> struct Math
+{
+	template <class P> static __device__ __forceinline__ P    pow_(P x, P y)               { return mpgos_b200::fm::pow(x, y); }
+	template <class P> static __device__ __forceinline__ P    sin_(P x)                    { return mpgos_b200::fm::sin(x); }
+	template <class P> static __device__ __forceinline__ P    cos_(P x)                    { return mpgos_b200::fm::cos(x); }
+	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { mpgos_b200::fm::sincospi(x, s, c); }
+	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { mpgos_b200::fm::sincos(x, s, c); }      // one evaluation for both
+};
+template <> struct Math<false>
+{
+	template <class P> static __device__ __forceinline__ P    pow_(P x, P y)               { return ::pow(x, y); }
+	template <class P> static __device__ __forceinline__ P    sin_(P x)                    { return ::sin(x); }
+	template <class P> static __device__ __forceinline__ P    cos_(P x)                    { return ::cos(x); }
+	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { ::sincospi(x, s, c); }
+	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { *s = ::sin(x);  *c = ::cos(x); }         // the reference's two calls
+};
+
+} // namespace fm
+} // namespace mpgos_b200
+
+// Redirection for an unmodified system definition (see the header comment).  Function-like macros: only calls are rewritten.
+#ifdef MPGOS_B200_FAST_MATH
+#define pow(x, y)         mpgos_b200::fm::pow(x, y)
+#define sin(x)            mpgos_b200::fm::sin(x)
+#define cos(x)            mpgos_b200::fm::cos(x)
+#define sincos(x, s, c)   mpgos_b200::fm::sincos(x, s, c)
+#define sincospi(x, s, c) mpgos_b200::fm::sincospi(x, s, c)
+#endif
+
+#endif

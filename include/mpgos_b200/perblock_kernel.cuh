@@ -620,7 +620,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			else
 			{
 				const P rel = fmin(P(1e30), P(1.0) / q);
-				mult = P(0.8) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+				mult = P(0.8) * (pow)(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
 				if (!Num<P>::finite(mult)) finite = false;
 			}
 			if (!finite)

@@ -372,7 +372,7 @@ __device__ __noinline__ int controller_exact(const PerThreadArgs<P, SD, NE, NSP,
 			update = update && (c->err[i] < tol_i);
 			rel = fmin(rel, tol_i / c->err[i]);
 		}
-		mult = P(0.9) * pow(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
+		mult = P(0.9) * (pow)(rel, update ? P(1.0 / 5.0) : P(1.0 / 4.0));
 		if (!Num<P>::finite(mult)) finite = false;
 		if (!finite)
 		{

@@ -8,7 +8,7 @@ anywhere (so that CPU-only checks can inspect the library's symbols), but creati
 without a CUDA device raises.
 """
 from .solver import (ProblemSolver, MpgosError, load_library, library_path, build_library,
-                     Variables, Options, Algorithms, run_workload, ABI_SYMBOLS, probe_fma_peak, probe_dmma_peak,
+                     Variables, Options, Algorithms, run_workload, ABI_SYMBOLS, probe_fma_peak, probe_dmma_peak, fast_math_probe,
                      apply_workload, read_back)
 from . import workloads
 from . import workloads_coupled

@@ -22,6 +22,8 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 64, 0, 0, kAlgRK4, false),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 64, 0, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("bubble_ensemble", BubbleEnsemble, 128, 0, 0, kAlgRKCK45, false),
+	COUPLED_ENTRY("bubble_ensemble_fm", BubbleEnsembleFm, 64, 0, 0, kAlgRKCK45, false),      // opt-in transcendentals (fast_math.cuh)
+	COUPLED_ENTRY("bubble_ensemble_fm", BubbleEnsembleFm, 16, 0, 0, kAlgRKCK45, false),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 1, 1, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 1, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 1, kAlgRK4, true),

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include "../../include/mpgos_b200/fast_math.cuh"
 
 namespace mpgos_b200 {
 namespace builtin {
@@ -18,19 +19,21 @@ namespace builtin {
 #define MPGOS_C_INIT_ARGS(P)  int sid, int uid, int& DOIDX, P& T, P& dT, P* TD, P* X, P* uPAR, P* sPAR, P* gPAR, int* igPAR, P* uACC, int* iuACC, P* sACC, int* isACC
 #define MPGOS_C_DEV           static __device__ __forceinline__ void
 
-template <class P>
-struct BubbleEnsemble
+// FAST: pow / sincospi / sin / cos from include/mpgos_b200/fast_math.cuh instead of the CUDA math library ("bubble_ensemble_fm")
+template <class P, bool FAST>
+struct BubbleEnsembleT
 {
+	using M = fm::Math<FAST>;
 	enum { UD = 2, NC = 1, NUP = 21, NSP = 0, NGP = 0, NiGP = 0, NUA = 0, NiUA = 0, NSA = 0, NiSA = 0, NE = 0 };
 	MPGOS_C_DEV OdeFunction(MPGOS_C_ODE_ARGS(P))
 	{
 		const P PI = P(3.14159265358979323846);
 		const P rx1 = P(1.0) / X[0];
-		const P p = pow(rx1, uPAR[10]);
+		const P p = M::pow_(rx1, uPAR[10]);
 		P s1, c1;
-		sincospi(P(2.0) * T, &s1, &c1);
-		const P s2 = sin(P(2.0) * uPAR[11] * PI * T + uPAR[12]);
-		const P c2 = cos(P(2.0) * uPAR[11] * PI * T + uPAR[12]);
+		M::sincospi_(P(2.0) * T, &s1, &c1);
+		P s2, c2;
+		M::sincos_(P(2.0) * uPAR[11] * PI * T + uPAR[12], &s2, &c2);
 		const P N = (uPAR[0] + uPAR[1] * X[1]) * p - uPAR[2] * (P(1.0) + uPAR[9] * X[1]) - uPAR[3] * rx1 - uPAR[4] * X[1] * rx1
 		          - P(1.5) * (P(1.0) - uPAR[9] * X[1] / P(3.0)) * X[1] * X[1] - (uPAR[5] * s1 + uPAR[6] * s2) * (P(1.0) + uPAR[9] * X[1])
 		          - X[0] * (uPAR[7] * c1 + uPAR[8] * c2);
@@ -47,6 +50,9 @@ struct BubbleEnsemble
 	MPGOS_C_DEV Initialization(MPGOS_C_INIT_ARGS(P)) { if (uid == 0) T = TD[0]; }
 	MPGOS_C_DEV Finalization(MPGOS_C_INIT_ARGS(P)) {}
 };
+
+template <class P> using BubbleEnsemble   = BubbleEnsembleT<P, false>;
+template <class P> using BubbleEnsembleFm = BubbleEnsembleT<P, true>;
 
 template <class P>
 struct DuffingRing

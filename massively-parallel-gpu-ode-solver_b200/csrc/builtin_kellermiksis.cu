@@ -16,6 +16,9 @@ static const BuiltinEntry kEntries[] = {
 	MPGOS_BUILTIN_ENTRY("kellermiksis_dense", KellerMiksisDense, double, kAlgRKCK45, true, MPGOS_MINB_KM),
 	MPGOS_BUILTIN_ENTRY("kellermiksis", KellerMiksis, float, kAlgRKCK45, false, MPGOS_MINB_KM),
 	MPGOS_BUILTIN_ENTRY("kellermiksis_dense", KellerMiksisDense, float, kAlgRKCK45, true, MPGOS_MINB_KM),
+	// the same systems with the opt-in transcendentals of include/mpgos_b200/fast_math.cuh
+	MPGOS_BUILTIN_ENTRY("kellermiksis_fm", KellerMiksisFm, double, kAlgRKCK45, false, MPGOS_MINB_KM),
+	MPGOS_BUILTIN_ENTRY("kellermiksis_dense_fm", KellerMiksisDenseFm, double, kAlgRKCK45, true, MPGOS_MINB_KM),
 };
 const BuiltinEntry* builtin_entries_kellermiksis(int* n) { *n = (int)(sizeof(kEntries) / sizeof(kEntries[0])); return kEntries; }
 }

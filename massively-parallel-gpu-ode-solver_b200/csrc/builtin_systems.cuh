@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 #include <math.h>
+#include "../../include/mpgos_b200/fast_math.cuh"
 
 namespace mpgos_b200 {
 namespace builtin {
@@ -149,20 +150,22 @@ struct Impact : Empty<P>
 };
 
 // T5_LargeTimeScaleDifferences/KellerMiksis_SystemDefinition.cuh:7-84 -- dual-frequency
-// Keller-Miksis bubble.  RESET_DOIDX adds T1's `DOIDX = 0` (config C4 adds dense output).
-template <class P, bool RESET_DOIDX>
+// Keller-Miksis bubble.  RESET_DOIDX adds T1's `DOIDX = 0` (config C4 adds dense output).  FAST: the same right-hand side with
+// pow / sincospi / sin / cos from include/mpgos_b200/fast_math.cuh instead of the CUDA math library (the "_fm" built-in names).
+template <class P, bool RESET_DOIDX, bool FAST = false>
 struct KellerMiksisT : Empty<P>
 {
+	using M = fm::Math<FAST>;
 	enum { SD = 2, NCP = 13, NSP = 0, NISP = 0, NE = 0, NA = 1, NIA = 0 };
 	MPGOS_DEV OdeFunction(MPGOS_ODE_ARGS(P))
 	{
 		const P PI = P(3.14159265358979323846);
 		const P rx1 = P(1.0) / X[0];
-		const P p = pow(rx1, cPAR[10]);
+		const P p = M::pow_(rx1, cPAR[10]);
 		P s1, c1;
-		sincospi(P(2.0) * T, &s1, &c1);
-		const P s2 = sin(P(2.0) * cPAR[11] * PI * T + cPAR[12]);
-		const P c2 = cos(P(2.0) * cPAR[11] * PI * T + cPAR[12]);
+		M::sincospi_(P(2.0) * T, &s1, &c1);
+		P s2, c2;
+		M::sincos_(P(2.0) * cPAR[11] * PI * T + cPAR[12], &s2, &c2);
 		const P N = (cPAR[0] + cPAR[1] * X[1]) * p - cPAR[2] * (P(1.0) + cPAR[9] * X[1]) - cPAR[3] * rx1 - cPAR[4] * X[1] * rx1
 		          - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1]
 		          - (cPAR[5] * s1 + cPAR[6] * s2) * (P(1.0) + cPAR[9] * X[1]) - X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
@@ -182,8 +185,10 @@ struct KellerMiksisT : Empty<P>
 		if (RESET_DOIDX) DOIDX = 0;
 	}
 };
-template <class P> using KellerMiksis      = KellerMiksisT<P, false>;
-template <class P> using KellerMiksisDense = KellerMiksisT<P, true>;
+template <class P> using KellerMiksis        = KellerMiksisT<P, false>;
+template <class P> using KellerMiksisDense   = KellerMiksisT<P, true>;
+template <class P> using KellerMiksisFm      = KellerMiksisT<P, false, true>;
+template <class P> using KellerMiksisDenseFm = KellerMiksisT<P, true, true>;
 
 } // namespace builtin
 } // namespace mpgos_b200

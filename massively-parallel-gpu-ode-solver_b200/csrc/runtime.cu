@@ -10,6 +10,7 @@
 // There is no CPU path: every entry point that needs the device fails with MPGOS_ERR_CUDA when
 // CUDA is unavailable.
 #include "../../include/mpgos_b200.h"
+#include "../../include/mpgos_b200/fast_math.cuh"
 #include "builtin_registry.h"
 
 #include <cuda_runtime.h>
@@ -975,6 +976,40 @@ int mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops)
 	return precision_bytes == 8 ? probe_fma_peak<double>(tflops) : probe_fma_peak<float>(tflops);
 }
 
+// ---- accuracy probe of include/mpgos_b200/fast_math.cuh (test support): out0/out1 = the fast functions, ref0/ref1 = CUDA's ----
+__global__ void fast_math_probe_kernel(int function, int n, const double* __restrict__ x, const double* __restrict__ y,
+                                       double* __restrict__ out0, double* __restrict__ out1, double* __restrict__ ref0, double* __restrict__ ref1)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double a = 0, b = 0, c = 0, d = 0;
+	if (function == 0)      { mpgos_b200::fm::sincos(x[i], &a, &b);    ::sincos(x[i], &c, &d); }
+	else if (function == 1) { mpgos_b200::fm::sincospi(x[i], &a, &b);  ::sincospi(x[i], &c, &d); }
+	else                    { a = mpgos_b200::fm::pow(x[i], y[i]);     c = ::pow(x[i], y[i]); }
+	out0[i] = a;  out1[i] = b;  ref0[i] = c;  ref1[i] = d;
+}
+
+int mpgos_fast_math_probe(int device, int function, int n, const double* x, const double* y, double* out0, double* out1, double* ref0, double* ref1)
+{
+	if (function < 0 || function > 2 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
+	if (n == 0) return MPGOS_OK;
+	CUDA_TRY(cudaSetDevice(device));
+	double* d = nullptr;
+	const size_t bytes = sizeof(double) * (size_t)n;
+	CUDA_TRY(cudaMalloc(&d, 6 * bytes));
+	CUDA_TRY(cudaMemcpy(d, x, bytes, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(d + n, y, bytes, cudaMemcpyHostToDevice));
+	fast_math_probe_kernel<<<(n + 255) / 256, 256>>>(function, n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, d + 4 * (size_t)n, d + 5 * (size_t)n);
+	cudaError_t e = cudaDeviceSynchronize();
+	if (e == cudaSuccess) e = cudaMemcpy(out0, d + 2 * (size_t)n, bytes, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(out1, d + 3 * (size_t)n, bytes, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(ref0, d + 4 * (size_t)n, bytes, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(ref1, d + 5 * (size_t)n, bytes, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(MPGOS_ERR_CUDA, "fast_math_probe -> %s", cudaGetErrorString(e));
+	return MPGOS_OK;
+}
+
 int mpgos_probe_dmma_peak(int device, double* tflops)
 {
 	if (!tflops) return fail(MPGOS_ERR_ARGUMENT, "probe_dmma_peak: bad argument");
@@ -1001,7 +1036,7 @@ static const std::vector<mpgos_b200::BuiltinEntry>& entries()
 	return all;
 }
 
-static const char* const kBuiltinNames[] = { "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", "tidprobe" };
+static const char* const kBuiltinNames[] = { "lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", "tidprobe", "kellermiksis_fm", "kellermiksis_dense_fm" };
 
 int mpgos_perthread_builtin_count(void) { return (int)(sizeof(kBuiltinNames) / sizeof(kBuiltinNames[0])); }
 const char* mpgos_perthread_builtin_name(int i) { return (i >= 0 && i < mpgos_perthread_builtin_count()) ? kBuiltinNames[i] : nullptr; }

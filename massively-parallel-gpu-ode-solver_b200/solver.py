@@ -82,7 +82,7 @@ ABI_SYMBOLS = (
     "mpgos_perthread_builtin_launcher", "mpgos_probe_fma_peak", "mpgos_perthread_save_state", "mpgos_perthread_restore_state",
     "mpgos_perthread_upload", "mpgos_perthread_download", "mpgos_probe_dmma_peak",
     "mpgos_perthread_create_sharded", "mpgos_perthread_shard_count", "mpgos_perthread_shard_info", "mpgos_perthread_shard_global_id",
-    "mpgos_shard_instances", "mpgos_shard_global_id",
+    "mpgos_shard_instances", "mpgos_shard_global_id", "mpgos_fast_math_probe",
 )
 
 
@@ -168,6 +168,18 @@ def probe_fma_peak(device: int = 0, precision_bytes: int = 8) -> float:
     v = C.c_double()
     _check(lib, lib.mpgos_probe_fma_peak(device, precision_bytes, C.byref(v)))
     return v.value
+
+
+def fast_math_probe(function: int, x, y=None, device: int = 0):
+    """(fast0, fast1, cuda0, cuda1): include/mpgos_b200/fast_math.cuh against the CUDA math library on the device; function 0 sincos,
+    1 sincospi, 2 pow(x, y)."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros_like(x) if y is None else np.ascontiguousarray(y, np.float64)
+    out = [np.empty_like(x) for _ in range(4)]
+    lib.mpgos_fast_math_probe.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    _check(lib, lib.mpgos_fast_math_probe(device, function, x.size, x.ctypes.data, y.ctypes.data, *[o.ctypes.data for o in out]))
+    return tuple(out)
 
 
 def probe_dmma_peak(device: int = 0) -> float:

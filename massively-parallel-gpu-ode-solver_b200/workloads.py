@@ -237,7 +237,7 @@ def impact_t6(NT: int = 1 << 20, phases: int = 128, ndo: int = 0) -> Workload:
     return Workload("impact", shape, opt, b, phases, 230, "T6 impact dynamics q-sweep")
 
 
-def keller_miksis_t5(NT: int = 1 << 18, phases: int = 32, ndo: int = 200) -> Workload:
+def keller_miksis_t5(NT: int = 1 << 18, phases: int = 32, ndo: int = 200, fast_math: bool = False) -> Workload:
     """C4: T5_LargeTimeScaleDifferences/KellerMiksis.cu:39,54-58,153-215 -- frequency sweep
     Logspace(20, 1000) kHz at PA1 = 1.5 bar, RE = 10 um; 13 control parameters.  The config adds
     dense output (NDO = 200, DenseOutputMinimumTimeStep 5e-3, dense index reset every phase)."""
@@ -273,7 +273,8 @@ def keller_miksis_t5(NT: int = 1 << 18, phases: int = 32, ndo: int = 200) -> Wor
     opt = Options(ThreadsPerBlock=64, RelativeTolerance=np.full(2, 1e-10), AbsoluteTolerance=np.full(2, 1e-10))
     if ndo > 0:
         opt.DenseOutputMinimumTimeStep = 5e-3
-    name = "kellermiksis_dense" if ndo > 0 else "kellermiksis"
+    # fast_math: the built-in system whose pow / sincospi / sin / cos come from include/mpgos_b200/fast_math.cuh (opt-in, <= 3 ulp)
+    name = ("kellermiksis_dense" if ndo > 0 else "kellermiksis") + ("_fm" if fast_math else "")
     return Workload(name, shape, opt, b, phases, 413, "T5 Keller-Miksis frequency sweep")
 
 

@@ -160,7 +160,7 @@ def bubble_geometry(UPS: int, seed: int = 20200818):
 
 
 def bubble_ensemble(NS: int = 1 << 16, UPS: int = 64, algorithm: int = RKCK45, phases: int = 1, ndo: int = 0,
-                    amplitude=(0.0, 5.0), frequency_khz: float = 1000.0, dtype=np.float64) -> CoupledWorkload:
+                    amplitude=(0.0, 5.0), frequency_khz: float = 1000.0, dtype=np.float64, fast_math: bool = False) -> CoupledWorkload:
     """C5: Tutorials_CoupledSystems_PerBlock/T2_BubbleEnsemble/BubbleEnsemble.cu:88-97, 225-353 -- NS systems of UPS
     coupled Keller-Miksis bubbles, pressure amplitude = Linspace(0, 5, NS) bar, full dense coupling matrix
     A[r][c] = RE_c^3 / RE_r^2 / dist_um shared by all systems, coupling strength 1 into component 1."""
@@ -211,7 +211,8 @@ def bubble_ensemble(NS: int = 1 << 16, UPS: int = 64, algorithm: int = RKCK45, p
         opt = CoupledOptions(InitialTimeStep=1e-3, MinimumTimeStep=1e-7,
                              RelativeTolerance=np.array([1e-5, 1e-5]), AbsoluteTolerance=np.array([1e-5, 1e-5]))
     flops = 6 * UPS * (48 + 7 + 2 * UPS + 3) + UPS * 110 + 9 + UPS * 6
-    return CoupledWorkload("bubble_ensemble", sh, opt, b, phases, flops, "T2_BubbleEnsemble amplitude sweep")
+    # fast_math: the built-in system with the opt-in transcendentals of include/mpgos_b200/fast_math.cuh (UPS 16 and 64)
+    return CoupledWorkload("bubble_ensemble_fm" if fast_math else "bubble_ensemble", sh, opt, b, phases, flops, "T2_BubbleEnsemble amplitude sweep")
 
 
 def duffing_ring(NS: int = 9, CBW: int = 1, CCI: int = 1, algorithm: int = RKCK45, phases: int = 1, ndo: int = 100,
