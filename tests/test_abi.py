@@ -68,11 +68,12 @@ def test_coupled_builtins_and_descriptor_checks(pkg):
 def test_builtin_systems_and_shapes(pkg):
     lib = pkg.load_library()
     names = [lib.mpgos_perthread_builtin_name(i).decode() for i in range(lib.mpgos_perthread_builtin_count())]
-    assert names == ["lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", "tidprobe"]
+    assert names == ["lorenz", "poincare", "duffing", "impact", "kellermiksis", "kellermiksis_dense", "tidprobe", "kellermiksis_fm", "kellermiksis_dense_fm"]
     from importlib import import_module
     solver = import_module(pkg.__name__ + ".solver")
     expect = {"lorenz": (3, 1, 0, 0, 0, 0, 0), "poincare": (2, 1, 1, 0, 0, 0, 0), "duffing": (2, 1, 1, 0, 2, 3, 1),
-              "impact": (3, 1, 4, 0, 2, 3, 2), "kellermiksis": (2, 13, 0, 0, 0, 1, 0), "kellermiksis_dense": (2, 13, 0, 0, 0, 1, 0), "tidprobe": (1, 1, 0, 0, 0, 1, 2)}
+              "impact": (3, 1, 4, 0, 2, 3, 2), "kellermiksis": (2, 13, 0, 0, 0, 1, 0), "kellermiksis_dense": (2, 13, 0, 0, 0, 1, 0), "tidprobe": (1, 1, 0, 0, 0, 1, 2),
+              "kellermiksis_fm": (2, 13, 0, 0, 0, 1, 0), "kellermiksis_dense_fm": (2, 13, 0, 0, 0, 1, 0)}
     for n, shape in expect.items():
         d = solver._Desc()
         assert lib.mpgos_perthread_builtin_desc(n.encode(), C.byref(d)) == 0
