@@ -5,6 +5,7 @@
 //
 //   mpgos_b200::fm::sincos / sin / cos (double)   <= 1.5 ulp for |x| <= 1e6, the CUDA function beyond that and for NaN / Inf
 //   mpgos_b200::fm::sincospi (double)             <= 1.7 ulp for |x| <= 2^30, the CUDA function beyond
+//   mpgos_b200::fm::rcp (double)                  <= 1 ulp for normal finite x, the division otherwise (built-in "_fm" systems only: user code writes 1.0 / x)
 //   mpgos_b200::fm::pow (double, double)          <= 3 ulp for normal positive finite x and |y log2 x| <= 1000, the CUDA function otherwise
 //                                                 (x <= 0, subnormal, Inf, NaN, over/underflowing results: all special cases are CUDA's)
 //   (errors measured against 200-bit references over the ranges of tests/test_fast_math_gpu.py; CUDA's own: sin/cos/sincospi/pow <= 2 ulp)
@@ -86,7 +87,8 @@ __device__ __forceinline__ void ldpair(int pair, double& a, double& b)
 // the CUDA functions, out of line: taken only outside the ranges stated above, and kept out of the callers' loop bodies
 static __device__ __noinline__ void   cuda_sincos(double x, double* s, double* c)   { ::sincos(x, s, c); }      // [cold>
 static __device__ __noinline__ void   cuda_sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
-static __device__ __noinline__ double cuda_pow(double x, double y)                  { return ::pow(x, y); }     // <cold]
+static __device__ __noinline__ double cuda_pow(double x, double y)                  { return ::pow(x, y); }
+static __device__ __noinline__ double cuda_rcp(double x)                            { return 1.0 / x; }         // <cold]
 
 // The three functions are real subroutines by default (MPGOS_B200_FM_INLINE 0).  Inlined into a step loop, their ~45 constants are
 // loop invariants: the compiler hoists the loads, runs out of the 63 uniform registers, parks the rest in vector registers and moves
@@ -204,20 +206,39 @@ MPGOS_FM_FN double pow(double x, double y)
 	const double g = zh - n;
 	ldpair(FM_LN2L_E13, ln2_lo, c13);
 	const double t = fma(g, ln2_lo, g * ln2_hi);
-	double p = c13;
-	ldpair(FM_E12_E11, a, b);  p = fma(p, t, a);  p = fma(p, t, b);
-	ldpair(FM_E10_E9, a, b);   p = fma(p, t, a);  p = fma(p, t, b);
-	ldpair(FM_E8_E7, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
-	ldpair(FM_E6_E5, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
-	ldpair(FM_E4_E3, a, b);    p = fma(p, t, a);  p = fma(p, t, b);
-	p = fma(p, t, 0.5);
-	p = fma(p, t, 1.0);        p = fma(p, t, 1.0);
+	// e^t = 1 + t + t^2 (E(t^2) + t O(t^2)): two Horner chains in t^2 side by side (the step loops that call this are latency-bound:
+	// one 13-deep chain of dependent FMAs costs more than its issue slots)
+	const double tt = t * t;
+	double pe, po;
+	ldpair(FM_E12_E11, pe, po);      po = fma(c13, tt, po);
+	ldpair(FM_E10_E9, a, b);         pe = fma(pe, tt, a);  po = fma(po, tt, b);
+	ldpair(FM_E8_E7, a, b);          pe = fma(pe, tt, a);  po = fma(po, tt, b);
+	ldpair(FM_E6_E5, a, b);          pe = fma(pe, tt, a);  po = fma(po, tt, b);
+	ldpair(FM_E4_E3, a, b);          pe = fma(pe, tt, a);  po = fma(po, tt, b);
+	pe = fma(pe, tt, 0.5);
+	double p = fma(po, t, pe);       // (t^2 / 2! + t^4 / 4! + ...) / t^2 + t (t^2 / 3! + ...) / t^2
+	p = fma(p, tt, t);
+	p = p + 1.0;
 	p = fma(p, zl * ln2_hi, p);                                                   // e^(zl ln 2) = 1 + zl ln 2
 	p = p * __hiloint2double((__double2loint(tn) + 1023) << 20, 0);
 	// zero, subnormal, negative, Inf, NaN base; overflow, underflow, y = NaN / Inf
 	if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u || !(fabs(zh) <= 1000.0)) p = cuda_pow(x, y);
 	return p;
 }
+
+// 1 / x for normal finite x of either sign (|x| in [2^-1020, 2^1020]); <= 1 ulp; the division otherwise.  The compiler's own
+// sequence for 1.0 / x is the same Newton iteration plus a range check, a slow-path call and a correction step for correct rounding
+// (~24 issue cycles against ~11).
+__device__ __forceinline__ double rcp(double x)
+{
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	r = fma(r, fma(-x, r, 1.0), r);
+	r = fma(r, fma(-x, r, 1.0), r);
+	if ((unsigned)((__double2hiint(x) & 0x7fffffff) - 0x00300000) >= 0x7fa00000u) r = cuda_rcp(x);
+	return r;
+}
+__device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
 
 // single precision: the CUDA functions
 __device__ __forceinline__ void  sincos(float x, float* s, float* c)   { ::sincosf(x, s, c); }
@@ -234,6 +255,7 @@ template <bool FAST> struct Math
 	template <class P> static __device__ __forceinline__ P    cos_(P x)                    { return mpgos_b200::fm::cos(x); }
 	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { mpgos_b200::fm::sincospi(x, s, c); }
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { mpgos_b200::fm::sincos(x, s, c); }      // one evaluation for both
+	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return mpgos_b200::fm::rcp(x); }
 };
 template <> struct Math<false>
 {
@@ -242,6 +264,7 @@ template <> struct Math<false>
 	template <class P> static __device__ __forceinline__ P    cos_(P x)                    { return ::cos(x); }
 	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { ::sincospi(x, s, c); }
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { *s = ::sin(x);  *c = ::cos(x); }         // the reference's two calls
+	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return P(1.0) / x; }
 };
 
 } // namespace fm

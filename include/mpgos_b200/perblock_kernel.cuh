@@ -57,7 +57,12 @@ struct PerBlockArgs
 	// unsliced phase; its controller state goes to the Slice* arrays.  SliceMode 2: the continuation, in the order the pilot's step
 	// counts give; systems that ended inside the pilot are skipped.  0: the whole phase in one launch.
 	int SliceMode;  P SliceFraction;
+	int MatrixInGlobal;      // scalar coupling only: the packed matrices do not fit into shared memory and are read from global memory
 	P* SliceDt;  P* SliceLastDt;  P* SliceDenseNext;  int* SliceSkipped;  int* SlicePaused;
+	// what a callback may have written into the parameter arrays before the pause: unit parameters, system parameters and coupling
+	// strengths live in registers / shared memory for the whole phase in the reference, so the continuation must see them as they
+	// were at the pause, not as they are in global memory
+	P* SliceUnitParameters;  P* SliceSystemParameters;  P* SliceCouplingStrength;
 	int ShardIndex, ShardCount, ShardTile;      // tile-cyclic shard of a multi-device solver (mpgos_b200_coupled.h); ShardCount <= 1: none
 	int NS, Active, SystemOffset, DenseCapacity, DenseOutputSaveFrequency, DeviceMessages;
 	P   InitialTimeStep, MaximumTimeStep, MinimumTimeStep, TimeStepGrowLimit, TimeStepShrinkLimit, DenseOutputMinimumTimeStep, MinimumTimeStepGuard;
@@ -284,7 +289,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 
 	MPGOS_B200_DYNAMIC_SHARED_MEMORY(dyn_smem);
 	P*   s_matrix = reinterpret_cast<P*>(dyn_smem);                      // [MSIZE x MCOPIES]  packed (scalar) or in fragment order (MMA)
-	P*   s_cptm   = s_matrix + MSIZE * MCOPIES;                         // [CPT_ALL]
+	P*   s_cptm   = s_matrix + ((!MMA && a.MatrixInGlobal) ? 0 : MSIZE * MCOPIES);      // [CPT_ALL]
 	P*   s_vpart  = s_cptm + CPT_ALL;                                   // [V_ELEMS]
 	P*   s_gpar   = s_vpart + V_ELEMS;                                  // [NGP]
 	int* s_igpar  = reinterpret_cast<int*>(s_gpar + NGP);               // [NiGP]
@@ -318,8 +323,11 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		}
 		for (int i = threadIdx.x; i < CPT_ALL; i += blockDim.x) s_cptm[i] = P(0);      // columns without a slot stay zero
 	}
-	else
+	else if (!a.MatrixInGlobal)
 		for (int i = threadIdx.x; i < MSIZE; i += blockDim.x) s_matrix[i] = a.CouplingMatrix[i];
+	// matrices too large for shared memory (dense FP64 from ~170 units on, or several couplings of 128 units) stay in global memory,
+	// where the reference keeps them by default (SharedCouplingMatrices = 0); they are shared by all systems, so L1 / L2 serve them
+	const P* const matrix = (!MMA && a.MatrixInGlobal) ? a.CouplingMatrix : s_matrix;
 	for (int i = threadIdx.x; i < NGP; i += blockDim.x)   s_gpar[i] = a.GlobalParameters[i];
 	for (int i = threadIdx.x; i < NiGP; i += blockDim.x)  s_igpar[i] = a.IntegerGlobalParameters[i];
 	for (int i = threadIdx.x; i < NC; i += blockDim.x)    s_cidx[i] = a.CouplingIndex[i];
@@ -378,14 +386,14 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 					S.dense_index = DENSE ? a.DenseOutputIndex[sys] : 0;  S.udt = 0;
 					S.dense_skipped = resumed ? a.SliceSkipped[sys] : 0;  S.dense_next_time = resumed ? a.SliceDenseNext[sys] : P(0);
 				}
-				if (unit < NSP)  S.spar[unit]     = a.SystemParameters[sys + unit * a.NS];
+				if (unit < NSP)  S.spar[unit]     = (resumed ? a.SliceSystemParameters : a.SystemParameters)[sys + unit * a.NS];
 				if (unit < NSA)  S.sacc[unit]     = a.SystemAccessories[sys + unit * a.NS];
 				if (unit < NiSA) S.isacc[unit]    = a.IntegerSystemAccessories[sys + unit * a.NS];
-				if (unit < NC)   S.strength[unit] = a.CouplingStrength[sys + unit * a.NS];
+				if (unit < NC)   S.strength[unit] = (resumed ? a.SliceCouplingStrength : a.CouplingStrength)[sys + unit * a.NS];
 				#pragma unroll
 				for (int i = 0; i < UD; i++)   x[i]     = a.ActualState[ug + i * NU];
 				#pragma unroll
-				for (int i = 0; i < NUP; i++)  upar[i]  = a.UnitParameters[ug + i * NU];
+				for (int i = 0; i < NUP; i++)  upar[i]  = (resumed ? a.SliceUnitParameters : a.UnitParameters)[ug + i * NU];
 				#pragma unroll
 				for (int i = 0; i < NUA; i++)  uacc[i]  = a.UnitAccessories[ug + i * NU];
 				#pragma unroll
@@ -496,7 +504,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 					#pragma unroll
 					for (int k = 0; k < NC; k++)
 					{
-						const P v = coupling_value<P, UPS, CBW, CCI>(s_matrix + k * MSTRIDE, S.cpt[buf][k], unit);
+						const P v = coupling_value<P, UPS, CBW, CCI>(matrix + k * MSTRIDE, S.cpt[buf][k], unit);
 						const P add = S.strength[k] * cpf[k] * v;
 						const int ci = s_cidx[k];
 						#pragma unroll
@@ -762,6 +770,16 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				#pragma unroll
 				for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[ug + i * NU] = iuacc[i];
 			}
+			if (paused)
+			{
+				if (live)
+				{
+					#pragma unroll
+					for (int i = 0; i < NUP; i++) a.SliceUnitParameters[ug + i * NU] = upar[i];
+				}
+				if (unit < NSP) a.SliceSystemParameters[sys + unit * a.NS] = S.spar[unit];
+				if (unit < NC)  a.SliceCouplingStrength[sys + unit * a.NS] = S.strength[unit];
+			}
 			if (unit < NSA)  a.SystemAccessories[sys + unit * a.NS] = S.sacc[unit];
 			if (unit < NiSA) a.IntegerSystemAccessories[sys + unit * a.NS] = S.isacc[unit];
 			if (unit == 0)
@@ -799,6 +817,13 @@ struct PerBlockLauncher
 #define MPGOS_B200_MMA_SLOTS 8
 #endif
 	static constexpr int  kMmaSlots = (UPS == 128) ? 4 : MPGOS_B200_MMA_SLOTS;      // 512 threads; with 128 units half of the instruction's N extent is used
+	// dynamic shared memory a block may ask for (227 KB per SM less the static part: slots, reduction words)
+	static constexpr size_t kDynamicSharedLimit = 200 * 1024;
+	template <int SLOTS> static constexpr size_t mma_shared_bytes()
+	{
+		using G = typename MmaGeometryFor<P, kCanMMA ? UPS : 32, kCanMMA ? SLOTS : 8>::type;
+		return sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * G::MCOPIES + (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS + NGP) + sizeof(int) * NiGP + 16;
+	}
 
 	template <int SLOTS, bool MMA>
 	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
@@ -806,7 +831,17 @@ struct PerBlockLauncher
 		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA>;
 		using G = typename MmaGeometryFor<P, MMA ? UPS : 32, MMA ? SLOTS : 8>::type;
 		const size_t extra = MMA ? (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
-		const size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * (MMA ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
+		size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * (MMA ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
+		PerBlockArgs<P, UD, NE> args = a;
+		args.MatrixInGlobal = 0;
+		if (smem > kDynamicSharedLimit)
+		{
+			// the matrices do not fit next to the block's other shared data: the tensor-core variant needs them there (launch() does not
+			// come here with it), the scalar variant reads them from global memory instead
+			if (MMA) return (int)cudaErrorInvalidConfiguration;
+			smem -= sizeof(P) * (size_t)packed_matrix_elements(UPS, NC, CBW, CCI);
+			args.MatrixInGlobal = 1;
+		}
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return (int)e;
 		int per_sm = 0;
@@ -820,7 +855,6 @@ struct PerBlockLauncher
 		if (e != cudaSuccess) return (int)e;
 		// queue order: with the previous phase's step counts at hand and more systems than two rounds of slots, the longest first
 		// (C5, whose expensive systems sit at the end of the amplitude sweep: 18.0 instead of 19.4 ms)
-		PerBlockArgs<P, UD, NE> args = a;
 		args.DispatchOrder = nullptr;  args.SliceMode = 0;
 		const bool many = (a.Active > 2 * grid * SLOTS) || L->DispatchHistory >= 2 || L->DispatchPilot >= 2;      // >= 2: forced (tests)
 		const bool can_order = L->d_DispatchOrder && L->d_DispatchScratch && many;
@@ -841,7 +875,7 @@ struct PerBlockLauncher
 			if (e != cudaSuccess) return (int)e;
 			args.DispatchOrder = L->d_DispatchOrder;
 		}
-		else if (L->DispatchPilot && can_order && L->d_SliceState)
+		else if (L->DispatchPilot && can_order && L->d_SliceState && L->d_SliceParameters)
 		{
 			// no history yet: the first tenth of the phase in index order tells what each system costs (for sweeps whose cost is set by a
 			// parameter -- C5's pressure amplitude), the rest follows in that order.  Emulated with two phases before it was built:
@@ -849,6 +883,9 @@ struct PerBlockLauncher
 			P* base = (P*)L->d_SliceState;
 			args.SliceDt = base;  args.SliceLastDt = base + L->desc.NS;  args.SliceDenseNext = base + 2 * (size_t)L->desc.NS;
 			args.SliceSkipped = (int*)(base + 3 * (size_t)L->desc.NS);  args.SlicePaused = args.SliceSkipped + L->desc.NS;
+			P* pbase = (P*)L->d_SliceParameters;
+			args.SliceUnitParameters = pbase;  args.SliceSystemParameters = pbase + (size_t)NUP * L->desc.NS * UPS;
+			args.SliceCouplingStrength = args.SliceSystemParameters + (size_t)NSP * L->desc.NS;
 			args.SliceMode = 1;  args.SliceFraction = P(0.1);
 			kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
 			e = cudaGetLastError();
@@ -878,6 +915,8 @@ struct PerBlockLauncher
 		a.DenseOutputStates = (P*)L->d_DenseOutputStates;  a.StepsAttempted = L->d_StepsAttempted;  a.StepsAccepted = L->d_StepsAccepted;  a.WorkQueue = L->d_WorkQueue;
 		a.LastPhaseSteps = L->d_LastPhaseSteps;  a.DispatchOrder = nullptr;
 		a.SliceMode = 0;  a.SliceFraction = P(0);  a.SliceDt = a.SliceLastDt = a.SliceDenseNext = nullptr;  a.SliceSkipped = a.SlicePaused = nullptr;
+		a.SliceUnitParameters = a.SliceSystemParameters = a.SliceCouplingStrength = nullptr;
+		a.MatrixInGlobal = 0;
 		a.ShardIndex = d.ShardIndex;  a.ShardCount = d.ShardCount;  a.ShardTile = d.ShardTile > 0 ? d.ShardTile : 1;
 		a.NS = d.NS;  a.Active = L->ActiveSystems < d.NS ? L->ActiveSystems : d.NS;  a.SystemOffset = d.SystemOffset;  a.DenseCapacity = d.NDO;
 		a.DenseOutputSaveFrequency = L->DenseOutputSaveFrequency;  a.DeviceMessages = L->DeviceMessages;
@@ -889,7 +928,7 @@ struct PerBlockLauncher
 		if (a.Active <= 0) return (int)cudaSuccess;
 		if constexpr (kCanMMA)
 		{
-			if (L->TensorCoreCoupling) return enqueue<kMmaSlots, true>(L, a, stream);
+			if (L->TensorCoreCoupling && mma_shared_bytes<kMmaSlots>() <= kDynamicSharedLimit) return enqueue<kMmaSlots, true>(L, a, stream);
 		}
 		return enqueue<SPBK, false>(L, a, stream);
 	}

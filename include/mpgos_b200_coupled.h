@@ -83,6 +83,8 @@ typedef struct mpgos_coupled_launch
 	unsigned int*       d_DispatchScratch;  /* [NS + 768] scratch of the ordering kernels */
 	int                 DispatchHistory;    /* 1: d_LastPhaseSteps describes the previous phase of these systems and cost order is wanted (2: also for short queues) */
 	void*               d_SliceState;       /* [NS x 40 bytes] controller state of systems paused at the end of a pilot slice */
+	void*               d_SliceParameters;  /* [(NUP x UPS + NSP + NC) x NS] unit parameters, system parameters and coupling strengths as the callbacks
+	                                           left them at the pause (allocated by the runtime on the first phase that uses a pilot slice) */
 	int                 DispatchPilot;      /* 1: no history: integrate a pilot slice first and order the rest by its step counts (2: also for short queues) */
 	size_t CouplingMatrixElements;
 	const double* RelativeTolerance;  const double* AbsoluteTolerance;  const double* EventTolerance;  const int* EventDirection;   /* host */

@@ -28,7 +28,7 @@ struct BubbleEnsembleT
 	MPGOS_C_DEV OdeFunction(MPGOS_C_ODE_ARGS(P))
 	{
 		const P PI = P(3.14159265358979323846);
-		const P rx1 = P(1.0) / X[0];
+		const P rx1 = M::rcp_(X[0]);
 		const P p = M::pow_(rx1, uPAR[10]);
 		P s1, c1;
 		M::sincospi_(P(2.0) * T, &s1, &c1);
@@ -38,7 +38,7 @@ struct BubbleEnsembleT
 		          - P(1.5) * (P(1.0) - uPAR[9] * X[1] / P(3.0)) * X[1] * X[1] - (uPAR[5] * s1 + uPAR[6] * s2) * (P(1.0) + uPAR[9] * X[1])
 		          - X[0] * (uPAR[7] * c1 + uPAR[8] * c2);
 		const P D = X[0] - uPAR[9] * X[0] * X[1] + uPAR[4] * uPAR[9];
-		const P rD = P(1.0) / D;
+		const P rD = M::rcp_(D);
 		F[0] = X[1];
 		F[1] = N * rD;
 		CPT[0] = -(2 * X[0] * X[1] * X[1] + X[0] * X[0] * N * rD);

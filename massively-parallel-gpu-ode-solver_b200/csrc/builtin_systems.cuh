@@ -160,7 +160,7 @@ struct KellerMiksisT : Empty<P>
 	MPGOS_DEV OdeFunction(MPGOS_ODE_ARGS(P))
 	{
 		const P PI = P(3.14159265358979323846);
-		const P rx1 = P(1.0) / X[0];
+		const P rx1 = M::rcp_(X[0]);
 		const P p = M::pow_(rx1, cPAR[10]);
 		P s1, c1;
 		M::sincospi_(P(2.0) * T, &s1, &c1);
@@ -170,7 +170,7 @@ struct KellerMiksisT : Empty<P>
 		          - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1]
 		          - (cPAR[5] * s1 + cPAR[6] * s2) * (P(1.0) + cPAR[9] * X[1]) - X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
 		const P D = X[0] - cPAR[9] * X[0] * X[1] + cPAR[4] * cPAR[9];
-		const P rD = P(1.0) / D;
+		const P rD = M::rcp_(D);
 		F[0] = X[1];
 		F[1] = N * rD;
 	}

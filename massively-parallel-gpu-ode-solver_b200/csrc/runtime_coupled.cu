@@ -40,6 +40,7 @@ struct mpgos_coupled_solver
 	int*          d_order = nullptr;           // [NS]
 	unsigned int* d_order_scratch = nullptr;   // [NS + 768]
 	void*         d_slice = nullptr;           // [NS x 40 bytes] pilot-slice state
+	void*         d_slice_params = nullptr;    // parameters as of the pause (allocated on the first phase that uses a pilot slice)
 	bool          history_valid = false;
 	int           DispatchOrder = 1;
 	double InitialTimeStep = 1e-2, MaximumTimeStep = 1.0e6, MinimumTimeStep = 1.0e-12, TimeStepGrowLimit = 5.0, TimeStepShrinkLimit = 0.1;
@@ -263,6 +264,7 @@ int mpgos_coupled_destroy(mpgos_coupled_solver* s)
 	if (s->d_order) cudaFree(s->d_order);
 	if (s->d_order_scratch) cudaFree(s->d_order_scratch);
 	if (s->d_slice) cudaFree(s->d_slice);
+	if (s->d_slice_params) cudaFree(s->d_slice_params);
 	if (s->t0) cudaEventDestroy(s->t0);
 	if (s->t1) cudaEventDestroy(s->t1);
 	if (s->event) cudaEventDestroy(s->event);
@@ -457,6 +459,16 @@ int mpgos_coupled_download(mpgos_coupled_solver* s, int variable, void* host_dst
 	return MPGOS_OK;
 }
 
+// the pilot slice pauses systems in mid-phase: room for the parameter arrays as the callbacks left them (allocated on first use)
+static int ensure_slice_parameters(mpgos_coupled_solver* s)
+{
+	if (s->d_slice_params || !s->DispatchOrder) return MPGOS_OK;
+	const mpgos_coupled_desc& d = s->desc;
+	const size_t elements = ((size_t)d.NUP * d.UPS + d.NSP + d.NC) * (size_t)d.NS;
+	CUDA_TRY(cudaMalloc(&s->d_slice_params, (elements ? elements : 1) * (size_t)d.PrecisionBytes));
+	return MPGOS_OK;
+}
+
 static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 {
 	L.AbiVersion = MPGOS_B200_ABI_VERSION;
@@ -472,6 +484,7 @@ static void cfill(mpgos_coupled_solver* s, mpgos_coupled_launch& L)
 	L.d_StepsAttempted = s->d_attempted;  L.d_StepsAccepted = s->d_accepted;  L.d_WorkQueue = s->d_queue;
 	L.d_LastPhaseSteps = s->d_last_steps;  L.d_DispatchOrder = s->d_order;  L.d_DispatchScratch = s->d_order_scratch;
 	L.DispatchHistory = (s->DispatchOrder && s->history_valid) ? s->DispatchOrder : 0;  L.DispatchPilot = (s->DispatchOrder && !s->history_valid) ? s->DispatchOrder : 0;  L.d_SliceState = s->d_slice;
+	L.d_SliceParameters = s->d_slice_params;
 	L.CouplingMatrixElements = s->var[MPGOS_CVAR_CouplingMatrix].elements;
 	L.RelativeTolerance = s->rtol.data();  L.AbsoluteTolerance = s->atol.data();  L.EventTolerance = s->evtol.data();  L.EventDirection = s->evdir.data();
 	L.InitialTimeStep = s->InitialTimeStep;  L.MaximumTimeStep = s->MaximumTimeStep;  L.MinimumTimeStep = s->MinimumTimeStep;
@@ -486,6 +499,7 @@ int mpgos_coupled_solve(mpgos_coupled_solver* s, mpgos_coupled_launcher launcher
 	for (mpgos_coupled_solver* c : s->shards) { const int rc = mpgos_coupled_solve(c, launcher);  if (rc != MPGOS_OK) return rc; }
 	if (!s->shards.empty()) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	if (!s->history_valid) { const int rc = ensure_slice_parameters(s);  if (rc != MPGOS_OK) return rc; }
 	mpgos_coupled_launch L;
 	cfill(s, L);
 	const int e = launcher(&L, (void*)s->stream);
@@ -518,6 +532,7 @@ int mpgos_coupled_solve_timed(mpgos_coupled_solver* s, mpgos_coupled_launcher la
 		return MPGOS_OK;
 	}
 	CUDA_TRY(cudaSetDevice(s->desc.Device));
+	{ const int rc = ensure_slice_parameters(s);  if (rc != MPGOS_OK) return rc; }
 	mpgos_coupled_launch L;
 	cfill(s, L);
 	CUDA_TRY(cudaEventRecord(s->t0, s->stream));

@@ -139,6 +139,7 @@ int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo,
 		if (ups == 128) return dispatch<BubbleEnsemble<P, 128>, P>(algorithm, ndo, b, o, shape);
 	}
 	if (!std::strcmp(system, "duffing_ring") && ups == 32 && cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 32, 0, 0>, P>(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 192 && cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 192, 0, 0>, P>(algorithm, ndo, b, o, shape);
 	if (!std::strcmp(system, "duffing_ring") && ups == 14)
 	{
 		if (cbw == 1 && cci == 1) return dispatch<DuffingRing<P, 14, 1, 1>, P>(algorithm, ndo, b, o, shape);

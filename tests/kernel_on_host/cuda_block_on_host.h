@@ -148,6 +148,19 @@ static inline int      min(int a, int b) { return a < b ? a : b; }
 // stand-ins for include/mpgos_b200/ptx_primitives.cuh (its include guard is taken here)
 #define MPGOS_B200_PTX_PRIMITIVES_CUH
 #define MPGOS_B200_DYNAMIC_SHARED_MEMORY(name) unsigned char* const name = g_dynamic_shared
+// ... and for include/mpgos_b200/fast_math.cuh: on the host both forms of the built-in systems use libm
+#define MPGOS_B200_FAST_MATH_CUH
+namespace mpgos_b200 { namespace fm {
+template <bool FAST> struct Math
+{
+	template <class P> static inline P    pow_(P x, P y)             { return std::pow(x, y); }
+	template <class P> static inline P    sin_(P x)                  { return std::sin(x); }
+	template <class P> static inline P    cos_(P x)                  { return std::cos(x); }
+	template <class P> static inline void sincospi_(P x, P* s, P* c) { sincospi(x, s, c); }
+	template <class P> static inline void sincos_(P x, P* s, P* c)   { *s = std::sin(x);  *c = std::cos(x); }
+	template <class P> static inline P    rcp_(P x)                  { return P(1.0) / x; }
+};
+} }
 namespace mpgos_b200 {
 static inline bool warp_any(bool p) { return p; }      // a lane's own condition is a valid answer (see ptx_primitives.cuh)
 static inline float sfu_lg2(float x) { return std::log2(x); }

@@ -73,6 +73,7 @@ template <bool FAST> struct Math
 	template <class P> static inline P    cos_(P x)                  { return std::cos(x); }
 	template <class P> static inline void sincospi_(P x, P* s, P* c) { sincospi(x, s, c); }
 	template <class P> static inline void sincos_(P x, P* s, P* c)   { *s = std::sin(x);  *c = std::cos(x); }
+	template <class P> static inline P    rcp_(P x)                  { return P(1.0) / x; }
 };
 } }
 namespace mpgos_b200 {

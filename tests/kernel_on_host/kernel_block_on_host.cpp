@@ -88,6 +88,7 @@ extern "C" int ref_coupled_run(const oracle_coupled_buffers* b, const oracle_cou
 	std::vector<unsigned int> last(NS, 0);
 	std::vector<int> order(NS), skipped(NS, 0), paused(NS, 0);
 	std::vector<P> sdt(NS), sldt(NS), sdn(NS);
+	std::vector<P> sup((size_t)NS * UPS * (NUP > 0 ? NUP : 1)), ssp((size_t)NS * (NSP > 0 ? NSP : 1)), scs((size_t)NS * (NC > 0 ? NC : 1));
 	unsigned int queue = 0;
 	PerBlockArgs<P, UD, NE> a;
 	std::memset(&a, 0, sizeof(a));
@@ -100,6 +101,7 @@ extern "C" int ref_coupled_run(const oracle_coupled_buffers* b, const oracle_cou
 	a.LastPhaseSteps = last.data();  a.DispatchOrder = nullptr;
 	a.SliceMode = 0;  a.SliceFraction = P(0);  a.SliceDt = sdt.data();  a.SliceLastDt = sldt.data();  a.SliceDenseNext = sdn.data();
 	a.SliceSkipped = skipped.data();  a.SlicePaused = paused.data();
+	a.SliceUnitParameters = sup.data();  a.SliceSystemParameters = ssp.data();  a.SliceCouplingStrength = scs.data();
 	a.NS = NS;  a.Active = o->ActiveSystems < NS ? o->ActiveSystems : NS;  a.SystemOffset = 0;  a.DenseCapacity = KOH_NDO;
 	a.DenseOutputSaveFrequency = o->DenseOutputSaveFrequency;  a.DeviceMessages = 0;
 	// exactly PerBlockLauncher::launch (perblock_kernel.cuh), which g++ cannot see (it sits behind __CUDACC__)

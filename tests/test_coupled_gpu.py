@@ -285,3 +285,20 @@ def test_cost_ordered_queue_on_a_long_queue_and_the_tensor_core_path(pkg):
     for f in COUPLED_RESULT_FIELDS:
         assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
     assert np.array_equal(aatt, batt) and np.array_equal(aacc, bacc) and (aatt > 0).all()
+
+
+def test_coupling_matrices_larger_than_shared_memory_are_read_from_global_memory(pkg, oracle):
+    """192 units with two FULL coupling matrices = 576 KB in double precision: they cannot be staged in shared memory (the reference
+    keeps dense matrices in global memory by default, SharedCouplingMatrices = 0), so the scalar coupling reads them from global
+    memory -- 5 systems of six warps each, events, accessories, dense output, against the checker."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.duffing_ring(NS=5, CBW=0, CCI=0, UPS=192, ndo=40, TPB=192, SPB=1)
+    rng = np.random.default_rng(3)
+    wl.buffers.CouplingMatrix[...] = rng.uniform(0.0, 0.02, (2, 192, 192)) * (1.0 - np.eye(192))[None]
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=1, host_threads=8)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=1)
+    assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)
+    assert np.abs(att - ratt).max() <= 2
+    assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
+    assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
