@@ -144,6 +144,32 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-GPU runs: keep this rank's host thread (and, by first touch, its pinned buffers) on the NUMA node its GPU hangs off, so that
+    eight ranks' host<->device copies do not all cross one memory controller.  Returns a description for the bench line.  On a box
+    whose GPUs all sit on one node (nvidia-smi topo: the pool's 8 x B200 boxes) this changes nothing -- and says so."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        if node < 0 or len(nodes) < 2:
+            return {"numa_node": node, "numa_nodes": len(nodes), "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "numa_nodes": len(nodes), "bound": bool(cpus), "cpus": len(cpus)}
+    except Exception as e:
+        return {"bound": False, "error": str(e)[:80]}
+
+
 def cpu_reference_run(pkg, name: str, precision: str, sample: int, threads: int, phases: int):
     """The reference's own kernel source compiled for the host (oracle/_ref, kind "reference"), or our
     CPU restatement of it when that library is absent / for the coupled module (kind "port"), over every
@@ -413,6 +439,19 @@ def measure(pkg, args, workload, precision, N, phases, steps, warmup, rank, loca
     for _ in range(2):
         step_e2e()
     drain_e2e()
+    # the copies alone, all ranks at once: what the host side (memory controllers, PCIe root) gives each rank for this step's bytes
+    barrier(); torch.cuda.synchronize()
+    tc0 = time.perf_counter()
+    for _ in range(3):
+        for a in e2e_arms:
+            for v, t in a.user_in.items():
+                a.ps.Upload(v, t.data_ptr(), t.numel() * t.element_size())
+            for v, t in a.user_out.items():
+                a.ps.Download(v, t.data_ptr(), t.numel() * t.element_size())
+            a.ps.InsertSynchronisationPoint()
+        drain_e2e()
+    torch.cuda.synchronize(); barrier()
+    copy_gbs = 3 * (h2d + d2h) / (time.perf_counter() - tc0) / 1e9
     for a in e2e_arms:
         a.ps.ResetStepCounters()
     barrier(); torch.cuda.synchronize()
@@ -427,9 +466,10 @@ def measure(pkg, args, workload, precision, N, phases, steps, warmup, rank, loca
 
     # ---- reduce over ranks -------------------------------------------------------------------------
     sharding = importlib.import_module(pkg.__name__ + ".sharding")
-    (region_ms, e2e_s, kmean), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms))],
-                                                                   [attempted, accepted, e2e_attempted], device="cuda")
+    (region_ms, e2e_s, kmean, neg_copy), counts = sharding.reduce_over_ranks([region_ms, e2e_s, float(np.mean(kernel_ms)), -copy_gbs],
+                                                                             [attempted, accepted, e2e_attempted], device="cuda")
     attempted, accepted, e2e_attempted = [int(x) for x in counts]
+    copy_gbs_min = -neg_copy       # the slowest rank's copy rate
 
     out = None
     if rank == 0:
@@ -464,7 +504,9 @@ def measure(pkg, args, workload, precision, N, phases, steps, warmup, rank, loca
                             "kernel_ms": kmean, "algorithmic_flops_per_launch": per_rank_attempted_per_launch * flops_per_step,
                             "fp64_pipe_utilisation_ncu": NCU_PIPE.get(f"{workload}_{precision}")},
                "e2e": {"value": e2e_attempted / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "ms_per_step": e2e_s / steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum},
+                       "ms_per_step": e2e_s / steps * 1e3, "chunks": len(e2e_arms), "state_checksum": final_state_checksum,
+                       "copies_alone_gbs_per_rank": copy_gbs_min,
+                       "copies_alone_note": "this step's H2D + D2H bytes without any kernel, all ranks at the same time (slowest rank): the host side's share of the e2e time"},
                "gpu_launches": steps * (phases + ordering_kernels), "clocks": clocks}
         if dense_samples is not None:
             # the only HBM stream that matters on this path: (SD + 1) words per stored point (24 B for Keller-Miksis)
@@ -582,7 +624,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     out = measure(pkg, args, args.workload, args.precision, N, args.phases, args.steps, args.warmup, rank, local_rank, world, full=True)
+    if rank == 0 and numa is not None:
+        out["host_binding"] = numa
 
     # ---- the other BASELINE configurations, after the headline (whose timing they cannot disturb) ----
     default_headline = (args.workload == "lorenz" and args.precision == "f64" and not args.instances and args.phases == 1
@@ -591,9 +636,15 @@ def main():
     if args.configs == "auto" and not default_headline:
         wanted = []
     configs = {}
+    if wanted and world > 1:
+        # strong scaling of the headline sweep: its 2^20 instances split over the GPUs (short kernels: launch latency and tails show)
+        wanted = wanted + [("C2_lorenz_rkck45_f64_strong_scaling", "lorenz", "f64", 1)]
     for key, wname, prec, phases in wanted:
+        strong = key.endswith("_strong_scaling")
         try:
-            r = measure(pkg, args, wname, prec, WORKLOADS[wname][2], phases, min(args.steps, 5), 3, rank, local_rank, world, full=False)
+            r = measure(pkg, args, wname, prec, WORKLOADS[wname][2] // (world if strong else 1), phases, min(args.steps, 5), 3, rank, local_rank, world, full=False)
+            if strong and r is not None:
+                r["scaling"] = "strong"
         except Exception as e:      # an extra configuration must never break the headline line
             r = {"error": f"{type(e).__name__}: {e}"[:300]}
             if world > 1:

@@ -91,6 +91,30 @@ struct DuffingRing
 	MPGOS_C_DEV Finalization(MPGOS_C_INIT_ARGS(P)) {}
 };
 
+// Not a tutorial system: callbacks that WRITE the parameter arrays (unit parameters in every unit, the system parameter and the
+// coupling strength... by unit 0), as the reference allows -- there the arrays live in registers / shared memory for the whole
+// phase.  Used to check that pausing a system in mid-phase (pilot slice) and resuming it later loses none of those writes.
+template <class P>
+struct ParameterDrift
+{
+	enum { UD = 1, NC = 1, NUP = 1, NSP = 1, NGP = 0, NiGP = 0, NUA = 0, NiUA = 0, NSA = 0, NiSA = 0, NE = 0 };
+	MPGOS_C_DEV OdeFunction(MPGOS_C_ODE_ARGS(P))
+	{
+		F[0] = -uPAR[0] * X[0] + sPAR[0];
+		CPT[0] = X[0];
+		CPF[0] = P(1.0);
+	}
+	MPGOS_C_DEV EventFunction(MPGOS_C_EV_ARGS(P)) {}
+	MPGOS_C_DEV ActionAfterEventDetection(MPGOS_C_EVACT_ARGS(P)) {}
+	MPGOS_C_DEV ActionAfterSuccessfulTimeStep(MPGOS_C_STEP_ARGS(P))
+	{
+		uPAR[0] *= P(1.0) + P(0.05) * dT;
+		if (uid == 0) sPAR[0] += P(0.1) * dT;
+	}
+	MPGOS_C_DEV Initialization(MPGOS_C_INIT_ARGS(P)) { if (uid == 0) T = TD[0]; }
+	MPGOS_C_DEV Finalization(MPGOS_C_INIT_ARGS(P)) {}
+};
+
 } // namespace builtin
 } // namespace mpgos_b200
 #endif

