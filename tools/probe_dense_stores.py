@@ -18,7 +18,12 @@ if case == "coupled_ring":
 else:
     wl = {"duffing_events": lambda: W.duffing_t1(NT=1 << 18, algorithm=W.RKCK45, ndo=200),
           "impact_dense": lambda: W.impact_t6(NT=1 << 18, ndo=200),
-          "kellermiksis_dense": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=200)}[case]()
+          "kellermiksis_dense": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=200),
+          "kellermiksis_dense_shuffled": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=200),
+          "impact_dense_shuffled": lambda: W.impact_t6(NT=1 << 18, ndo=200),
+          "duffing_events_shuffled": lambda: W.duffing_t1(NT=1 << 18, algorithm=W.RKCK45, ndo=200)}[case]()
+    if case.endswith("_shuffled"):       # neighbouring lanes integrate unrelated instances: they reach their storage points in different iterations
+        wl.buffers = wl.buffers.take(np.random.default_rng(0).permutation(wl.NT))
     out, att, acc = pkg.run_workload(wl, phases=1)
     pts = int(np.minimum(out.DenseIndex, 200).sum())
     same = float(np.mean(out.DenseIndex.reshape(-1, 32).max(1) == out.DenseIndex.reshape(-1, 32).min(1)))
