@@ -94,7 +94,8 @@ def test_tc1_ring_tutorial_against_the_checker(pkg, oracle):
         assert abs(int(fields["Ndt"]) - int(ref.IntegerSystemAccessories[0, sid])) <= 2
         assert rel_err(float(fields["t"]), ref.ActualTime[sid]) < 2e-6
         assert rel_err(float(fields["dtmax"]), ref.SystemAccessories[1, sid]) < 1e-5
-        states = [l for l in blk.splitlines() if l.strip() and l.strip()[0].isdigit() and l.count(",") >= 3][:14]
+        body = blk.split("UID,")[1].splitlines()[1:]
+        states = [l for l in body if l.strip() and l.strip()[0].isdigit()][:14]
         x = np.array([[float(v) for v in l.split(",")[1:3]] for l in states])
         assert x.shape == (14, 2)
         assert np.abs(x[:, 0] - ref.ActualState[0, sid]).max() < 2e-5 and np.abs(x[:, 1] - ref.ActualState[1, sid]).max() < 2e-5
@@ -104,6 +105,11 @@ def test_tc1_ring_tutorial_against_the_checker(pkg, oracle):
         n = int(ref.DenseIndex[sid])
         series = [r for r in rows if r.count(",") >= 2 * 14]
         assert abs(len(series) - min(n, 500)) <= 2
+        m = min(len(series), n, 500) - 2
+        t = np.array([float(r.split(",")[0]) for r in series[:m]])
+        assert np.abs(t - ref.DenseTime[:m, sid]).max() < 1e-5 * max(1.0, t.max())
+        x0 = np.array([float(r.split(",")[1]) for r in series[:m]])          # unit 0, component 0
+        assert np.abs(x0 - ref.DenseState[:m, 0, sid, 0]).max() < 1e-4
 
 
 def sorted_rows(path):
