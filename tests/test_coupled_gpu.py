@@ -37,6 +37,7 @@ def test_duffing_ring_events_accessories_dense_output(name, ccases, pkg, oracle)
     tag, wl, phases = ccases[name]
     ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=phases)
     out, att, acc = pkg.run_coupled_workload(wl, phases=phases)
+    print(f"[parity {name}] state {rel_err(out.ActualState, ref.ActualState).max():.2e}  time {rel_err(out.ActualTime, ref.ActualTime).max():.2e}  step diff {np.abs(att - ratt).max()}  same dense index {(out.DenseIndex == ref.DenseIndex).mean():.3f}")
     assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)   # event counters of every unit
     assert np.abs(att - ratt).max() <= 2 and np.abs(acc - racc).max() <= 2
     assert np.abs(out.IntegerSystemAccessories - ref.IntegerSystemAccessories).max() <= 2   # step counter kept by unit 0

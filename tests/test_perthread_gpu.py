@@ -102,6 +102,7 @@ def test_rkck45_endpoints_and_step_counts(name, refill, cases, pkg, oracle):
     wl, phases = cases[name]
     ref, ratt, racc = oracle.run_oracle(wl, phases=phases)
     out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
+    print(f"[parity {name} refill={refill}] endpoint {rel_err(out.ActualState, ref.ActualState).max():.2e}  same attempted {(att == ratt).mean():.4f}  max diff {np.abs(att - ratt).max()}")
     assert np.array_equal(out.ActualTime, ref.ActualTime)                    # every instance ends exactly on TD[1]
     assert rel_err(out.ActualState, ref.ActualState).max() < tol
     assert (att == ratt).mean() >= same_frac and np.abs(att - ratt).max() <= max_diff
@@ -140,6 +141,7 @@ def test_impact_dynamics_events(refill, cases, pkg, oracle):
     ref, ratt, racc = oracle.run_oracle(wl, phases=phases)
     out, att, acc = pkg.run_workload(wl, phases=phases, lane_refill=refill)
     ok = np.array_equal(out.IntegerAccessories, ref.IntegerAccessories)
+    print(f"[parity impact refill={refill}] endpoint {rel_err(out.ActualState, ref.ActualState).max():.2e}  time {rel_err(out.ActualTime, ref.ActualTime).max():.2e}  same attempted {(att == ratt).mean():.4f}  max diff {np.abs(att - ratt).max()}")
     assert ok
     assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
     assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6
