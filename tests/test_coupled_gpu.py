@@ -41,12 +41,13 @@ def test_duffing_ring_events_accessories_dense_output(name, ccases, pkg, oracle)
     assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)   # event counters of every unit
     assert np.abs(att - ratt).max() <= 2 and np.abs(acc - racc).max() <= 2
     assert np.abs(out.IntegerSystemAccessories - ref.IntegerSystemAccessories).max() <= 2   # step counter kept by unit 0
-    assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-6                     # event-terminated phases
-    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-5
-    assert rel_err(out.UnitAccessories, ref.UnitAccessories).max() < 1e-5
-    assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
+    # observed on B200: states 5e-13, event-terminated end times 4e-15, identical step counts and dense indices on every system
+    assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-10                    # event-terminated phases
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-9
+    assert rel_err(out.UnitAccessories, ref.UnitAccessories).max() < 1e-9
+    assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-9
     same = out.DenseIndex == ref.DenseIndex
-    assert same.mean() >= 0.7
+    assert same.mean() >= 0.95
     n = int(min(ref.DenseIndex.min(), out.DenseIndex.min()))
     cols = np.where(same)[0]
     assert rel_err(out.DenseTime[:n - 1][:, cols], ref.DenseTime[:n - 1][:, cols]).max() < 1e-6

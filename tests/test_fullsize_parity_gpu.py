@@ -7,8 +7,9 @@ sweeps the small parity cases never visit (Lorenz near rho = 21, the impact osci
 and the coupled bubbles driven at up to 5 bar, where collapses are violent and the controller's exact-pow fallback and the
 forced minimum step are most likely to be reached).
 
-Tolerances (stated per north_star): adaptive RKCK45 endpoints relative 1e-6 (Lorenz, Keller-Miksis), 1e-5 (impact, event-terminated),
-1e-7 (coupled bubbles); step counts identical on the fraction of instances written at each assert, the rest within a few steps
+Tolerances (stated per north_star; observed on B200 in round 2: endpoints 2e-10 (Lorenz), 4e-10 (impact), 8e-14 (Keller-Miksis), 6e-15
+(coupled bubbles), step counts identical on EVERY sampled instance): adaptive RKCK45 endpoints relative 1e-8 (Lorenz, impact), 1e-10
+(Keller-Miksis), 1e-11 (coupled bubbles); step counts identical on >= 98 % of the sample, the rest within 2 steps
 (GPU and CPU differ by FMA contraction, CUDA-vs-glibc libm and the Newton root of the controller, i.e. O(1e-16) per step, which
 flips an accept/reject decision only when err and tol agree to ~1e-15)."""
 import copy
@@ -48,9 +49,9 @@ def test_c2_lorenz_full_launch_strided_sample_against_checker(pkg, workloads, or
     same = (att[idx] == ratt).mean()
     report("C2", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()))
     assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
-    assert err.max() < 1e-6
-    assert same >= 0.95 and np.abs(att[idx] - ratt).max() <= 3
-    assert (acc[idx] == racc).mean() >= 0.95 and np.abs(acc[idx] - racc).max() <= 3
+    assert err.max() < 1e-8
+    assert same >= 0.98 and np.abs(att[idx] - ratt).max() <= 2
+    assert (acc[idx] == racc).mean() >= 0.98 and np.abs(acc[idx] - racc).max() <= 2
 
 
 def test_c3_impact_full_launch_strided_sample_against_checker(pkg, workloads, oracle):
@@ -65,10 +66,10 @@ def test_c3_impact_full_launch_strided_sample_against_checker(pkg, workloads, or
     report("C3", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()),
            time_err=f"{rel_err(out.ActualTime[idx], ref.ActualTime).max():.2e}")
     assert np.array_equal(out.IntegerAccessories[:, idx], ref.IntegerAccessories)
-    assert err.max() < 1e-5
-    assert rel_err(out.ActualTime[idx], ref.ActualTime).max() < 1e-6
-    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-5
-    assert same >= 0.80 and np.abs(att[idx] - ratt).max() <= 12
+    assert err.max() < 1e-8
+    assert rel_err(out.ActualTime[idx], ref.ActualTime).max() < 1e-8
+    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-8
+    assert same >= 0.98 and np.abs(att[idx] - ratt).max() <= 2
 
 
 def test_c4_kellermiksis_dense_full_launch_strided_sample_against_checker(pkg, workloads, oracle):
@@ -84,14 +85,14 @@ def test_c4_kellermiksis_dense_full_launch_strided_sample_against_checker(pkg, w
     report("C4", instances=idx.size, max_err=f"{err.max():.2e}", same_steps=f"{same:.4f}", max_step_diff=int(np.abs(att[idx] - ratt).max()),
            same_dense_index=f"{same_di.mean():.4f}")
     assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
-    assert err.max() < 1e-6
-    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-6
-    assert same >= 0.90 and np.abs(att[idx] - ratt).max() <= 8
-    assert same_di.mean() >= 0.90
+    assert err.max() < 1e-10
+    assert rel_err(out.Accessories[:, idx], ref.Accessories).max() < 1e-10
+    assert same >= 0.98 and np.abs(att[idx] - ratt).max() <= 2
+    assert same_di.mean() >= 0.98
     n = int(ref.DenseIndex.min())
     cols = np.where(same_di)[0]
-    assert rel_err(out.DenseTime[:n][:, idx[cols]], ref.DenseTime[:n][:, cols]).max() < 1e-5
-    assert rel_err(out.DenseState[:n][:, :, idx[cols]], ref.DenseState[:n][:, :, cols]).max() < 1e-4
+    assert rel_err(out.DenseTime[:n][:, idx[cols]], ref.DenseTime[:n][:, cols]).max() < 1e-9
+    assert rel_err(out.DenseState[:n][:, :, idx[cols]], ref.DenseState[:n][:, :, cols]).max() < 1e-8
 
 
 @pytest.mark.parametrize("path", ["tensor_core", "scalar", "pilot_slice_forced"])
@@ -99,7 +100,7 @@ def test_c5_bench_sweep_0_to_5_bar_strided_sample_against_checker(path, pkg, ora
     """C5 exactly as bench.py runs it: bubble_ensemble(NS=8192, UPS=64), pressure amplitude linspace(0, 5) bar -- through the FP64
     tensor-core (DMMA) coupling with the default pilot slice + cost-ordered continuation, through the scalar coupling, and with the
     pilot-slice mechanism forced (DispatchOrder = 2).  48 strided systems including the last one (5 bar, the most violent collapse)
-    against the CPU checker.  Tolerance: endpoints 1e-7 relative, step counts within 1 on every system (the matrix product sums in
+    against the CPU checker.  Tolerance: endpoints 1e-11 relative (observed 6e-15), step counts within 1 on every system (the matrix product sums in
     a different order than the reference's single accumulator)."""
     WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
     wl = WC.bubble_ensemble(NS=8192, UPS=64)
@@ -114,6 +115,6 @@ def test_c5_bench_sweep_0_to_5_bar_strided_sample_against_checker(path, pkg, ora
            max_step_diff=int(np.abs(att[idx] - ratt).max()), steps_last=int(att[-1]), steps_first=int(att[0]))
     assert np.array_equal(out.ActualTime[idx], ref.ActualTime)
     assert np.isfinite(out.ActualState).all()
-    assert err.max() < 1e-7
+    assert err.max() < 1e-11
     assert np.abs(att[idx] - ratt).max() <= 1 and np.abs(acc[idx] - racc).max() <= 1
-    assert (att[idx] == ratt).mean() >= 0.9
+    assert (att[idx] == ratt).mean() >= 0.98
