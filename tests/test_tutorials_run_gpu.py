@@ -9,8 +9,9 @@ completion in a scratch directory and their output FILES are checked:
     strided subset of the sweep (the periodic windows agree return by return; chaotic windows are compared as sets);
   * TC1 ring of Duffing oscillators (coupled module, events, system accessories, dense output): Results.txt and the
     DenseOutput_<sid>.txt files against the checker;
-  * T1 (one object, two launches) and T7 (two objects, double buffering) integrate the same Duffing scan: their Duffing.txt files
-    must hold the same rows -- the asynchronous orchestration changes nothing; T8 (two devices) the same when two GPUs exist;
+  * T1 (one object, two launches), T7 (two objects, double buffering) and T8 (two devices) integrate the same Duffing scan and save
+    the same 32 returns: Duffing.txt against the checker (periodic windows return by return, chaotic ones by range), T8's file row
+    for row against T7's -- the asynchronous orchestration changes nothing;
   * T2 Lorenz (RK4 as shipped) and TC2 bubble ensemble (random geometry seeded by the clock) run to completion.
 """
 import importlib
@@ -112,27 +113,70 @@ def test_tc1_ring_tutorial_against_the_checker(pkg, oracle):
         assert np.abs(x0 - ref.DenseState[:m, 0, sid, 0]).max() < 1e-4
 
 
-def sorted_rows(path):
+DUFFING_NT = 46080          # both halves of the scan (Reference.cu:33, DoubleBuffering.cu:34)
+
+
+def duffing_scan(path):
+    """Duffing.txt -> [instance of the scan, save, column]: rows grouped by the control parameter k (first column), in file order (=
+    chronological for one instance).  Columns: k, B, x1, x2, three accessories (Reference.cu:181-198)."""
     rows = load_rows(path)
-    assert np.isfinite(rows).all()
-    return rows[np.lexsort(rows.T[::-1])]
+    assert rows.shape == (DUFFING_NT * 32, 7) and np.isfinite(rows).all()
+    order = np.argsort(rows[:, 0], kind="stable")
+    scan = rows[order].reshape(DUFFING_NT, 32, 7)
+    assert (scan[:, :, 0] == scan[:, :1, 0]).all()          # every k exactly 32 times
+    return scan
 
 
-def test_t1_and_t7_write_the_same_scan():
-    """T1: one solver object, two launches one after the other.  T7: two objects, copies of one overlapping the kernels of the other.
-    Same instances, same phases: the files must hold the same rows (compared as sorted sets; both go through the same kernel)."""
+def duffing_checker(workloads, oracle, tutorial_options, n=384):
+    """The CPU checker on a strided subset of the scan: the states after phases 1025 .. 1056, which is what all three programs save
+    (T1: 1024 transient launches, then 32 x (Solve, copy, save), Reference.cu:97-117; T7: 1 + 1024 launches, then 31 x (copy, Solve, save)
+    and a last copy, DoubleBuffering.cu:94-143; T8: 1 + 1023 launches, then 32 x (Solve, copy, save), MultiGPUSingleNode.cu:84-133)."""
+    from cases import subsample
+    wl = workloads.duffing_t1(NT=DUFFING_NT, algorithm=workloads.RKCK45, ndo=0)
+    if not tutorial_options:
+        # T7 / T8 set only these (DoubleBuffering.cu:62-76); everything else stays at the solver's defaults
+        wl.options = workloads.Options(ThreadsPerBlock=64, RelativeTolerance=np.full(2, 1e-9), AbsoluteTolerance=np.full(2, 1e-9),
+                                       EventDirection=np.array([-1, 0], np.int32))
+    idx = np.unique(np.linspace(0, DUFFING_NT - 1, n).round().astype(np.int64))
+    sub = subsample(wl, n)
+    assert np.array_equal(sub.buffers.ControlParameters[0], wl.buffers.ControlParameters[0][idx])
+    b, _, _ = oracle.run_oracle(sub, phases=1024, host_threads=8)
+    ref = []
+    for _ in range(32):
+        b, _, _ = oracle.run_oracle(sub, buffers=b, phases=1, host_threads=8)
+        ref.append(b.ActualState.T.copy())
+    return idx, np.array(ref).transpose(1, 0, 2)             # [n, 32, 2]
+
+
+def check_scan_against_checker(name, scan, idx, ref, stale_saves=0):
+    """Most of this scan is chaotic (about 3 instances in 4): after 1000 periods the device and the CPU sit on other points of the same
+    attractor.  The periodic windows (at most 16 distinct returns) must agree return by return to 1e-6 -- with `stale_saves` > 0 as
+    sets, for a program that reads its host arrays without waiting for the copy -- and the chaotic ones must stay inside the range the
+    checker's chaotic instances cover."""
+    got = scan[idx][:, :, 2:4]
+    assert np.allclose(scan[idx, 0, 0], np.linspace(0.2, 0.3, DUFFING_NT)[idx], rtol=1e-9, atol=0)
+    periodic = np.array([len(np.unique(np.round(ref[i, :, 0], 5))) <= 16 for i in range(ref.shape[0])])
+    assert 40 <= periodic.sum() <= ref.shape[0] - 40
+    if stale_saves == 0:
+        err = np.abs(got - ref).max(axis=(1, 2))
+    else:
+        d = np.abs(got[:, :, None, :] - ref[:, None, :, :]).max(-1)          # [n, got save, ref save]
+        err = np.maximum(d.min(2).max(1), d.min(1).max(1))
+    ok = err[periodic] < (1e-6 if stale_saves == 0 else 1e-5)          # a stale row is one return further from the limit cycle
+    print(f"[tutorial {name}] periodic instances {int(periodic.sum())} of {ref.shape[0]}: agree with the checker {ok.mean():.3f}, "
+          f"max error among them {err[periodic][ok].max():.2e}")
+    assert ok.mean() >= 0.97
+    lo, hi = ref[~periodic].min(axis=(0, 1)), ref[~periodic].max(axis=(0, 1))
+    span = hi - lo
+    assert (got[~periodic].min(axis=(0, 1)) >= lo - 0.1 * span).all() and (got[~periodic].max(axis=(0, 1)) <= hi + 0.1 * span).all()
+
+
+def test_t1_reference_tutorial_against_the_checker(workloads, oracle):
+    """T1: one solver object, the two halves of the scan one after the other, every launch waited for."""
     tmp1, out1 = run_tutorial("T1_Reference")
-    tmp7, out7 = run_tutorial("T7_DoubleBuffering")
     assert "Test finished" in out1
-    a, b = sorted_rows(os.path.join(tmp1, "Duffing.txt")), sorted_rows(os.path.join(tmp7, "Duffing.txt"))
-    assert a.shape == b.shape and a.shape[0] == 2 * 23040 * 32
-    # T7's own loop reads the host arrays right after ENQUEUEING the device-to-host copy (DoubleBuffering.cu:121-126: no
-    # SynchroniseSolver between SynchroniseFromDeviceToHost and SaveData), so a save may catch rows of the phase before; every row it
-    # writes must still be a row of the same scan: present in T1's file, or the state after the last transient phase (which T1 never saves)
-    known = set(map(bytes, np.ascontiguousarray(a)))
-    found = np.fromiter((bytes(r) in known for r in np.ascontiguousarray(b)), bool, b.shape[0])
-    print(f"[tutorial T7] rows of the double-buffered scan found in the sequential scan: {found.mean():.5f}")
-    assert found.mean() >= 0.96          # at most one of the 32 saves per object may be the unsaved phase
+    idx, ref = duffing_checker(workloads, oracle, tutorial_options=True)
+    check_scan_against_checker("T1", duffing_scan(os.path.join(tmp1, "Duffing.txt")), idx, ref)
     for tid in (0, 4789, 15479):
         lines = open(os.path.join(tmp1, f"DenseOutput_{tid}.txt")).read()
         assert "ControlParameters:" in lines and "Time series:" in lines
@@ -140,17 +184,35 @@ def test_t1_and_t7_write_the_same_scan():
         assert series.shape[1] == 3 and series.shape[0] >= 10 and (np.diff(series[:, 0]) > 0).all()
 
 
-def test_t8_two_devices_writes_the_same_scan_as_t1():
+def test_t7_double_buffering_tutorial_against_the_checker(workloads, oracle):
+    """T7: two objects, the copies of one overlapping the kernels of the other.  Its loop reads the host arrays right after ENQUEUEING
+    the device-to-host copy (DoubleBuffering.cu:121-127: SaveData follows SynchroniseFromDeviceToHost without a SynchroniseSolver), so
+    a save may catch rows of the save before: compared as sets per instance."""
+    tmp7, out7 = run_tutorial("T7_DoubleBuffering")
+    idx, ref = duffing_checker(workloads, oracle, tutorial_options=False)
+    check_scan_against_checker("T7", duffing_scan(os.path.join(tmp7, "Duffing.txt")), idx, ref, stale_saves=1)
+
+
+def test_t8_two_devices_writes_the_scan_of_t7(workloads, oracle):
+    """T8 on two devices (its configuration line set to devices 0 and 1, oracle/Makefile; the program as shipped -- devices 0 and 2 --
+    runs where a third GPU exists).  T8 waits for its copies (MultiGPUSingleNode.cu:127-132) and saves the same phases as T7 with the
+    same options, through the same kernel: against the checker return by return, and row for row the file T7 writes, up to the rows T7
+    reads too early."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    tmp1, _ = run_tutorial("T1_Reference")
-    tmp8, _ = run_tutorial("T8_MultiGPUSingleNode")
-    a, b = sorted_rows(os.path.join(tmp1, "Duffing.txt")), sorted_rows(os.path.join(tmp8, "Duffing.txt"))
-    known = set(map(bytes, np.ascontiguousarray(a)))
-    found = np.fromiter((bytes(r) in known for r in np.ascontiguousarray(b)), bool, b.shape[0])
-    print(f"[tutorial T8] rows of the two-device scan found in the sequential scan: {found.mean():.5f}")
-    assert a.shape == b.shape and found.all()          # T8 waits for its copies (MultiGPUSingleNode.cu:128-132): every row identical
+    programs = ["T8_MultiGPUSingleNode_dev01"] + (["T8_MultiGPUSingleNode"] if torch.cuda.device_count() >= 3 else [])
+    idx, ref = duffing_checker(workloads, oracle, tutorial_options=False)
+    tmp7, _ = run_tutorial("T7_DoubleBuffering")
+    scan7 = duffing_scan(os.path.join(tmp7, "Duffing.txt"))
+    for program in programs:
+        tmp8, out8 = run_tutorial(program)
+        assert "Test finished" in out8
+        scan8 = duffing_scan(os.path.join(tmp8, "Duffing.txt"))
+        check_scan_against_checker(program, scan8, idx, ref)
+        same = (scan8 == scan7).all(axis=2)
+        print(f"[tutorial {program}] rows identical to the double-buffered single-device scan: {same.mean():.5f}")
+        assert same.mean() >= 0.90
 
 
 def test_t2_lorenz_and_tc2_bubble_ensemble_tutorials_run_to_completion():
