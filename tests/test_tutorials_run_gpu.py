@@ -12,7 +12,9 @@ completion in a scratch directory and their output FILES are checked:
   * T1 (one object, two launches), T7 (two objects, double buffering) and T8 (two devices) integrate the same Duffing scan and save
     the same 32 returns: Duffing.txt against the checker (periodic windows return by return, chaotic ones by range), T8's file row
     for row against T7's -- the asynchronous orchestration changes nothing;
-  * T2 Lorenz (RK4 as shipped) and TC2 bubble ensemble (random geometry seeded by the clock) run to completion.
+  * T3 (the Duffing scan without events) and T5 (Keller-Miksis frequency sweep, 1088 launches of 46 080 bubbles) against the checker;
+  * T4 (dual-frequency bubbles, events), T2 Lorenz (RK4 as shipped) and TC2 bubble ensemble (random geometry seeded by the clock) run
+    to completion and write well-formed files.
 """
 import importlib
 import os
@@ -116,23 +118,23 @@ def test_tc1_ring_tutorial_against_the_checker(pkg, oracle):
 DUFFING_NT = 46080          # both halves of the scan (Reference.cu:33, DoubleBuffering.cu:34)
 
 
-def duffing_scan(path):
+def duffing_scan(path, columns=7):
     """Duffing.txt -> [instance of the scan, save, column]: rows grouped by the control parameter k (first column), in file order (=
-    chronological for one instance).  Columns: k, B, x1, x2, three accessories (Reference.cu:181-198)."""
+    chronological for one instance).  Columns: k, B, x1, x2, three accessories (Reference.cu:181-198); T3 writes k, x1, x2."""
     rows = load_rows(path)
-    assert rows.shape == (DUFFING_NT * 32, 7) and np.isfinite(rows).all()
+    assert rows.shape == (DUFFING_NT * 32, columns) and np.isfinite(rows).all()
     order = np.argsort(rows[:, 0], kind="stable")
-    scan = rows[order].reshape(DUFFING_NT, 32, 7)
+    scan = rows[order].reshape(DUFFING_NT, 32, columns)
     assert (scan[:, :, 0] == scan[:, :1, 0]).all()          # every k exactly 32 times
     return scan
 
 
-def duffing_checker(workloads, oracle, tutorial_options, n=384):
+def duffing_checker(workloads, oracle, tutorial_options, n=384, events=True):
     """The CPU checker on a strided subset of the scan: the states after phases 1025 .. 1056, which is what all three programs save
     (T1: 1024 transient launches, then 32 x (Solve, copy, save), Reference.cu:97-117; T7: 1 + 1024 launches, then 31 x (copy, Solve, save)
     and a last copy, DoubleBuffering.cu:94-143; T8: 1 + 1023 launches, then 32 x (Solve, copy, save), MultiGPUSingleNode.cu:84-133)."""
     from cases import subsample
-    wl = workloads.duffing_t1(NT=DUFFING_NT, algorithm=workloads.RKCK45, ndo=0)
+    wl = workloads.duffing_t1(NT=DUFFING_NT, algorithm=workloads.RKCK45, ndo=0) if events else workloads.poincare_t3(NT=DUFFING_NT, algorithm=workloads.RKCK45)
     if not tutorial_options:
         # T7 / T8 set only these (DoubleBuffering.cu:62-76); everything else stays at the solver's defaults
         wl.options = workloads.Options(ThreadsPerBlock=64, RelativeTolerance=np.full(2, 1e-9), AbsoluteTolerance=np.full(2, 1e-9),
@@ -148,12 +150,12 @@ def duffing_checker(workloads, oracle, tutorial_options, n=384):
     return idx, np.array(ref).transpose(1, 0, 2)             # [n, 32, 2]
 
 
-def check_scan_against_checker(name, scan, idx, ref, stale_saves=0):
+def check_scan_against_checker(name, scan, idx, ref, stale_saves=0, first_state_column=2):
     """Most of this scan is chaotic (about 3 instances in 4): after 1000 periods the device and the CPU sit on other points of the same
     attractor.  The periodic windows (at most 16 distinct returns) must agree return by return to 1e-6 -- with `stale_saves` > 0 as
     sets, for a program that reads its host arrays without waiting for the copy -- and the chaotic ones must stay inside the range the
     checker's chaotic instances cover."""
-    got = scan[idx][:, :, 2:4]
+    got = scan[idx][:, :, first_state_column:first_state_column + 2]
     assert np.allclose(scan[idx, 0, 0], np.linspace(0.2, 0.3, DUFFING_NT)[idx], rtol=1e-9, atol=0)
     periodic = np.array([len(np.unique(np.round(ref[i, :, 0], 5))) <= 16 for i in range(ref.shape[0])])
     assert 40 <= periodic.sum() <= ref.shape[0] - 40
@@ -213,6 +215,51 @@ def test_t8_two_devices_writes_the_scan_of_t7(workloads, oracle):
         same = (scan8 == scan7).all(axis=2)
         print(f"[tutorial {program}] rows identical to the double-buffered single-device scan: {same.mean():.5f}")
         assert same.mean() >= 0.90
+
+
+def test_t3_poincare_section_tutorial_against_the_checker(workloads, oracle):
+    """T3: the Duffing scan without events, all 46 080 instances in one launch (Poincare.cu:82-109)."""
+    tmp, out = run_tutorial("T3_PoincareSection")
+    idx, ref = duffing_checker(workloads, oracle, tutorial_options=True, events=False)
+    check_scan_against_checker("T3", duffing_scan(os.path.join(tmp, "DuffingPoincare.txt"), columns=3), idx, ref, first_state_column=1)
+
+
+def test_t5_keller_miksis_tutorial_against_the_checker(workloads, oracle):
+    """T5: 46 080 bubbles, 1024 transient + 64 recorded periods; KellerMiksis.txt holds id, frequency, the state after the transient
+    and the largest radius of the 64 periods (KellerMiksis.cu:63-106).  The checker on a strided subset: periodic bubbles agree to
+    1e-6; a few sit in chaotic windows of the frequency sweep."""
+    from cases import subsample
+    tmp, out = run_tutorial("T5_LargeTimeScaleDifferences", timeout=900)
+    rows = load_rows(os.path.join(tmp, "KellerMiksis.txt"))
+    NT = 46080
+    assert rows.shape == (NT, 5) and np.isfinite(rows).all() and np.array_equal(rows[:, 0], np.arange(NT))
+    wl = workloads.keller_miksis_t5(NT=NT, ndo=0)
+    idx = np.unique(np.linspace(0, NT - 1, 64).round().astype(np.int64))
+    sub = subsample(wl, 64)
+    assert np.allclose(rows[idx, 1], workloads.logspace(20.0, 1000.0, NT)[idx], rtol=1e-9)
+    b, _, _ = oracle.run_oracle(sub, phases=1024, host_threads=8)
+    state = b.ActualState.T.copy()
+    top = np.zeros(idx.size)
+    for _ in range(64):
+        b, _, _ = oracle.run_oracle(sub, buffers=b, phases=1, host_threads=8)
+        top = np.maximum(top, b.Accessories[0])
+    err = np.maximum(rel_err(rows[idx, 2:4], state).max(axis=1), rel_err(rows[idx, 4], top))
+    print(f"[tutorial T5] bubbles agreeing with the checker to 1e-6: {(err < 1e-6).mean():.3f}  median error {np.median(err):.2e}")
+    assert (err < 1e-6).mean() >= 0.80
+    assert (rows[:, 4] >= rows[:, 2] - 1e-9).all() and rows[:, 4].max() < 1.5 * top.max() + 1.0
+
+
+def test_t4_quasiperiodic_forcing_tutorial_runs_to_completion():
+    """T4: dual-frequency driven bubbles, 4 launches of 16 384 instances with two events and event-driven accessories; one file of
+    136 columns per launch (QuasiperiodicForcing.cu:93-190): parameters, times, 64 local maxima, 64 local minima."""
+    tmp, out = run_tutorial("T4_QuasiperiodicForcing", timeout=900)
+    files = sorted(f for f in os.listdir(tmp) if f.startswith("KellerMiksis_Collapse_"))
+    assert len(files) == 4, files
+    for f in files:
+        rows = load_rows(os.path.join(tmp, f))
+        assert rows.shape == (16384, 136) and np.isfinite(rows).all()
+        assert (rows[:, 8:72].max(axis=1) >= rows[:, 72:136].min(axis=1)).all()          # local maxima above local minima
+        assert (rows[:, 7] > 0).all()                                                       # the recorded periods took time
 
 
 def test_t2_lorenz_and_tc2_bubble_ensemble_tutorials_run_to_completion():
