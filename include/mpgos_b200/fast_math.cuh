@@ -226,6 +226,121 @@ MPGOS_FM_FN double pow(double x, double y)
 	return p;
 }
 
+// pow, sincospi and sincos of three unrelated arguments in ONE subroutine: x^y, (sin, cos)(pi a), (sin, cos)(b).  The three
+// evaluations are independent chains of dependent FP64 instructions (latency 8 cycles each); in one basic block the compiler
+// interleaves them, so a warp issues three instructions where it waited for one -- what a right-hand side of the Keller-Miksis type
+// needs when few warps are resident (the block-per-system kernel: 4 per scheduler) -- and two of the three calls with their
+// argument and result moves go away.  Outside the fast ranges of ANY of the three, all five results are the CUDA functions'.
+struct PowSinCos2 { double p, s1, c1, s2, c2; };
+
+static __device__ __noinline__ PowSinCos2 cuda_pow_sincospi_sincos(double x, double y, double a, double b)      // [cold>
+{
+	PowSinCos2 o;
+	o.p = ::pow(x, y);
+	::sincospi(a, &o.s1, &o.c1);
+	::sincos(b, &o.s2, &o.c2);
+	return o;
+}                                                                                                               // <cold]
+
+MPGOS_FM_FN PowSinCos2 pow_sincospi_sincos(double x, double y, double a, double b)
+{
+	PowSinCos2 o;
+	// --- reductions of the two trigonometric arguments
+	double two_over_pi, p1, p2, p3, pi_hi, pi_lo;
+	ldpair(FM_2OPI_PIO2A, two_over_pi, p1);
+	ldpair(FM_PIO2B_PIO2C, p2, p3);
+	ldpair(FM_PIHI_PILO, pi_hi, pi_lo);
+	const double tb = fma(b, two_over_pi, MPGOS_FM_MAGIC);
+	const double ta = fma(a, 2.0, MPGOS_FM_MAGIC);
+	const double nb = tb - MPGOS_FM_MAGIC;
+	const double na = ta - MPGOS_FM_MAGIC;
+	double rb = fma(-nb, p1, b);
+	const double ra0 = fma(na, -0.5, a);
+	rb = fma(-nb, p2, rb);
+	rb = fma(-nb, p3, rb);
+	const double ra = fma(ra0, pi_lo, ra0 * pi_hi);
+	// --- log of the base (as in pow above)
+	const int hx = __double2hiint(x);
+	const int h2 = hx + (0x3ff00000 - 0x3fe6a09e);
+	const int e = (h2 >> 20) - 0x3ff;
+	const double m = __hiloint2double((h2 & 0x000fffff) + 0x3fe6a09e, __double2loint(x));
+	const double ke = __hiloint2double(0x43300000, 0x80000000 ^ e) - 4503601774854144.0;
+	const double f = m - 1.0;
+	const double den = 2.0 + f;
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+	r = fma(r, fma(-den, r, 1.0), r);
+	r = fma(r, fma(-den, r, 1.0), r);
+	const double s = f * r;
+	const double z = s * s, w = z * z;
+	double lg6, lg7, lg4, lg5, lg2, lg3, lg1, l2e_hi, l2e_lo, ln2_hi, ln2_lo, c13, ca, cb;
+	// --- the two sine / cosine kernels side by side with the logarithm's polynomial
+	const double za = ra * ra, zb = rb * rb;
+	double psa, pca, psb, pcb;
+	ldpair(FM_S6C6, psa, pca);  psb = psa;  pcb = pca;
+	ldpair(FM_LG6_LG7, lg6, lg7);
+	ldpair(FM_S5C5, ca, cb);  psa = fma(psa, za, ca);  pca = fma(pca, za, cb);  psb = fma(psb, zb, ca);  pcb = fma(pcb, zb, cb);
+	ldpair(FM_LG4_LG5, lg4, lg5);
+	ldpair(FM_S4C4, ca, cb);  psa = fma(psa, za, ca);  pca = fma(pca, za, cb);  psb = fma(psb, zb, ca);  pcb = fma(pcb, zb, cb);
+	ldpair(FM_LG2_LG3, lg2, lg3);
+	ldpair(FM_S3C3, ca, cb);  psa = fma(psa, za, ca);  pca = fma(pca, za, cb);  psb = fma(psb, zb, ca);  pcb = fma(pcb, zb, cb);
+	ldpair(FM_LG1_L2EH, lg1, l2e_hi);
+	ldpair(FM_S2C2, ca, cb);  psa = fma(psa, za, ca);  pca = fma(pca, za, cb);  psb = fma(psb, zb, ca);  pcb = fma(pcb, zb, cb);
+	const double t1 = w * fma(w, fma(w, lg6, lg4), lg2);
+	const double t2 = z * fma(w, fma(w, fma(w, lg7, lg5), lg3), lg1);
+	ldpair(FM_S1C1, ca, cb);  psa = fma(psa, za, ca);  pca = fma(pca, za, cb);  psb = fma(psb, zb, ca);  pcb = fma(pcb, zb, cb);
+	const double hfsq = 0.5 * f * f;
+	const double logm = f - (hfsq - s * (hfsq + (t2 + t1)));
+	const double sa = fma(ra * za, psa, ra), sb = fma(rb * zb, psb, rb);
+	const double cca = fma(za * za, pca, fma(za, -0.5, 1.0)), ccb = fma(zb * zb, pcb, fma(zb, -0.5, 1.0));
+	{
+		const int qa = __double2loint(ta), qb = __double2loint(tb);
+		const bool odda = (qa & 1) != 0, oddb = (qb & 1) != 0;
+		const double ua = odda ? cca : sa, va = odda ? sa : cca, ub = oddb ? ccb : sb, vb = oddb ? sb : ccb;
+		o.s1 = __hiloint2double((int)((unsigned)__double2hiint(ua) ^ ((unsigned)(qa & 2) << 30)), __double2loint(ua));
+		o.c1 = __hiloint2double((int)((unsigned)__double2hiint(va) ^ ((unsigned)((qa + 1) & 2) << 30)), __double2loint(va));
+		o.s2 = __hiloint2double((int)((unsigned)__double2hiint(ub) ^ ((unsigned)(qb & 2) << 30)), __double2loint(ub));
+		o.c2 = __hiloint2double((int)((unsigned)__double2hiint(vb) ^ ((unsigned)((qb + 1) & 2) << 30)), __double2loint(vb));
+	}
+	// --- y log2(x) and 2^(.) (as in pow above)
+	ldpair(FM_L2EL_LN2H, l2e_lo, ln2_hi);
+	const double hi = fma(logm, l2e_hi, ke);
+	double lo = fma(logm, l2e_hi, ke - hi);
+	lo = fma(logm, l2e_lo, lo);
+	const double zh = y * hi;
+	const double zl = fma(y, lo, fma(y, hi, -zh));
+	const double tn = zh + MPGOS_FM_MAGIC;
+	const double n = tn - MPGOS_FM_MAGIC;
+	const double g = zh - n;
+	ldpair(FM_LN2L_E13, ln2_lo, c13);
+	const double t = fma(g, ln2_lo, g * ln2_hi);
+	const double tt = t * t;
+	double pe, po;
+	ldpair(FM_E12_E11, pe, po);      po = fma(c13, tt, po);
+	ldpair(FM_E10_E9, ca, cb);       pe = fma(pe, tt, ca);  po = fma(po, tt, cb);
+	ldpair(FM_E8_E7, ca, cb);        pe = fma(pe, tt, ca);  po = fma(po, tt, cb);
+	ldpair(FM_E6_E5, ca, cb);        pe = fma(pe, tt, ca);  po = fma(po, tt, cb);
+	ldpair(FM_E4_E3, ca, cb);        pe = fma(pe, tt, ca);  po = fma(po, tt, cb);
+	pe = fma(pe, tt, 0.5);
+	double p = fma(po, t, pe);
+	p = fma(p, tt, t);
+	p = p + 1.0;
+	p = fma(p, zl * ln2_hi, p);
+	o.p = p * __hiloint2double((__double2loint(tn) + 1023) << 20, 0);
+	if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u || !(fabs(zh) <= 1000.0) || !(fabs(a) <= 1073741824.0) || !(fabs(b) <= 1.0e6))
+		o = cuda_pow_sincospi_sincos(x, y, a, b);
+	return o;
+}
+__device__ __forceinline__ void pow_sincospi_sincos(double x, double y, double a, double b, double* p, double* s1, double* c1, double* s2, double* c2)
+{
+	const PowSinCos2 o = pow_sincospi_sincos(x, y, a, b);
+	*p = o.p;  *s1 = o.s1;  *c1 = o.c1;  *s2 = o.s2;  *c2 = o.c2;
+}
+__device__ __forceinline__ void pow_sincospi_sincos(float x, float y, float a, float b, float* p, float* s1, float* c1, float* s2, float* c2)
+{
+	*p = ::powf(x, y);  ::sincospif(a, s1, c1);  ::sincosf(b, s2, c2);
+}
+
 // 1 / x for normal finite x of either sign (|x| in [2^-1020, 2^1020]); <= 1 ulp; the division otherwise.  The compiler's own
 // sequence for 1.0 / x is the same Newton iteration plus a range check, a slow-path call and a correction step for correct rounding
 // (~24 issue cycles against ~11).
@@ -256,6 +371,8 @@ template <bool FAST> struct Math
 	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { mpgos_b200::fm::sincospi(x, s, c); }
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { mpgos_b200::fm::sincos(x, s, c); }      // one evaluation for both
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return mpgos_b200::fm::rcp(x); }
+	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
+	{ mpgos_b200::fm::pow_sincospi_sincos(x, y, a, b, p, s1, c1, s2, c2); }
 };
 template <> struct Math<false>
 {
@@ -265,6 +382,8 @@ template <> struct Math<false>
 	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { ::sincospi(x, s, c); }
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { *s = ::sin(x);  *c = ::cos(x); }         // the reference's two calls
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return P(1.0) / x; }
+	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
+	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
 };
 
 } // namespace fm

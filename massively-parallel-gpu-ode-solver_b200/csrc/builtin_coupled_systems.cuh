@@ -9,6 +9,10 @@
 #include <math.h>
 #include "../../include/mpgos_b200/fast_math.cuh"
 
+#ifndef MPGOS_B200_FM_BUNDLE
+#define MPGOS_B200_FM_BUNDLE 1      // A/B switch (tools/build_variant.sh): 0 = three separate subroutine calls
+#endif
+
 namespace mpgos_b200 {
 namespace builtin {
 
@@ -29,11 +33,16 @@ struct BubbleEnsembleT
 	{
 		const P PI = P(3.14159265358979323846);
 		const P rx1 = M::rcp_(X[0]);
-		const P p = M::pow_(rx1, uPAR[10]);
-		P s1, c1;
+		P p, s1, c1, s2, c2;
+#if MPGOS_B200_FM_BUNDLE
+		// one subroutine for the three transcendental evaluations of the right-hand side (fast_math.cuh; the CUDA-library form makes the
+		// reference's three calls)
+		M::pow_sincospi_sincos_(rx1, uPAR[10], P(2.0) * T, P(2.0) * uPAR[11] * PI * T + uPAR[12], &p, &s1, &c1, &s2, &c2);
+#else
+		p = M::pow_(rx1, uPAR[10]);
 		M::sincospi_(P(2.0) * T, &s1, &c1);
-		P s2, c2;
 		M::sincos_(P(2.0) * uPAR[11] * PI * T + uPAR[12], &s2, &c2);
+#endif
 		const P N = (uPAR[0] + uPAR[1] * X[1]) * p - uPAR[2] * (P(1.0) + uPAR[9] * X[1]) - uPAR[3] * rx1 - uPAR[4] * X[1] * rx1
 		          - P(1.5) * (P(1.0) - uPAR[9] * X[1] / P(3.0)) * X[1] * X[1] - (uPAR[5] * s1 + uPAR[6] * s2) * (P(1.0) + uPAR[9] * X[1])
 		          - X[0] * (uPAR[7] * c1 + uPAR[8] * c2);

@@ -985,13 +985,23 @@ __global__ void fast_math_probe_kernel(int function, int n, const double* __rest
 	double a = 0, b = 0, c = 0, d = 0;
 	if (function == 0)      { mpgos_b200::fm::sincos(x[i], &a, &b);    ::sincos(x[i], &c, &d); }
 	else if (function == 1) { mpgos_b200::fm::sincospi(x[i], &a, &b);  ::sincospi(x[i], &c, &d); }
-	else                    { a = mpgos_b200::fm::pow(x[i], y[i]);     c = ::pow(x[i], y[i]); }
+	else if (function == 2) { a = mpgos_b200::fm::pow(x[i], y[i]);     c = ::pow(x[i], y[i]); }
+	else
+	{
+		// the bundled subroutine: 3 = its pow (x^y; trigonometric arguments in range), 4 = its sincospi(x), 5 = its sincos(y)
+		double p, s1, c1, s2, c2;
+		if (function == 3) mpgos_b200::fm::pow_sincospi_sincos(x[i], y[i], 0.3 * y[i], 1.7 * y[i], &p, &s1, &c1, &s2, &c2);
+		else               mpgos_b200::fm::pow_sincospi_sincos(1.0 + 0.5 * ::fabs(::sin(x[i])), 4.2, x[i], y[i], &p, &s1, &c1, &s2, &c2);
+		if (function == 3)      { a = p;   c = ::pow(x[i], y[i]); }
+		else if (function == 4) { a = s1;  b = c1;  ::sincospi(x[i], &c, &d); }
+		else                    { a = s2;  b = c2;  ::sincos(y[i], &c, &d); }
+	}
 	out0[i] = a;  out1[i] = b;  ref0[i] = c;  ref1[i] = d;
 }
 
 int mpgos_fast_math_probe(int device, int function, int n, const double* x, const double* y, double* out0, double* out1, double* ref0, double* ref1)
 {
-	if (function < 0 || function > 2 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
+	if (function < 0 || function > 5 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
 	if (n == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(device));
 	double* d = nullptr;

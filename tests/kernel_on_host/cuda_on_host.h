@@ -74,6 +74,8 @@ template <bool FAST> struct Math
 	template <class P> static inline void sincospi_(P x, P* s, P* c) { sincospi(x, s, c); }
 	template <class P> static inline void sincos_(P x, P* s, P* c)   { *s = std::sin(x);  *c = std::cos(x); }
 	template <class P> static inline P    rcp_(P x)                  { return P(1.0) / x; }
+	template <class P> static inline void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
+	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
 };
 } }
 namespace mpgos_b200 {

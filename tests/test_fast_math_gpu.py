@@ -47,6 +47,40 @@ def test_sincos_sincospi_pow_accuracy_in_ulp(pkg):
         assert e <= 3.0
 
 
+def test_bundled_subroutine_accuracy_in_ulp(pkg):
+    """fm::pow_sincospi_sincos (one subroutine, three interleaved evaluations): the same bounds as the separate functions."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(12)
+    n = 4000
+    for (xl, xh, yl, yh) in ((0.5, 2.0, 1.0, 5.0), (1e-2, 1e2, 4.2, 4.2), (1e-3, 1e3, -6.0, 6.0)):
+        x = np.exp(rng.uniform(np.log(xl), np.log(xh), n))
+        y = rng.uniform(yl, yh, n)
+        p, _, rp, _ = pkg.fast_math_probe(3, x, y)
+        ref = [mp.power(mp.mpf(float(a)), mp.mpf(float(b))) for a, b in zip(x, y)]
+        e = ulps(p, ref)
+        print(f"[fast_math] bundle pow x in [{xl:g}, {xh:g}], y in [{yl:g}, {yh:g}]: {e:.2f} ulp (CUDA: {ulps(rp, ref):.2f})")
+        assert e <= 3.0
+    x = rng.uniform(-64.0, 64.0, n)
+    y = rng.uniform(-1.0e3, 1.0e3, n)
+    s, c, _, _ = pkg.fast_math_probe(4, x, y)
+    es, ec = ulps(s, [mp.sin(mp.pi * mp.mpf(float(v))) for v in x]), ulps(c, [mp.cos(mp.pi * mp.mpf(float(v))) for v in x])
+    s2, c2, _, _ = pkg.fast_math_probe(5, x, y)
+    es2, ec2 = ulps(s2, [mp.sin(mp.mpf(float(v))) for v in y]), ulps(c2, [mp.cos(mp.mpf(float(v))) for v in y])
+    print(f"[fast_math] bundle sincospi: {es:.2f} / {ec:.2f} ulp, sincos: {es2:.2f} / {ec2:.2f} ulp")
+    assert max(es, ec) <= 1.8 and max(es2, ec2) <= 1.6
+    # any argument outside its fast range: all five results are the CUDA functions'
+    x = np.array([np.inf, 3e9, np.nan, 0.25, 0.25])
+    y = np.array([1.0, 1.0, 1.0, 1e7, np.inf])
+    for f in (4, 5):
+        a, b, ra, rb = pkg.fast_math_probe(f, x, y)
+        assert np.array_equal(a, ra, equal_nan=True) and np.array_equal(b, rb, equal_nan=True)
+    x = np.array([0.0, -2.0, np.inf, np.nan, 5e-324, 2.0, 2.0])
+    y = np.array([2.0, 2.0, 0.5, 1.0, 2.0, 1e6, -1e6])
+    p, _, rp, _ = pkg.fast_math_probe(3, x, y)
+    assert np.array_equal(p, rp, equal_nan=True)
+
+
 def test_special_cases_are_the_cuda_functions(pkg):
     x = np.array([0.0, -0.0, -2.0, -8.0, np.inf, np.nan, 1.0, 2.0, 5e-324, 1e-310, 1e300, 1e-300, 3.0, 0.5, np.inf, 2.0, 2.0])
     y = np.array([2.0, -1.0, 2.0, 1.0 / 3.0, 0.5, 1.0, np.nan, np.inf, 2.0, 0.5, 2.0, 2.0, 0.0, -np.inf, -1.0, 1e6, -1e6])

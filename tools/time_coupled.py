@@ -8,10 +8,10 @@ WC = pkg.workloads_coupled
 NS = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 UPS = int(os.environ.get('UPS', '64'))
 DT = np.float32 if os.environ.get('F32') else np.float64
-wl = WC.bubble_ensemble(NS=NS, UPS=UPS, dtype=DT)
+wl = WC.bubble_ensemble(NS=NS, UPS=UPS, dtype=DT, fast_math=bool(os.environ.get('FM')))
 if os.environ.get('REVERSE'):      # the same sweep stored back to front
     wl.buffers = wl.buffers.take(np.arange(NS)[::-1])
-with pkg.CoupledProblemSolver("bubble_ensemble", NS, UPS, Precision=DT) as ps:
+with pkg.CoupledProblemSolver(wl.name, NS, UPS, Precision=DT) as ps:
     pkg.apply_coupled_workload(ps, wl)
     ps.SolverOption(pkg.CoupledOptions.TensorCoreCoupling, int(os.environ.get('TC', '1')))
     ps.SolverOption(pkg.CoupledOptions.DispatchOrder, int(os.environ.get('DISPATCH', '1')))

@@ -8,6 +8,7 @@ pkg = importlib.import_module("massively-parallel-gpu-ode-solver_b200")
 W = pkg.workloads
 GEN = {"lorenz": lambda: W.lorenz(NT=1 << 20), "lorenz_f32": lambda: W.lorenz(NT=1 << 20, dtype=np.float32), "impact": lambda: W.impact_t6(NT=1 << 20),
        "kellermiksis": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=0), "kellermiksis_dense": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=200),
+       "kellermiksis_dense_fm": lambda: W.keller_miksis_t5(NT=1 << 18, ndo=200, fast_math=True),
        "duffing": lambda: W.duffing_t1(NT=10000, algorithm=W.RK4)}
 lib = os.environ.get("MPGOS_B200_LIBRARY", "(default)").split("/")[-1]
 for spec in (sys.argv[1:] or ["impact:8", "kellermiksis:2", "lorenz:1"]):
