@@ -10,8 +10,8 @@ completion in a scratch directory and their output FILES are checked:
   * TC1 ring of Duffing oscillators (coupled module, events, system accessories, dense output): Results.txt and the
     DenseOutput_<sid>.txt files against the checker;
   * T1 (one object, two launches), T7 (two objects, double buffering) and T8 (two devices) integrate the same Duffing scan and save
-    the same 32 returns: Duffing.txt against the checker (periodic windows return by return, chaotic ones by range), T8's file row
-    for row against T7's -- the asynchronous orchestration changes nothing;
+    the same 32 returns: in Duffing.txt every saved return must be the checker's one-period image of the return saved before it
+    (chaotic instances included), T8's file row for row T7's -- the asynchronous orchestration changes nothing;
   * T3 (the Duffing scan without events) and T5 (Keller-Miksis frequency sweep, 1088 launches of 46 080 bubbles) against the checker;
   * T4 (dual-frequency bubbles, events), T2 Lorenz (RK4 as shipped) and TC2 bubble ensemble (random geometry seeded by the clock) run
     to completion and write well-formed files.
@@ -129,56 +129,64 @@ def duffing_scan(path, columns=7):
     return scan
 
 
-def duffing_checker(workloads, oracle, tutorial_options, n=384, events=True):
-    """The CPU checker on a strided subset of the scan: the states after phases 1025 .. 1056, which is what all three programs save
-    (T1: 1024 transient launches, then 32 x (Solve, copy, save), Reference.cu:97-117; T7: 1 + 1024 launches, then 31 x (copy, Solve, save)
-    and a last copy, DoubleBuffering.cu:94-143; T8: 1 + 1023 launches, then 32 x (Solve, copy, save), MultiGPUSingleNode.cu:84-133)."""
-    from cases import subsample
+def duffing_workload(workloads, tutorial_options, events):
     wl = workloads.duffing_t1(NT=DUFFING_NT, algorithm=workloads.RKCK45, ndo=0) if events else workloads.poincare_t3(NT=DUFFING_NT, algorithm=workloads.RKCK45)
     if not tutorial_options:
         # T7 / T8 set only these (DoubleBuffering.cu:62-76); everything else stays at the solver's defaults
         wl.options = workloads.Options(ThreadsPerBlock=64, RelativeTolerance=np.full(2, 1e-9), AbsoluteTolerance=np.full(2, 1e-9),
                                        EventDirection=np.array([-1, 0], np.int32))
+    return wl
+
+
+def check_scan_against_checker(name, scan, workloads, oracle, tutorial_options=True, events=True, first_state_column=2, stale_saves=False, n=384):
+    """Three instances in four of this scan are chaotic, and the periodic windows hold coexisting attractors reached through chaotic
+    transients: after 1000 periods the device and the CPU need not sit on the same orbit (measured: 84 % of the periodic instances do,
+    to 6e-11).  What IS determined: every saved return is the image of the one before under one period of the flow.  For a strided
+    subset of the scan, each saved state (as printed, 11 digits) is integrated over one phase by the CPU checker with the tutorial's
+    options and compared with the state the program saved next: 384 instances x 31 consecutive saves, chaotic or not, to 1e-6.
+    `stale_saves`: the program reads its host arrays without waiting for the copy, so a save may repeat the one before."""
+    import copy
     idx = np.unique(np.linspace(0, DUFFING_NT - 1, n).round().astype(np.int64))
-    sub = subsample(wl, n)
-    assert np.array_equal(sub.buffers.ControlParameters[0], wl.buffers.ControlParameters[0][idx])
+    got = scan[idx][:, :, first_state_column:first_state_column + 2]                     # [n, 32, 2]
+    assert np.allclose(scan[idx, 0, 0], np.linspace(0.2, 0.3, DUFFING_NT)[idx], rtol=1e-9, atol=0)
+    wl = duffing_workload(workloads, tutorial_options, events)
+    pairs = np.repeat(idx, 31)
+    sub = copy.copy(wl)
+    sub.buffers = wl.buffers.take(pairs)
+    sub.buffers.ActualState[0] = got[:, :31, 0].reshape(-1)
+    sub.buffers.ActualState[1] = got[:, :31, 1].reshape(-1)
+    out, _, _ = oracle.run_oracle(sub, phases=1, host_threads=8)
+    nxt = out.ActualState.T.reshape(idx.size, 31, 2)
+    err = np.abs(nxt - got[:, 1:, :]).max(axis=2)                                         # [n, 31]
+    ok = err < 1e-6
+    if stale_saves:
+        ok |= (got[:, 1:, :] == got[:, :31, :]).all(axis=2)                               # the save before, read again
+    print(f"[tutorial {name}] saved returns that are the checker's image of the return before: {ok.mean():.5f} of {ok.size}, "
+          f"largest error among them {err[err < 1e-6].max():.2e}")
+    assert ok.mean() >= (0.90 if stale_saves else 1.0)
+    # the orbit itself where it is unique: periodic instances whose attractor the checker's own 1056 periods reach too
+    sub = copy.copy(wl)
+    sub.buffers = wl.buffers.take(idx)
     b, _, _ = oracle.run_oracle(sub, phases=1024, host_threads=8)
     ref = []
     for _ in range(32):
         b, _, _ = oracle.run_oracle(sub, buffers=b, phases=1, host_threads=8)
         ref.append(b.ActualState.T.copy())
-    return idx, np.array(ref).transpose(1, 0, 2)             # [n, 32, 2]
-
-
-def check_scan_against_checker(name, scan, idx, ref, stale_saves=0, first_state_column=2):
-    """Most of this scan is chaotic (about 3 instances in 4): after 1000 periods the device and the CPU sit on other points of the same
-    attractor.  The periodic windows (at most 16 distinct returns) must agree return by return to 1e-6 -- with `stale_saves` > 0 as
-    sets, for a program that reads its host arrays without waiting for the copy -- and the chaotic ones must stay inside the range the
-    checker's chaotic instances cover."""
-    got = scan[idx][:, :, first_state_column:first_state_column + 2]
-    assert np.allclose(scan[idx, 0, 0], np.linspace(0.2, 0.3, DUFFING_NT)[idx], rtol=1e-9, atol=0)
+    ref = np.array(ref).transpose(1, 0, 2)
     periodic = np.array([len(np.unique(np.round(ref[i, :, 0], 5))) <= 16 for i in range(ref.shape[0])])
-    assert 40 <= periodic.sum() <= ref.shape[0] - 40
-    if stale_saves == 0:
-        err = np.abs(got - ref).max(axis=(1, 2))
-    else:
-        d = np.abs(got[:, :, None, :] - ref[:, None, :, :]).max(-1)          # [n, got save, ref save]
-        err = np.maximum(d.min(2).max(1), d.min(1).max(1))
-    ok = err[periodic] < (1e-6 if stale_saves == 0 else 1e-5)          # a stale row is one return further from the limit cycle
-    print(f"[tutorial {name}] periodic instances {int(periodic.sum())} of {ref.shape[0]}: agree with the checker {ok.mean():.3f}, "
-          f"max error among them {err[periodic][ok].max():.2e}")
-    assert ok.mean() >= 0.97
-    lo, hi = ref[~periodic].min(axis=(0, 1)), ref[~periodic].max(axis=(0, 1))
-    span = hi - lo
-    assert (got[~periodic].min(axis=(0, 1)) >= lo - 0.1 * span).all() and (got[~periodic].max(axis=(0, 1)) <= hi + 0.1 * span).all()
+    d = np.abs(got[:, :, None, :] - ref[:, None, :, :]).max(-1)
+    same_orbit = np.maximum(d.min(2).max(1), d.min(1).max(1))[periodic] < 1e-5
+    print(f"[tutorial {name}] periodic instances {int(periodic.sum())} of {ref.shape[0]}: on the checker's orbit {same_orbit.mean():.3f}")
+    assert same_orbit.mean() >= 0.6
+    lo, hi = ref.min(axis=(0, 1)), ref.max(axis=(0, 1))
+    assert (got.min(axis=(0, 1)) >= lo - 0.1 * (hi - lo)).all() and (got.max(axis=(0, 1)) <= hi + 0.1 * (hi - lo)).all()
 
 
 def test_t1_reference_tutorial_against_the_checker(workloads, oracle):
     """T1: one solver object, the two halves of the scan one after the other, every launch waited for."""
     tmp1, out1 = run_tutorial("T1_Reference")
     assert "Test finished" in out1
-    idx, ref = duffing_checker(workloads, oracle, tutorial_options=True)
-    check_scan_against_checker("T1", duffing_scan(os.path.join(tmp1, "Duffing.txt")), idx, ref)
+    check_scan_against_checker("T1", duffing_scan(os.path.join(tmp1, "Duffing.txt")), workloads, oracle)
     for tid in (0, 4789, 15479):
         lines = open(os.path.join(tmp1, f"DenseOutput_{tid}.txt")).read()
         assert "ControlParameters:" in lines and "Time series:" in lines
@@ -191,8 +199,7 @@ def test_t7_double_buffering_tutorial_against_the_checker(workloads, oracle):
     the device-to-host copy (DoubleBuffering.cu:121-127: SaveData follows SynchroniseFromDeviceToHost without a SynchroniseSolver), so
     a save may catch rows of the save before: compared as sets per instance."""
     tmp7, out7 = run_tutorial("T7_DoubleBuffering")
-    idx, ref = duffing_checker(workloads, oracle, tutorial_options=False)
-    check_scan_against_checker("T7", duffing_scan(os.path.join(tmp7, "Duffing.txt")), idx, ref, stale_saves=1)
+    check_scan_against_checker("T7", duffing_scan(os.path.join(tmp7, "Duffing.txt")), workloads, oracle, tutorial_options=False, stale_saves=True)
 
 
 def test_t8_two_devices_writes_the_scan_of_t7(workloads, oracle):
@@ -204,14 +211,13 @@ def test_t8_two_devices_writes_the_scan_of_t7(workloads, oracle):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     programs = ["T8_MultiGPUSingleNode_dev01"] + (["T8_MultiGPUSingleNode"] if torch.cuda.device_count() >= 3 else [])
-    idx, ref = duffing_checker(workloads, oracle, tutorial_options=False)
     tmp7, _ = run_tutorial("T7_DoubleBuffering")
     scan7 = duffing_scan(os.path.join(tmp7, "Duffing.txt"))
     for program in programs:
         tmp8, out8 = run_tutorial(program)
         assert "Test finished" in out8
         scan8 = duffing_scan(os.path.join(tmp8, "Duffing.txt"))
-        check_scan_against_checker(program, scan8, idx, ref)
+        check_scan_against_checker(program, scan8, workloads, oracle, tutorial_options=False)
         same = (scan8 == scan7).all(axis=2)
         print(f"[tutorial {program}] rows identical to the double-buffered single-device scan: {same.mean():.5f}")
         assert same.mean() >= 0.90
@@ -220,8 +226,7 @@ def test_t8_two_devices_writes_the_scan_of_t7(workloads, oracle):
 def test_t3_poincare_section_tutorial_against_the_checker(workloads, oracle):
     """T3: the Duffing scan without events, all 46 080 instances in one launch (Poincare.cu:82-109)."""
     tmp, out = run_tutorial("T3_PoincareSection")
-    idx, ref = duffing_checker(workloads, oracle, tutorial_options=True, events=False)
-    check_scan_against_checker("T3", duffing_scan(os.path.join(tmp, "DuffingPoincare.txt"), columns=3), idx, ref, first_state_column=1)
+    check_scan_against_checker("T3", duffing_scan(os.path.join(tmp, "DuffingPoincare.txt"), columns=3), workloads, oracle, events=False, first_state_column=1)
 
 
 def test_t5_keller_miksis_tutorial_against_the_checker(workloads, oracle):
