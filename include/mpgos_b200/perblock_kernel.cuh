@@ -71,7 +71,14 @@ struct PerBlockArgs
 };
 
 // resident blocks per SM the kernel is compiled for: as many as keep 512 threads (128 registers each) on the SM
-__host__ __device__ constexpr int coupled_min_blocks(int threads) { return threads >= 512 ? 1 : (512 / threads > 4 ? 4 : 512 / threads); }
+// (MPGOS_B200_COUPLED_THREADS_PER_SM: A/B builds with 768 threads at 80 registers or 1024 at 64)
+#ifndef MPGOS_B200_COUPLED_THREADS_PER_SM
+#define MPGOS_B200_COUPLED_THREADS_PER_SM 512
+#endif
+__host__ __device__ constexpr int coupled_min_blocks(int threads)
+{
+	return threads >= MPGOS_B200_COUPLED_THREADS_PER_SM ? 1 : (MPGOS_B200_COUPLED_THREADS_PER_SM / threads > 4 ? 4 : MPGOS_B200_COUPLED_THREADS_PER_SM / threads);
+}
 
 __host__ __device__ constexpr int packed_matrix_elements(int UPS, int NC, int CBW, int CCI)
 {

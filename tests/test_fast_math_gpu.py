@@ -81,6 +81,33 @@ def test_bundled_subroutine_accuracy_in_ulp(pkg):
     assert np.array_equal(p, rp, equal_nan=True)
 
 
+def test_bundle_with_reciprocals(pkg):
+    """fm::pow_sincospi_sincos_rcp2: reciprocals <= 1 ulp (against the correctly rounded division), pow and sine as above; zero, Inf,
+    NaN or a subnormal divisor hand all results to the CUDA functions."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 200
+    rng = np.random.default_rng(13)
+    n = 4000
+    x = np.exp(rng.uniform(np.log(1e-200), np.log(1e200), n)) * rng.choice([-1.0, 1.0], n)
+    y = np.exp(rng.uniform(np.log(1e-3), np.log(1e3), n))
+    ru, rv, du, dv = pkg.fast_math_probe(6, x, y)
+    eu = np.abs(ru - du) / np.spacing(np.abs(du))
+    ev = np.abs(rv - dv) / np.spacing(np.abs(dv))
+    print(f"[fast_math] bundle reciprocals: {eu.max():.2f} / {ev.max():.2f} ulp from the rounded quotient")
+    assert eu.max() <= 1.0 and ev.max() <= 1.0
+    x = np.exp(rng.uniform(np.log(1e-2), np.log(1e2), n))
+    y = rng.uniform(-6.0, 6.0, n)
+    p, s, rp, rs = pkg.fast_math_probe(7, x, y)
+    ep = ulps(p, [mp.power(mp.mpf(float(a)), mp.mpf(float(b))) for a, b in zip(x, y)])
+    es = ulps(s, [mp.sin(mp.mpf(float(v))) for v in y])
+    print(f"[fast_math] bundle with reciprocals: pow {ep:.2f} ulp, sin {es:.2f} ulp")
+    assert ep <= 3.0 and es <= 1.6
+    x = np.array([0.0, np.inf, np.nan, 5e-324, 2.0, -0.0])
+    y = np.array([3.0, 3.0, 3.0, 3.0, 0.0, 1e-320])
+    ru, rv, du, dv = pkg.fast_math_probe(6, x, y)
+    assert np.array_equal(ru, du, equal_nan=True) and np.array_equal(rv, dv, equal_nan=True)
+
+
 def test_special_cases_are_the_cuda_functions(pkg):
     x = np.array([0.0, -0.0, -2.0, -8.0, np.inf, np.nan, 1.0, 2.0, 5e-324, 1e-310, 1e300, 1e-300, 3.0, 0.5, np.inf, 2.0, 2.0])
     y = np.array([2.0, -1.0, 2.0, 1.0 / 3.0, 0.5, 1.0, np.nan, np.inf, 2.0, 0.5, 2.0, 2.0, 0.0, -np.inf, -1.0, 1e6, -1e6])
