@@ -88,7 +88,9 @@ __device__ __forceinline__ void ldpair(int pair, double& a, double& b)
 static __device__ __noinline__ void   cuda_sincos(double x, double* s, double* c)   { ::sincos(x, s, c); }      // [cold>
 static __device__ __noinline__ void   cuda_sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
 static __device__ __noinline__ double cuda_pow(double x, double y)                  { return ::pow(x, y); }
-static __device__ __noinline__ double cuda_rcp(double x)                            { return 1.0 / x; }         // <cold]
+static __device__ __noinline__ double cuda_rcp(double x)                            { return 1.0 / x; }
+struct Rcp2 { double a, b; };
+static __device__ __noinline__ Rcp2   cuda_rcp2(double a, double b)                 { Rcp2 o;  o.a = 1.0 / a;  o.b = 1.0 / b;  return o; }      // <cold]
 
 // The three functions are real subroutines by default (MPGOS_B200_FM_INLINE 0).  Inlined into a step loop, their ~45 constants are
 // loop invariants: the compiler hoists the loads, runs out of the 63 uniform registers, parks the rest in vector registers and moves
@@ -222,7 +224,7 @@ MPGOS_FM_FN double pow(double x, double y)
 	p = fma(p, zl * ln2_hi, p);                                                   // e^(zl ln 2) = 1 + zl ln 2
 	p = p * __hiloint2double((__double2loint(tn) + 1023) << 20, 0);
 	// zero, subnormal, negative, Inf, NaN base; overflow, underflow, y = NaN / Inf
-	if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u || !(fabs(zh) <= 1000.0)) p = cuda_pow(x, y);
+	if (((unsigned)(hx - 0x00100000) >= 0x7fe00000u) | !(fabs(zh) <= 1000.0)) p = cuda_pow(x, y);      // bitwise: one branch
 	return p;
 }
 
@@ -231,12 +233,7 @@ MPGOS_FM_FN double pow(double x, double y)
 // interleaves them, so a warp issues three instructions where it waited for one -- what a right-hand side of the Keller-Miksis type
 // needs when few warps are resident (the block-per-system kernel: 4 per scheduler) -- and two of the three calls with their
 // argument and result moves go away.  Outside the fast ranges of ANY of the three, all five results are the CUDA functions'.
-//
-// The second form adds two reciprocals, 1/u and 1/v (two more independent chains: a Keller-Miksis right-hand side divides by the
-// radius and by the denominator of the acceleration): the whole transcendental and division work of such a right-hand side in one
-// basic block, five chains deep.
 struct PowSinCos2 { double p, s1, c1, s2, c2; };
-struct PowSinCos2Rcp2 { double p, s1, c1, s2, c2, ru, rv; };
 
 static __device__ __noinline__ PowSinCos2 cuda_pow_sincospi_sincos(double x, double y, double a, double b)      // [cold>
 {
@@ -245,35 +242,11 @@ static __device__ __noinline__ PowSinCos2 cuda_pow_sincospi_sincos(double x, dou
 	::sincospi(a, &o.s1, &o.c1);
 	::sincos(b, &o.s2, &o.c2);
 	return o;
-}
-static __device__ __noinline__ PowSinCos2Rcp2 cuda_pow_sincospi_sincos_rcp2(double x, double y, double a, double b, double u, double v)
-{
-	PowSinCos2Rcp2 o;
-	o.p = ::pow(x, y);
-	::sincospi(a, &o.s1, &o.c1);
-	::sincos(b, &o.s2, &o.c2);
-	o.ru = 1.0 / u;
-	o.rv = 1.0 / v;
-	return o;
 }                                                                                                               // <cold]
 
-__device__ __forceinline__ void store_rcp2(PowSinCos2&, double, double) {}
-__device__ __forceinline__ void store_rcp2(PowSinCos2Rcp2& o, double ru, double rv) { o.ru = ru;  o.rv = rv; }
-template <class Out> __device__ __forceinline__ Out cuda_bundle(double x, double y, double a, double b, double u, double v);
-template <> __device__ __forceinline__ PowSinCos2 cuda_bundle<PowSinCos2>(double x, double y, double a, double b, double, double) { return cuda_pow_sincospi_sincos(x, y, a, b); }
-template <> __device__ __forceinline__ PowSinCos2Rcp2 cuda_bundle<PowSinCos2Rcp2>(double x, double y, double a, double b, double u, double v) { return cuda_pow_sincospi_sincos_rcp2(x, y, a, b, u, v); }
-
-// the body shared by both forms; RCP2 adds the two reciprocal chains
-template <bool RCP2, class Out>
-__device__ __forceinline__ Out pow_sincospi_sincos_body(double x, double y, double a, double b, double u, double v)
+MPGOS_FM_FN PowSinCos2 pow_sincospi_sincos(double x, double y, double a, double b)
 {
-	Out o;
-	double ru = 0.0, rv = 0.0;
-	if (RCP2)
-	{
-		asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ru) : "d"(u));
-		asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rv) : "d"(v));
-	}
+	PowSinCos2 o;
 	// --- reductions of the two trigonometric arguments
 	double two_over_pi, p1, p2, p3, pi_hi, pi_lo;
 	ldpair(FM_2OPI_PIO2A, two_over_pi, p1);
@@ -299,9 +272,7 @@ __device__ __forceinline__ Out pow_sincospi_sincos_body(double x, double y, doub
 	double r;
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
 	r = fma(r, fma(-den, r, 1.0), r);
-	if (RCP2) { ru = fma(ru, fma(-u, ru, 1.0), ru);  rv = fma(rv, fma(-v, rv, 1.0), rv); }
 	r = fma(r, fma(-den, r, 1.0), r);
-	if (RCP2) { ru = fma(ru, fma(-u, ru, 1.0), ru);  rv = fma(rv, fma(-v, rv, 1.0), rv); }
 	const double s = f * r;
 	const double z = s * s, w = z * z;
 	double lg6, lg7, lg4, lg5, lg2, lg3, lg1, l2e_hi, l2e_lo, ln2_hi, ln2_lo, c13, ca, cb;
@@ -358,24 +329,9 @@ __device__ __forceinline__ Out pow_sincospi_sincos_body(double x, double y, doub
 	p = p + 1.0;
 	p = fma(p, zl * ln2_hi, p);
 	o.p = p * __hiloint2double((__double2loint(tn) + 1023) << 20, 0);
-	bool bad = (unsigned)(hx - 0x00100000) >= 0x7fe00000u || !(fabs(zh) <= 1000.0) || !(fabs(a) <= 1073741824.0) || !(fabs(b) <= 1.0e6);
-	if (RCP2)
-	{
-		bad = bad || (unsigned)((__double2hiint(u) & 0x7fffffff) - 0x00300000) >= 0x7fa00000u
-		          || (unsigned)((__double2hiint(v) & 0x7fffffff) - 0x00300000) >= 0x7fa00000u;
-		store_rcp2(o, ru, rv);
-	}
-	if (bad) o = cuda_bundle<Out>(x, y, a, b, u, v);
+	const bool bad = ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) | !(fabs(zh) <= 1000.0) | !(fabs(a) <= 1073741824.0) | !(fabs(b) <= 1.0e6);      // bitwise: one branch
+	if (bad) o = cuda_pow_sincospi_sincos(x, y, a, b);
 	return o;
-}
-
-MPGOS_FM_FN PowSinCos2 pow_sincospi_sincos(double x, double y, double a, double b)
-{
-	return pow_sincospi_sincos_body<false, PowSinCos2>(x, y, a, b, 0.0, 0.0);
-}
-MPGOS_FM_FN PowSinCos2Rcp2 pow_sincospi_sincos_rcp2(double x, double y, double a, double b, double u, double v)
-{
-	return pow_sincospi_sincos_body<true, PowSinCos2Rcp2>(x, y, a, b, u, v);
 }
 __device__ __forceinline__ void pow_sincospi_sincos(double x, double y, double a, double b, double* p, double* s1, double* c1, double* s2, double* c2)
 {
@@ -385,17 +341,6 @@ __device__ __forceinline__ void pow_sincospi_sincos(double x, double y, double a
 __device__ __forceinline__ void pow_sincospi_sincos(float x, float y, float a, float b, float* p, float* s1, float* c1, float* s2, float* c2)
 {
 	*p = ::powf(x, y);  ::sincospif(a, s1, c1);  ::sincosf(b, s2, c2);
-}
-__device__ __forceinline__ void pow_sincospi_sincos_rcp2(double x, double y, double a, double b, double u, double v,
-                                                         double* p, double* s1, double* c1, double* s2, double* c2, double* ru, double* rv)
-{
-	const PowSinCos2Rcp2 o = pow_sincospi_sincos_rcp2(x, y, a, b, u, v);
-	*p = o.p;  *s1 = o.s1;  *c1 = o.c1;  *s2 = o.s2;  *c2 = o.c2;  *ru = o.ru;  *rv = o.rv;
-}
-__device__ __forceinline__ void pow_sincospi_sincos_rcp2(float x, float y, float a, float b, float u, float v,
-                                                         float* p, float* s1, float* c1, float* s2, float* c2, float* ru, float* rv)
-{
-	*p = ::powf(x, y);  ::sincospif(a, s1, c1);  ::sincosf(b, s2, c2);  *ru = 1.0f / u;  *rv = 1.0f / v;
 }
 
 // 1 / x for normal finite x of either sign (|x| in [2^-1020, 2^1020]); <= 1 ulp; the division otherwise.  The compiler's own
@@ -411,6 +356,26 @@ __device__ __forceinline__ double rcp(double x)
 	return r;
 }
 __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+// two reciprocals side by side: one basic block (the two Newton chains interleave), one range check for both
+__device__ __forceinline__ void rcp2(double a, double b, double* ra, double* rb)
+{
+	double r, q;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(b));
+	r = fma(r, fma(-a, r, 1.0), r);
+	q = fma(q, fma(-b, q, 1.0), q);
+	r = fma(r, fma(-a, r, 1.0), r);
+	q = fma(q, fma(-b, q, 1.0), q);
+	// (one unsigned comparison for both: the larger of the two biased exponent words; bitwise, not short-circuit: one branch)
+	const unsigned ka = (unsigned)((__double2hiint(a) & 0x7fffffff) - 0x00300000), kb = (unsigned)((__double2hiint(b) & 0x7fffffff) - 0x00300000);
+	if (max(ka, kb) >= 0x7fa00000u)
+	{
+		const Rcp2 o = cuda_rcp2(a, b);
+		r = o.a;  q = o.b;
+	}
+	*ra = r;  *rb = q;
+}
+__device__ __forceinline__ void rcp2(float a, float b, float* ra, float* rb) { *ra = 1.0f / a;  *rb = 1.0f / b; }
 
 // single precision: the CUDA functions
 __device__ __forceinline__ void  sincos(float x, float* s, float* c)   { ::sincosf(x, s, c); }
@@ -430,8 +395,7 @@ template <bool FAST> struct Math
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return mpgos_b200::fm::rcp(x); }
 	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
 	{ mpgos_b200::fm::pow_sincospi_sincos(x, y, a, b, p, s1, c1, s2, c2); }
-	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_rcp2_(P x, P y, P a, P b, P u, P v, P* p, P* s1, P* c1, P* s2, P* c2, P* ru, P* rv)
-	{ mpgos_b200::fm::pow_sincospi_sincos_rcp2(x, y, a, b, u, v, p, s1, c1, s2, c2, ru, rv); }
+	template <class P> static __device__ __forceinline__ void rcp2_(P a, P b, P* ra, P* rb)      { mpgos_b200::fm::rcp2(a, b, ra, rb); }
 };
 template <> struct Math<false>
 {
@@ -443,8 +407,7 @@ template <> struct Math<false>
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return P(1.0) / x; }
 	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
 	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
-	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_rcp2_(P x, P y, P a, P b, P u, P v, P* p, P* s1, P* c1, P* s2, P* c2, P* ru, P* rv)
-	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2);  *ru = rcp_(u);  *rv = rcp_(v); }
+	template <class P> static __device__ __forceinline__ void rcp2_(P a, P b, P* ra, P* rb)      { *ra = P(1.0) / a;  *rb = P(1.0) / b; }
 };
 
 } // namespace fm

@@ -12,7 +12,7 @@
 #include "../../include/mpgos_b200/fast_math.cuh"
 
 #ifndef MPGOS_B200_FM_BUNDLE
-#define MPGOS_B200_FM_BUNDLE 2      // A/B switch (tools/build_variant.sh): 0 = three separate subroutine calls, 1 = one for pow + sincospi + sincos, 2 = ... and both reciprocals
+#define MPGOS_B200_FM_BUNDLE 1      // A/B switch (tools/build_variant.sh): 0 = the fast-math forms make three separate subroutine calls, as the CUDA-library forms do
 #endif
 
 namespace mpgos_b200 {
@@ -164,39 +164,35 @@ struct KellerMiksisT : Empty<P>
 	MPGOS_DEV OdeFunction(MPGOS_ODE_ARGS(P))
 	{
 		const P PI = P(3.14159265358979323846);
-		P rx1, rD, p, s1, c1, s2, c2;
+		P rx1, rD, p, s1, c1, s2, c2, N;
 		const P D = X[0] - cPAR[9] * X[0] * X[1] + cPAR[4] * cPAR[9];
-#if MPGOS_B200_FM_BUNDLE == 2
+#if MPGOS_B200_FM_BUNDLE
 		if (FAST)
 		{
-			// fast-math form: (1/x)^y as x^(-y) (no reciprocal ahead of the logarithm) and both reciprocals of the right-hand side inside
-			// the same subroutine -- five independent chains in one basic block
-			M::pow_sincospi_sincos_rcp2_(X[0], -cPAR[10], P(2.0) * T, P(2.0) * cPAR[11] * PI * T + cPAR[12], X[0], D, &p, &s1, &c1, &s2, &c2, &rx1, &rD);
+			// fast-math form: the two reciprocals side by side, ONE subroutine for the three transcendental evaluations (fast_math.cuh),
+			// and the seven terms of the numerator summed as a tree: the four that need no transcendental ahead of the call, the other
+			// three side by side after it (the reference's left-to-right sum is a chain of seven dependent additions)
+			M::rcp2_(X[0], D, &rx1, &rD);
+			const P w = P(1.0) + cPAR[9] * X[1];
+			const P Q = -(cPAR[2] * w) - cPAR[3] * rx1 - cPAR[4] * X[1] * rx1 - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1];
+			M::pow_sincospi_sincos_(rx1, cPAR[10], P(2.0) * T, P(2.0) * cPAR[11] * PI * T + cPAR[12], &p, &s1, &c1, &s2, &c2);
+			const P u = (cPAR[0] + cPAR[1] * X[1]) * p + Q;
+			const P v = (cPAR[5] * s1 + cPAR[6] * s2) * w;
+			const P g = X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
+			N = (u - v) - g;
 		}
 		else
+#endif
 		{
 			rx1 = M::rcp_(X[0]);
 			p = M::pow_(rx1, cPAR[10]);
 			M::sincospi_(P(2.0) * T, &s1, &c1);
 			M::sincos_(P(2.0) * cPAR[11] * PI * T + cPAR[12], &s2, &c2);
+			N = (cPAR[0] + cPAR[1] * X[1]) * p - cPAR[2] * (P(1.0) + cPAR[9] * X[1]) - cPAR[3] * rx1 - cPAR[4] * X[1] * rx1
+			  - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1]
+			  - (cPAR[5] * s1 + cPAR[6] * s2) * (P(1.0) + cPAR[9] * X[1]) - X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
 			rD = M::rcp_(D);
 		}
-#elif MPGOS_B200_FM_BUNDLE
-		rx1 = M::rcp_(X[0]);
-		rD = M::rcp_(D);
-		// one subroutine for the three transcendental evaluations of the right-hand side (fast_math.cuh; the CUDA-library form makes the
-		// reference's three calls)
-		M::pow_sincospi_sincos_(rx1, cPAR[10], P(2.0) * T, P(2.0) * cPAR[11] * PI * T + cPAR[12], &p, &s1, &c1, &s2, &c2);
-#else
-		rx1 = M::rcp_(X[0]);
-		rD = M::rcp_(D);
-		p = M::pow_(rx1, cPAR[10]);
-		M::sincospi_(P(2.0) * T, &s1, &c1);
-		M::sincos_(P(2.0) * cPAR[11] * PI * T + cPAR[12], &s2, &c2);
-#endif
-		const P N = (cPAR[0] + cPAR[1] * X[1]) * p - cPAR[2] * (P(1.0) + cPAR[9] * X[1]) - cPAR[3] * rx1 - cPAR[4] * X[1] * rx1
-		          - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1]
-		          - (cPAR[5] * s1 + cPAR[6] * s2) * (P(1.0) + cPAR[9] * X[1]) - X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
 		F[0] = X[1];
 		F[1] = N * rD;
 	}

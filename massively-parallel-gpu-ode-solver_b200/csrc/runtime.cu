@@ -986,15 +986,7 @@ __global__ void fast_math_probe_kernel(int function, int n, const double* __rest
 	if (function == 0)      { mpgos_b200::fm::sincos(x[i], &a, &b);    ::sincos(x[i], &c, &d); }
 	else if (function == 1) { mpgos_b200::fm::sincospi(x[i], &a, &b);  ::sincospi(x[i], &c, &d); }
 	else if (function == 2) { a = mpgos_b200::fm::pow(x[i], y[i]);     c = ::pow(x[i], y[i]); }
-	else if (function >= 6)
-	{
-		// the bundle with two reciprocals: 6 = 1/x and 1/y, 7 = its pow(x, y) and its sincos(y) (sine)
-		double p, s1, c1, s2, c2, ru, rv;
-		if (function == 6) mpgos_b200::fm::pow_sincospi_sincos_rcp2(1.5, 4.2, 0.3, 0.4, x[i], y[i], &p, &s1, &c1, &s2, &c2, &ru, &rv);
-		else               mpgos_b200::fm::pow_sincospi_sincos_rcp2(x[i], y[i], 0.3 * y[i], y[i], 3.0, 7.0, &p, &s1, &c1, &s2, &c2, &ru, &rv);
-		if (function == 6) { a = ru;  b = rv;  c = 1.0 / x[i];  d = 1.0 / y[i]; }
-		else               { a = p;   b = s2;  c = ::pow(x[i], y[i]);  d = ::sin(y[i]); }
-	}
+	else if (function == 6) { mpgos_b200::fm::rcp2(x[i], y[i], &a, &b);  c = 1.0 / x[i];  d = 1.0 / y[i]; }
 	else
 	{
 		// the bundled subroutine: 3 = its pow (x^y; trigonometric arguments in range), 4 = its sincospi(x), 5 = its sincos(y)
@@ -1010,7 +1002,7 @@ __global__ void fast_math_probe_kernel(int function, int n, const double* __rest
 
 int mpgos_fast_math_probe(int device, int function, int n, const double* x, const double* y, double* out0, double* out1, double* ref0, double* ref1)
 {
-	if (function < 0 || function > 7 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
+	if (function < 0 || function > 6 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
 	if (n == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(device));
 	double* d = nullptr;

@@ -76,8 +76,7 @@ template <bool FAST> struct Math
 	template <class P> static inline P    rcp_(P x)                  { return P(1.0) / x; }
 	template <class P> static inline void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
 	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
-	template <class P> static inline void pow_sincospi_sincos_rcp2_(P x, P y, P a, P b, P u, P v, P* p, P* s1, P* c1, P* s2, P* c2, P* ru, P* rv)
-	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2);  *ru = P(1.0) / u;  *rv = P(1.0) / v; }
+	template <class P> static inline void rcp2_(P a, P b, P* ra, P* rb) { *ra = P(1.0) / a;  *rb = P(1.0) / b; }
 };
 } }
 namespace mpgos_b200 {
