@@ -5,3 +5,8 @@ for lib in "" build/variants/libmpgos_b200_bundle1.so; do
   MPGOS_B200_LIBRARY=$lib TPBS=128 REFILLS=0 python tools/time_perthread.py kellermiksis_dense_fm:2 2>&1 | tail -1
   MPGOS_B200_LIBRARY=$lib FM=1 python tools/time_coupled.py 2>&1 | tail -1
 done 2>&1 | tee gpurun_out/r2c8_ab.txt
+# four DMMA accumulator chains; two blocks of four systems per SM with four chains
+for lib in build/variants/libmpgos_b200_dmma4.so build/variants/libmpgos_b200_s4dmma4.so; do
+  MPGOS_B200_LIBRARY=$lib FM=1 python tools/time_coupled.py 2>&1 | tail -1
+  MPGOS_B200_LIBRARY=$lib python tools/time_coupled.py 2>&1 | tail -1
+done 2>&1 | tee -a gpurun_out/r2c8_ab.txt
