@@ -246,7 +246,8 @@ int   mpgos_probe_fma_peak(int device, int precision_bytes, double* tflops);
 int   mpgos_probe_dmma_peak(int device, double* tflops);
 /* Test support for include/mpgos_b200/fast_math.cuh: evaluates function 0 (sincos: out0 = sin, out1 = cos), 1 (sincospi) or 2 (pow(x, y):
  * out0) on the device for n host values; ref0 / ref1 receive the CUDA math library's results for the same inputs.  Functions 3, 4, 5:
- * the bundled subroutine pow_sincospi_sincos -- its pow(x, y), its sincospi(x), its sincos(y); 6: rcp2 -- 1/x and 1/y. */
+ * the bundled subroutine pow_sincospi_sincos -- its pow(x, y), its sincospi(x), its sincos(y); 6: rcp2 -- 1/x and 1/y; 7: out = the CUDA
+ * library's sin(x), cos(x), ref = its sincos(x). */
 int   mpgos_fast_math_probe(int device, int function, int n, const double* x, const double* y, double* out0, double* out1, double* ref0, double* ref1);
 
 #ifdef __cplusplus

@@ -384,6 +384,12 @@ __device__ __forceinline__ float cos(float x)                          { return 
 __device__ __forceinline__ void  sincospi(float x, float* s, float* c) { ::sincospif(x, s, c); }
 __device__ __forceinline__ float pow(float x, float y)                 { return ::powf(x, y); }
 
+#ifndef MPGOS_B200_STD_SINCOS
+#define MPGOS_B200_STD_SINCOS 0      // A/B: the CUDA-library forms take sin and cos of one argument from one ::sincos call
+#endif
+__device__ __forceinline__ void cuda_sincos_inline(double x, double* s, double* c) { ::sincos(x, s, c); }
+__device__ __forceinline__ void cuda_sincos_inline(float x, float* s, float* c)    { ::sincosf(x, s, c); }
+
 // compile-time choice between these functions and CUDA's, for code that exists in both forms (the built-in systems)
 template <bool FAST> struct Math
 {
@@ -403,7 +409,11 @@ template <> struct Math<false>
 	template <class P> static __device__ __forceinline__ P    sin_(P x)                    { return ::sin(x); }
 	template <class P> static __device__ __forceinline__ P    cos_(P x)                    { return ::cos(x); }
 	template <class P> static __device__ __forceinline__ void sincospi_(P x, P* s, P* c)   { ::sincospi(x, s, c); }
+#if MPGOS_B200_STD_SINCOS
+	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { mpgos_b200::fm::cuda_sincos_inline(x, s, c); }
+#else
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { *s = ::sin(x);  *c = ::cos(x); }         // the reference's two calls
+#endif
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return P(1.0) / x; }
 	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
 	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }

@@ -987,6 +987,7 @@ __global__ void fast_math_probe_kernel(int function, int n, const double* __rest
 	else if (function == 1) { mpgos_b200::fm::sincospi(x[i], &a, &b);  ::sincospi(x[i], &c, &d); }
 	else if (function == 2) { a = mpgos_b200::fm::pow(x[i], y[i]);     c = ::pow(x[i], y[i]); }
 	else if (function == 6) { mpgos_b200::fm::rcp2(x[i], y[i], &a, &b);  c = 1.0 / x[i];  d = 1.0 / y[i]; }
+	else if (function == 7) { a = ::sin(x[i]);  b = ::cos(x[i]);  ::sincos(x[i], &c, &d); }      // the CUDA library against itself: sin, cos | sincos
 	else
 	{
 		// the bundled subroutine: 3 = its pow (x^y; trigonometric arguments in range), 4 = its sincospi(x), 5 = its sincos(y)
@@ -1002,7 +1003,7 @@ __global__ void fast_math_probe_kernel(int function, int n, const double* __rest
 
 int mpgos_fast_math_probe(int device, int function, int n, const double* x, const double* y, double* out0, double* out1, double* ref0, double* ref1)
 {
-	if (function < 0 || function > 6 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
+	if (function < 0 || function > 7 || n < 0 || !x || !y || !out0 || !out1 || !ref0 || !ref1) return fail(MPGOS_ERR_ARGUMENT, "fast_math_probe: bad argument");
 	if (n == 0) return MPGOS_OK;
 	CUDA_TRY(cudaSetDevice(device));
 	double* d = nullptr;

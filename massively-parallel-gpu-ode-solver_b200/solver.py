@@ -172,7 +172,7 @@ def probe_fma_peak(device: int = 0, precision_bytes: int = 8) -> float:
 
 def fast_math_probe(function: int, x, y=None, device: int = 0):
     """(fast0, fast1, cuda0, cuda1): include/mpgos_b200/fast_math.cuh against the CUDA math library on the device; function 0 sincos,
-    1 sincospi, 2 pow(x, y); the bundled subroutine pow_sincospi_sincos: 3 its pow(x, y), 4 its sincospi(x), 5 its sincos(y); 6 rcp2: 1/x and 1/y."""
+    1 sincospi, 2 pow(x, y); the bundled subroutine pow_sincospi_sincos: 3 its pow(x, y), 4 its sincospi(x), 5 its sincos(y); 6 rcp2: 1/x and 1/y; 7: CUDA's sin(x), cos(x) against CUDA's sincos(x)."""
     lib = load_library()
     x = np.ascontiguousarray(x, np.float64)
     y = np.zeros_like(x) if y is None else np.ascontiguousarray(y, np.float64)
