@@ -384,11 +384,16 @@ __device__ __forceinline__ float cos(float x)                          { return 
 __device__ __forceinline__ void  sincospi(float x, float* s, float* c) { ::sincospif(x, s, c); }
 __device__ __forceinline__ float pow(float x, float y)                 { return ::powf(x, y); }
 
+// The CUDA-library forms of the built-in systems take sin and cos of one argument from ONE ::sincos call: the CUDA library's sincos
+// returns exactly the bits of its sin and its cos (14 million random arguments up to 1e300 and the special values, on the device:
+// tests/test_fast_math_gpu.py::test_cuda_sincos_is_cuda_sin_and_cos pins it), so the results are those of the reference's two calls
+// at one range reduction instead of two: Keller-Miksis 36.9 -> 32.8 ms, coupled bubbles 18.9 -> 17.1 ms, same checksums
+// (profiles/r2_variant_ab_runs.txt).  MPGOS_B200_STD_SINCOS 0 restores the two calls.
 #ifndef MPGOS_B200_STD_SINCOS
-#define MPGOS_B200_STD_SINCOS 0      // A/B: the CUDA-library forms take sin and cos of one argument from one ::sincos call
+#define MPGOS_B200_STD_SINCOS 1
 #endif
 __device__ __forceinline__ void cuda_sincos_inline(double x, double* s, double* c) { ::sincos(x, s, c); }
-__device__ __forceinline__ void cuda_sincos_inline(float x, float* s, float* c)    { ::sincosf(x, s, c); }
+__device__ __forceinline__ void cuda_sincos_inline(float x, float* s, float* c)    { *s = ::sinf(x);  *c = ::cosf(x); }      // single precision: unchanged (not checked)
 
 // compile-time choice between these functions and CUDA's, for code that exists in both forms (the built-in systems)
 template <bool FAST> struct Math

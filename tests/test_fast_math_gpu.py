@@ -98,6 +98,19 @@ def test_two_reciprocals_side_by_side(pkg):
     assert np.array_equal(ru, du, equal_nan=True) and np.array_equal(rv, dv, equal_nan=True)
 
 
+def test_cuda_sincos_is_cuda_sin_and_cos(pkg):
+    """The CUDA-library forms of the built-in systems call ::sincos(x) where the reference's definitions call sin(x) and cos(x): on
+    the device the three functions must agree bit for bit (they share one reduction and one pair of kernels)."""
+    rng = np.random.default_rng(5)
+    for scale in (1.0, 10.0, 1e3, 1e5, 1e8, 1e15, 1e300):
+        x = rng.uniform(-scale, scale, 400_000)
+        s, c, s2, c2 = pkg.fast_math_probe(7, x)
+        assert np.array_equal(s, s2) and np.array_equal(c, c2), scale
+    x = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 1e-310, np.pi, np.pi / 2, 105414357.0, 1e22])
+    s, c, s2, c2 = pkg.fast_math_probe(7, x)
+    assert np.array_equal(s, s2, equal_nan=True) and np.array_equal(c, c2, equal_nan=True) and np.array_equal(np.signbit(s), np.signbit(s2))
+
+
 def test_special_cases_are_the_cuda_functions(pkg):
     x = np.array([0.0, -0.0, -2.0, -8.0, np.inf, np.nan, 1.0, 2.0, 5e-324, 1e-310, 1e300, 1e-300, 3.0, 0.5, np.inf, 2.0, 2.0])
     y = np.array([2.0, -1.0, 2.0, 1.0 / 3.0, 0.5, 1.0, np.nan, np.inf, 2.0, 0.5, 2.0, 2.0, 0.0, -np.inf, -1.0, 1e6, -1e6])
