@@ -91,6 +91,10 @@ def test_c4_kellermiksis_dense_full_launch_strided_sample_against_checker(pkg, w
     assert same_di.mean() >= 0.98
     n = int(ref.DenseIndex.min())
     cols = np.where(same_di)[0]
+    dte = rel_err(out.DenseTime[:n][:, idx[cols]], ref.DenseTime[:n][:, cols])
+    dse = rel_err(out.DenseState[:n][:, :, idx[cols]], ref.DenseState[:n][:, :, cols])
+    report("C4 dense output", points=n, time_err=f"{dte.max():.2e}", time_err_median_over_instances=f"{np.median(dte.max(axis=0)):.2e}", state_err=f"{dse.max():.2e}",
+           worst_instance=int(idx[cols][dte.max(axis=0).argmax()]))
     assert rel_err(out.DenseTime[:n][:, idx[cols]], ref.DenseTime[:n][:, cols]).max() < 1e-9
     assert rel_err(out.DenseState[:n][:, :, idx[cols]], ref.DenseState[:n][:, :, cols]).max() < 1e-8
 

@@ -116,6 +116,7 @@ def test_rkck45_endpoints_and_step_counts(name, refill, cases, pkg, oracle):
         assert same.mean() >= same_frac
         n = int(ref.DenseIndex.min())
         cols = np.where(same)[0]
+        print(f"[parity {name} refill={refill}] dense time {rel_err(out.DenseTime[:n][:, cols], ref.DenseTime[:n][:, cols]).max():.2e}  dense state {rel_err(out.DenseState[:n][:, :, cols], ref.DenseState[:n][:, :, cols]).max():.2e}")
         assert rel_err(out.DenseTime[:n][:, cols], ref.DenseTime[:n][:, cols]).max() < tol * 10
         assert rel_err(out.DenseState[:n][:, :, cols], ref.DenseState[:n][:, :, cols]).max() < tol * 100
 
