@@ -31,9 +31,17 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #ifdef MPGOS_B200_FAST_MATH
-// everything the interface headers include, before the names below become macros
+// everything the interface headers and the tutorials' programs include that mentions these names (std::pow inside <random>, ...),
+// before the names below become macros
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <complex>
+#include <ctime>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <valarray>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -428,13 +436,40 @@ template <> struct Math<false>
 } // namespace fm
 } // namespace mpgos_b200
 
-// Redirection for an unmodified system definition (see the header comment).  Function-like macros: only calls are rewritten.
+// Redirection for an unmodified system definition (see the header comment).  Function-like macros: only calls are rewritten.  The
+// targets are host + device: in device code the functions above, in host code the C library (a tutorial's main() computes its
+// parameters with pow and is part of the same translation unit).
+namespace mpgos_b200 {
+namespace fm {
+namespace redirect {
+#ifdef __CUDA_ARCH__
+#define MPGOS_FM_PICK(fast, standard) fast
+#else
+#define MPGOS_FM_PICK(fast, standard) standard
+#endif
+// argument types as in C: float stays float, everything else (double, integers) is double
+template <class A> struct Real { using type = double; };
+template <> struct Real<float> { using type = float; };
+template <class A, class B> struct Real2 { using type = double; };
+template <> struct Real2<float, float> { using type = float; };
+template <class A, class B> __host__ __device__ __forceinline__ typename Real2<A, B>::type pow(A x, B y)
+{
+	using R = typename Real2<A, B>::type;
+	return MPGOS_FM_PICK(mpgos_b200::fm::pow((R)x, (R)y), ::pow((R)x, (R)y));
+}
+template <class A> __host__ __device__ __forceinline__ typename Real<A>::type sin(A x) { using R = typename Real<A>::type;  return MPGOS_FM_PICK(mpgos_b200::fm::sin((R)x), ::sin((R)x)); }
+template <class A> __host__ __device__ __forceinline__ typename Real<A>::type cos(A x) { using R = typename Real<A>::type;  return MPGOS_FM_PICK(mpgos_b200::fm::cos((R)x), ::cos((R)x)); }
+template <class A, class P> __host__ __device__ __forceinline__ void sincos(A x, P* s, P* c)   { MPGOS_FM_PICK(mpgos_b200::fm::sincos((P)x, s, c), ::sincos((P)x, s, c)); }
+template <class A, class P> __host__ __device__ __forceinline__ void sincospi(A x, P* s, P* c) { MPGOS_FM_PICK(mpgos_b200::fm::sincospi((P)x, s, c), ::sincospi((P)x, s, c)); }
+} // namespace redirect
+} // namespace fm
+} // namespace mpgos_b200
 #ifdef MPGOS_B200_FAST_MATH
-#define pow(x, y)         mpgos_b200::fm::pow(x, y)
-#define sin(x)            mpgos_b200::fm::sin(x)
-#define cos(x)            mpgos_b200::fm::cos(x)
-#define sincos(x, s, c)   mpgos_b200::fm::sincos(x, s, c)
-#define sincospi(x, s, c) mpgos_b200::fm::sincospi(x, s, c)
+#define pow(x, y)         mpgos_b200::fm::redirect::pow(x, y)
+#define sin(x)            mpgos_b200::fm::redirect::sin(x)
+#define cos(x)            mpgos_b200::fm::redirect::cos(x)
+#define sincos(x, s, c)   mpgos_b200::fm::redirect::sincos(x, s, c)
+#define sincospi(x, s, c) mpgos_b200::fm::redirect::sincospi(x, s, c)
 #endif
 
 #endif

@@ -23,10 +23,13 @@ def _tutorials():
     return out
 
 
-def _compile(item):
+FAST_MATH = ["-DMPGOS_B200_FAST_MATH", "-include", "mpgos_b200/fast_math.cuh"]
+
+
+def _compile(item, extra=()):
     name, src = item
     with tempfile.TemporaryDirectory() as tmp:
-        cmd = ["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", os.path.join(ROOT, "include"),
+        cmd = ["nvcc", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", "-I", os.path.join(ROOT, "include"), *extra,
                "-I", os.path.dirname(src), "-c", src, "-o", os.path.join(tmp, "t.o")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return name, r.returncode, r.stderr[-1500:]
@@ -39,6 +42,19 @@ def test_every_reference_tutorial_compiles_unmodified_against_the_dropin_headers
     assert len(items) >= 10          # T1..T8 per-thread, T1..T2 coupled
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
         results = list(pool.map(_compile, items))
+    failed = [(n, err) for n, rc, err in results if rc != 0]
+    assert not failed, failed
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "SourceCodes")) or shutil.which("nvcc") is None,
+                    reason="needs /root/reference and nvcc (development container)")
+def test_every_reference_tutorial_compiles_unmodified_with_the_fast_math_redirect():
+    """The opt-in transcendentals for UNMODIFIED programs: -DMPGOS_B200_FAST_MATH -include mpgos_b200/fast_math.cuh turns the calls of
+    pow / sin / cos / sincos / sincospi into the fast functions in device code and leaves host code (the tutorials' main() programs
+    compute parameters with pow, the bubble tutorial includes <random>) on the C library."""
+    items = _tutorials()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+        results = list(pool.map(lambda it: _compile(it, FAST_MATH), items))
     failed = [(n, err) for n, rc, err in results if rc != 0]
     assert not failed, failed
 

@@ -229,12 +229,15 @@ def test_t3_poincare_section_tutorial_against_the_checker(workloads, oracle):
     check_scan_against_checker("T3", duffing_scan(os.path.join(tmp, "DuffingPoincare.txt"), columns=3), workloads, oracle, events=False, first_state_column=1)
 
 
-def test_t5_keller_miksis_tutorial_against_the_checker(workloads, oracle):
+@pytest.mark.parametrize("program", ["T5_LargeTimeScaleDifferences", "T5_LargeTimeScaleDifferences_fm"])
+def test_t5_keller_miksis_tutorial_against_the_checker(program, workloads, oracle):
     """T5: 46 080 bubbles, 1024 transient + 64 recorded periods; KellerMiksis.txt holds id, frequency, the state after the transient
     and the largest radius of the 64 periods (KellerMiksis.cu:63-106).  The checker on a strided subset: periodic bubbles agree to
-    1e-6; a few sit in chaotic windows of the frequency sweep."""
+    1e-6; a few sit in chaotic windows of the frequency sweep.  "_fm": the same unmodified program compiled with
+    -DMPGOS_B200_FAST_MATH -include mpgos_b200/fast_math.cuh (oracle/Makefile): the opt-in transcendentals through the redirect."""
     from cases import subsample
-    tmp, out = run_tutorial("T5_LargeTimeScaleDifferences", timeout=900)
+    tmp, out = run_tutorial(program, timeout=900)
+    print(f"[tutorial {program}] " + " ".join(l.strip() for l in out.splitlines() if "simulation time" in l))
     rows = load_rows(os.path.join(tmp, "KellerMiksis.txt"))
     NT = 46080
     assert rows.shape == (NT, 5) and np.isfinite(rows).all() and np.array_equal(rows[:, 0], np.arange(NT))
@@ -249,7 +252,7 @@ def test_t5_keller_miksis_tutorial_against_the_checker(workloads, oracle):
         b, _, _ = oracle.run_oracle(sub, buffers=b, phases=1, host_threads=8)
         top = np.maximum(top, b.Accessories[0])
     err = np.maximum(rel_err(rows[idx, 2:4], state).max(axis=1), rel_err(rows[idx, 4], top))
-    print(f"[tutorial T5] bubbles agreeing with the checker to 1e-6: {(err < 1e-6).mean():.3f}  median error {np.median(err):.2e}")
+    print(f"[tutorial {program}] bubbles agreeing with the checker to 1e-6: {(err < 1e-6).mean():.3f}  median error {np.median(err):.2e}")
     assert (err < 1e-6).mean() >= 0.80
     assert (rows[:, 4] >= rows[:, 2] - 1e-9).all() and rows[:, 4].max() < 1.5 * top.max() + 1.0
 
@@ -270,8 +273,10 @@ def test_t4_quasiperiodic_forcing_tutorial_runs_to_completion():
 def test_t2_lorenz_and_tc2_bubble_ensemble_tutorials_run_to_completion():
     tmp, out = run_tutorial("T2_Lorenz")
     assert "Simulation time" in out or "Total" in out
-    tmp, out = run_tutorial("TC2_BubbleEnsemble", timeout=900)
-    files = [f for f in os.listdir(tmp) if f.endswith(".txt")]
-    assert files, out[-500:]
-    big = max(files, key=lambda f: os.path.getsize(os.path.join(tmp, f)))
-    assert os.path.getsize(os.path.join(tmp, big)) > 1000
+    for program in ("TC2_BubbleEnsemble", "TC2_BubbleEnsemble_fm"):          # "_fm": with the fast-math redirect (oracle/Makefile)
+        tmp, out = run_tutorial(program, timeout=900)
+        files = [f for f in os.listdir(tmp) if f.endswith(".txt")]
+        assert files, out[-500:]
+        big = max(files, key=lambda f: os.path.getsize(os.path.join(tmp, f)))
+        assert os.path.getsize(os.path.join(tmp, big)) > 1000
+        print(f"[tutorial {program}] " + " ".join(l.strip() for l in out.splitlines() if "time" in l.lower())[:300])
