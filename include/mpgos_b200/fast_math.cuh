@@ -143,7 +143,9 @@ __device__ __forceinline__ SinCos kernel_sincos(double r, int q)
 	return out;
 }
 
-MPGOS_FM_FN SinCos sincos_core(double x)
+// (const: no side effects, the result depends on the argument alone -- sin(x) and cos(x) of one argument in an unmodified definition
+// then share one call)
+MPGOS_FM_FN __attribute__((const)) SinCos sincos_core(double x)
 {
 	double two_over_pi, p1, p2, p3;
 	ldpair(FM_2OPI_PIO2A, two_over_pi, p1);
@@ -161,7 +163,7 @@ __device__ __forceinline__ void sincos(double x, double* sn, double* cs) { const
 __device__ __forceinline__ double sin(double x) { double s, c; mpgos_b200::fm::sincos(x, &s, &c); return s; }
 __device__ __forceinline__ double cos(double x) { double s, c; mpgos_b200::fm::sincos(x, &s, &c); return c; }
 
-MPGOS_FM_FN SinCos sincospi_core(double x)
+MPGOS_FM_FN __attribute__((const)) SinCos sincospi_core(double x)
 {
 	double pi_hi, pi_lo;
 	ldpair(FM_PIHI_PILO, pi_hi, pi_lo);
@@ -177,7 +179,7 @@ __device__ __forceinline__ void sincospi(double x, double* sn, double* cs) { con
 // x^y for normal positive finite x and moderate |y log2 x|; everything else (including every special case of the C standard) is
 // the CUDA function's.  Straight-line: the fast path is computed unconditionally (on operands outside its range it produces
 // garbage, never a fault) and replaced at the end.
-MPGOS_FM_FN double pow(double x, double y)
+MPGOS_FM_FN __attribute__((const)) double pow(double x, double y)
 {
 	const int hx = __double2hiint(x);
 	// x = 2^e m, m in [sqrt(1/2), sqrt(2))
@@ -252,7 +254,7 @@ static __device__ __noinline__ PowSinCos2 cuda_pow_sincospi_sincos(double x, dou
 	return o;
 }                                                                                                               // <cold]
 
-MPGOS_FM_FN PowSinCos2 pow_sincospi_sincos(double x, double y, double a, double b)
+MPGOS_FM_FN __attribute__((const)) PowSinCos2 pow_sincospi_sincos(double x, double y, double a, double b)
 {
 	PowSinCos2 o;
 	// --- reductions of the two trigonometric arguments
