@@ -24,6 +24,8 @@
 //     #include "mpgos_b200/fast_math.cuh"
 //     #include "KellerMiksis_SystemDefinition.cuh"
 //     #include "SingleSystem_PerThread_Interface.cuh"
+// or, for a whole program as it is:  nvcc -DMPGOS_B200_FAST_MATH -include mpgos_b200/fast_math.cuh Program.cu ...  The redirect applies to
+// device code only: host code of the same translation unit (a tutorial's main() computes its parameters with pow) keeps the C library.
 // Single-precision calls are passed on to the CUDA functions unchanged.
 #ifndef MPGOS_B200_FAST_MATH_CUH
 #define MPGOS_B200_FAST_MATH_CUH
