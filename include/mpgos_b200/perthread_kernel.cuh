@@ -1038,7 +1038,7 @@ struct PerThreadLauncher
 		// 128, Lorenz / impact unchanged: profiles/r2_variant_ab_runs.txt).  Per-instance arithmetic does not depend on the block shape.
 		{
 			const int sms = L->MultiProcessorCount > 0 ? L->MultiProcessorCount : 148;
-			if (block < 128 && active >= 128 * 16 * sms) block = 128;
+			if (block < 128 && active >= 128 * 8 * sms) block = 128;      // at least two waves of 128-thread blocks at 4 resident blocks per SM
 		}
 		int grid = (active + block - 1) / block;
 		if (REFILL)
