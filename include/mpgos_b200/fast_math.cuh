@@ -404,9 +404,7 @@ __device__ __forceinline__ float pow(float x, float y)                 { return 
 #ifndef MPGOS_B200_STD_SINCOS
 #define MPGOS_B200_STD_SINCOS 1
 #endif
-#ifndef MPGOS_B200_STD_BUNDLE
-#define MPGOS_B200_STD_BUNDLE 0
-#endif
+
 __device__ __forceinline__ void cuda_sincos_inline(double x, double* s, double* c) { ::sincos(x, s, c); }
 __device__ __forceinline__ void cuda_sincos_inline(float x, float* s, float* c)    { *s = ::sinf(x);  *c = ::cosf(x); }      // single precision: unchanged (not checked)
 
@@ -435,16 +433,8 @@ template <> struct Math<false>
 	template <class P> static __device__ __forceinline__ void sincos_(P x, P* s, P* c)     { *s = ::sin(x);  *c = ::cos(x); }         // the reference's two calls
 #endif
 	template <class P> static __device__ __forceinline__ P    rcp_(P x)                    { return P(1.0) / x; }
-#if MPGOS_B200_STD_BUNDLE
-	// A/B: the three CUDA-library evaluations as one subroutine (the same functions, the same bits)
-	static __device__ __forceinline__ void pow_sincospi_sincos_(double x, double y, double a, double b, double* p, double* s1, double* c1, double* s2, double* c2)
-	{ const PowSinCos2 o = cuda_pow_sincospi_sincos(x, y, a, b);  *p = o.p;  *s1 = o.s1;  *c1 = o.c1;  *s2 = o.s2;  *c2 = o.c2; }
-	static __device__ __forceinline__ void pow_sincospi_sincos_(float x, float y, float a, float b, float* p, float* s1, float* c1, float* s2, float* c2)
-	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
-#else
 	template <class P> static __device__ __forceinline__ void pow_sincospi_sincos_(P x, P y, P a, P b, P* p, P* s1, P* c1, P* s2, P* c2)
 	{ *p = pow_(x, y);  sincospi_(a, s1, c1);  sincos_(b, s2, c2); }
-#endif
 	template <class P> static __device__ __forceinline__ void rcp2_(P a, P b, P* ra, P* rb)      { *ra = P(1.0) / a;  *rb = P(1.0) / b; }
 };
 

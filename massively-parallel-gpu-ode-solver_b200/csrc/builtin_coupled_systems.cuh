@@ -53,13 +53,9 @@ struct BubbleEnsembleT
 #endif
 		{
 			rx1 = M::rcp_(X[0]);
-#if MPGOS_B200_STD_BUNDLE
-			M::pow_sincospi_sincos_(rx1, uPAR[10], P(2.0) * T, P(2.0) * uPAR[11] * PI * T + uPAR[12], &p, &s1, &c1, &s2, &c2);
-#else
 			p = M::pow_(rx1, uPAR[10]);
 			M::sincospi_(P(2.0) * T, &s1, &c1);
 			M::sincos_(P(2.0) * uPAR[11] * PI * T + uPAR[12], &s2, &c2);
-#endif
 			N = (uPAR[0] + uPAR[1] * X[1]) * p - uPAR[2] * (P(1.0) + uPAR[9] * X[1]) - uPAR[3] * rx1 - uPAR[4] * X[1] * rx1
 			  - P(1.5) * (P(1.0) - uPAR[9] * X[1] / P(3.0)) * X[1] * X[1]
 			  - (uPAR[5] * s1 + uPAR[6] * s2) * (P(1.0) + uPAR[9] * X[1]) - X[0] * (uPAR[7] * c1 + uPAR[8] * c2);

@@ -185,13 +185,9 @@ struct KellerMiksisT : Empty<P>
 #endif
 		{
 			rx1 = M::rcp_(X[0]);
-#if MPGOS_B200_STD_BUNDLE
-			M::pow_sincospi_sincos_(rx1, cPAR[10], P(2.0) * T, P(2.0) * cPAR[11] * PI * T + cPAR[12], &p, &s1, &c1, &s2, &c2);
-#else
 			p = M::pow_(rx1, cPAR[10]);
 			M::sincospi_(P(2.0) * T, &s1, &c1);
 			M::sincos_(P(2.0) * cPAR[11] * PI * T + cPAR[12], &s2, &c2);
-#endif
 			N = (cPAR[0] + cPAR[1] * X[1]) * p - cPAR[2] * (P(1.0) + cPAR[9] * X[1]) - cPAR[3] * rx1 - cPAR[4] * X[1] * rx1
 			  - P(1.5) * (P(1.0) - cPAR[9] * X[1] * (P(1.0) / P(3.0))) * X[1] * X[1]
 			  - (cPAR[5] * s1 + cPAR[6] * s2) * (P(1.0) + cPAR[9] * X[1]) - X[0] * (cPAR[7] * c1 + cPAR[8] * c2);
