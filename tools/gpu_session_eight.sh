@@ -1,4 +1,4 @@
-# round 2, 8-GPU session: one solver object over 1 / 2 / 4 / 8 devices, and the driver's launch line at N = 8 (headline + C5 + strong scaling)
+# eight-GPU session (gpurun --gpus 8 -- 'bash tools/gpu_session_eight.sh'): one solver object over 1 / 2 / 4 / 8 devices, and the driver's launch line at N = 8 (headline + C5 + strong scaling)
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 python tools/probe_sharded_scaling.py 2>&1 | tail -8 | tee gpurun_out/r2s8_sharded_object.txt

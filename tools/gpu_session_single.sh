@@ -1,6 +1,8 @@
-# round 2, final single-GPU session: the whole GPU suite, the bench line of both arms, the ncu launch list of the bench command, one
-# --set full capture per configuration's kernel, compute-sanitizer over the round-2 cases
+# single-GPU session at the end of a round (gpurun -- 'bash tools/gpu_session_single.sh'): smoke(), the whole GPU suite, the bench line of both
+# arms, the ncu launch list of the bench command, one --set full capture per configuration's kernel, compute-sanitizer over the round-2 cases.
+# Outputs under gpurun_out/ (r2f_*); the summaries committed under profiles/ come from them.
 mkdir -p gpurun_out
+( time python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" ) 2>&1 | tail -6
 ( time python -m pytest tests -m gpu -x -q -s ) > gpurun_out/r2f_pytest.txt 2>&1; tail -5 gpurun_out/r2f_pytest.txt
 ( time python bench.py --impl reference --steps 3 --warmup 1 ) > gpurun_out/r2f_bench_reference_n1.json 2> gpurun_out/r2f_bench_reference.err; tail -c 600 gpurun_out/r2f_bench_reference_n1.json
 ( time python bench.py --steps 10 --warmup 3 ) > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench.err; tail -3 gpurun_out/r2f_bench.err

@@ -1,4 +1,4 @@
-# round 2, final 2-GPU session: the tests that need two devices, the tutorial programs, and the driver's launch line at N = 2
+# two-GPU session (gpurun --gpus 2 -- 'bash tools/gpu_session_two.sh'): the tests that need two devices, the tutorial programs, and the driver's launch line at N = 2
 mkdir -p gpurun_out
 nvidia-smi -L
 ( time python -m pytest tests/test_sharded_solver.py tests/test_tutorials_run_gpu.py tests/test_orchestration_gpu.py tests/test_coupled_gpu.py -m gpu -q -s ) > gpurun_out/r2f2_pytest.txt 2>&1; tail -8 gpurun_out/r2f2_pytest.txt; grep "tutorial" gpurun_out/r2f2_pytest.txt | head
