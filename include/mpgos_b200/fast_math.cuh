@@ -26,6 +26,8 @@
 //     #include "SingleSystem_PerThread_Interface.cuh"
 // or, for a whole program as it is:  nvcc -DMPGOS_B200_FAST_MATH -include mpgos_b200/fast_math.cuh Program.cu ...  The redirect applies to
 // device code only: host code of the same translation unit (a tutorial's main() computes its parameters with pow) keeps the C library.
+// The redirect is a set of function-like macros (pow, sin, cos, sincos, sincospi): library headers that use these names themselves
+// (the C++ standard headers below are taken care of; thrust, cub, ... are not) must be included BEFORE this header.
 // Single-precision calls are passed on to the CUDA functions unchanged.
 #ifndef MPGOS_B200_FAST_MATH_CUH
 #define MPGOS_B200_FAST_MATH_CUH
