@@ -277,16 +277,26 @@ __device__ __forceinline__ void mma_coupling_product_f32(const float4* __restric
 template <class P, int UPS, int SLOTS> struct MmaGeometryFor { using type = MmaGeometry<UPS, SLOTS>; };
 template <int UPS, int SLOTS> struct MmaGeometryFor<float, UPS, SLOTS> { using type = MmaGeometryF32<UPS, SLOTS>; };
 
+// threads of a slot when every thread integrates UPT units (UPT > 1: systems of more than 1024 units; the reference's "multiple block
+// launches", Solver.cuh:1508, 2215): thread t of the slot owns units t, t + TPS, t + 2 TPS, ...
+__host__ __device__ constexpr int slot_threads(int UPS, int UPT) { return (((UPS + UPT - 1) / UPT + 31) / 32) * 32; }
+
 template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP, int NSP, int NGP, int NiGP, int NUA, int NiUA, int NSA, int NiSA,
-          int NE, bool DENSE, int ALG, int SPBK, bool MMA>
-__global__ void __launch_bounds__(SPBK * (((UPS + 31) / 32) * 32), coupled_min_blocks(SPBK * (((UPS + 31) / 32) * 32)))
+          int NE, bool DENSE, int ALG, int SPBK, bool MMA, int UPT = 1>
+__global__ void __launch_bounds__(SPBK * slot_threads(UPS, UPT), coupled_min_blocks(SPBK * slot_threads(UPS, UPT)))
 perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 {
-	constexpr int UPSP = ((UPS + 31) / 32) * 32;
-	constexpr int WPS = UPSP / 32;
+	constexpr int UPSP = ((UPS + 31) / 32) * 32;      // units of a system, padded to whole warps (shared arrays)
+	constexpr int TPS = slot_threads(UPS, UPT);       // threads of a slot (UPT == 1: UPSP)
+	constexpr int WPS = TPS / 32;
+	static_assert(UPT >= 1 && (UPT == 1 || !MMA), "several units per thread: scalar coupling only");
 	constexpr int MSIZE = packed_matrix_elements(UPS, NC, CBW, CCI);
 	constexpr int MSTRIDE = MSIZE / (NC > 0 ? NC : 1);
-	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA, MMA>;
+	// coupling terms of the slot's units: inside the slot's static shared struct, or (several units per thread: up to 4096 units) in
+	// dynamic shared memory behind the global parameters
+	constexpr bool BIG = UPT > 1;
+	using Slot = SlotShared<P, UPS, UPSP, NC, NSP, NSA, NiSA, MMA || BIG>;
+	static_assert(sizeof(Slot) * SPBK <= 47 * 1024, "the coupling terms of the block's systems do not fit into static shared memory");
 	using G = typename MmaGeometryFor<P, MMA ? UPS : 32, MMA ? SPBK : 8>::type;
 	constexpr int MCOPIES   = MMA ? G::MCOPIES : 1;                        // FP32: big and small TF32 parts of the matrix
 	constexpr int CPT_ELEMS = MMA ? NC * G::NCOL * G::CS : 0;              // coupling terms of the systems of the block (MMA variant)
@@ -300,6 +310,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	P*   s_vpart  = s_cptm + CPT_ALL;                                   // [V_ELEMS]
 	P*   s_gpar   = s_vpart + V_ELEMS;                                  // [NGP]
 	int* s_igpar  = reinterpret_cast<int*>(s_gpar + NGP);               // [NiGP]
+	P*   s_cptbig = reinterpret_cast<P*>((reinterpret_cast<size_t>(s_igpar + NiGP) + 15) & ~(size_t)15);      // [SPBK][2][NC][UPSP] when BIG (16-byte aligned)
 	__shared__ Slot s_slots[SPBK];
 	__shared__ int  s_cidx[AtLeastOne<NC>::value];
 
@@ -340,9 +351,12 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	for (int i = threadIdx.x; i < NC; i += blockDim.x)    s_cidx[i] = a.CouplingIndex[i];
 	__syncthreads();
 
-	const int  slot = threadIdx.x / UPSP;
-	const int  unit = threadIdx.x % UPSP;
+	const int  slot = threadIdx.x / TPS;
+	const int  unit = threadIdx.x % TPS;     // the thread's first unit (its only one when UPT == 1); unit 0's thread does the system-scope work
 	const bool is_unit = unit < UPS;         // padding lanes only take part in barriers
+	// u-th unit of this thread, and whether it exists
+	auto unit_of = [&](int u) { return unit + u * TPS; };
+	auto is_unit_of = [&](int u) { return unit + u * TPS < UPS; };
 	const int  wis  = unit / 32;             // warp within the slot
 	const int  lane = unit & 31;
 	const int  warp = threadIdx.x / 32;
@@ -350,13 +364,13 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 	const size_t NU = (size_t)a.NS * UPS;    // unit-scope stride
 
 	// unit-scope data of the slot's current system: registers
-	P   x[UD], upar[AtLeastOne<NUP>::value], uacc[AtLeastOne<NUA>::value], ev[AtLeastOne<NE>::value];
-	int iuacc[AtLeastOne<NiUA>::value];
+	P   x[UPT][UD], upar[UPT][AtLeastOne<NUP>::value], uacc[UPT][AtLeastOne<NUA>::value], ev[UPT][AtLeastOne<NE>::value];
+	int iuacc[UPT][AtLeastOne<NiUA>::value];
 	P   dt_new = a.InitialTimeStep;
 	unsigned attempted = 0, accepted = 0;
 	int    pos = blockIdx.x * SPBK + slot;      // position in the system queue
 	int    sys = 0, gsys = 0;
-	size_t ug = 0;
+	auto ug_of = [&](int u) { return (size_t)sys * UPS + (is_unit_of(u) ? unit_of(u) : 0); };      // unit-scope index of the thread's u-th unit
 	bool   have = false, dry = false, first = true, resumed = false;
 	int    buf = 0;
 
@@ -371,7 +385,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			if (!first)
 			{
 				if (unit == 0) S.next_system = (int)(gridDim.x * SPBK + atomicAdd(a.WorkQueue, 1u));
-				slot_barrier<UPSP>(slot);
+				slot_barrier<TPS>(slot);
 				pos = S.next_system;
 			}
 			first = false;
@@ -384,7 +398,6 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			if (!dry && !(resumed && a.SlicePaused[sys] == 0))      // continuation: a system that ended inside the pilot is skipped
 			{
 				gsys = (a.ShardCount > 1 ? ((sys / a.ShardTile) * a.ShardCount + a.ShardIndex) * a.ShardTile + sys % a.ShardTile : sys) + a.SystemOffset;
-				ug   = (size_t)sys * UPS + (is_unit ? unit : 0);
 				// ---- load: system scope -> shared, unit scope -> registers (Solver.cuh:2279-2435) ---------------
 				if (unit == 0)
 				{
@@ -398,63 +411,78 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				if (unit < NiSA) S.isacc[unit]    = a.IntegerSystemAccessories[sys + unit * a.NS];
 				if (unit < NC)   S.strength[unit] = (resumed ? a.SliceCouplingStrength : a.CouplingStrength)[sys + unit * a.NS];
 				#pragma unroll
-				for (int i = 0; i < UD; i++)   x[i]     = a.ActualState[ug + i * NU];
-				#pragma unroll
-				for (int i = 0; i < NUP; i++)  upar[i]  = (resumed ? a.SliceUnitParameters : a.UnitParameters)[ug + i * NU];
-				#pragma unroll
-				for (int i = 0; i < NUA; i++)  uacc[i]  = a.UnitAccessories[ug + i * NU];
-				#pragma unroll
-				for (int i = 0; i < NiUA; i++) iuacc[i] = a.IntegerUnitAccessories[ug + i * NU];
-				slot_barrier<UPSP>(slot);
+				for (int u = 0; u < UPT; u++)
+				{
+					const size_t g = ug_of(u);
+					#pragma unroll
+					for (int i = 0; i < UD; i++)   x[u][i]     = a.ActualState[g + i * NU];
+					#pragma unroll
+					for (int i = 0; i < NUP; i++)  upar[u][i]  = (resumed ? a.SliceUnitParameters : a.UnitParameters)[g + i * NU];
+					#pragma unroll
+					for (int i = 0; i < NUA; i++)  uacc[u][i]  = a.UnitAccessories[g + i * NU];
+					#pragma unroll
+					for (int i = 0; i < NiUA; i++) iuacc[u][i] = a.IntegerUnitAccessories[g + i * NU];
+				}
+				slot_barrier<TPS>(slot);
 
-				if (is_unit && !resumed) Sys::Initialization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-				slot_barrier<UPSP>(slot);
+				if (!resumed)
+				{
+					#pragma unroll
+					for (int u = 0; u < UPT; u++)
+						if (is_unit_of(u)) Sys::Initialization(gsys, unit_of(u), S.dense_index, S.t, S.dt, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+				}
+				slot_barrier<TPS>(slot);
 				if (a.SliceMode == 1)
 				{
 					if (unit == 0) S.slice_time = S.t + a.SliceFraction * (S.td[1] - S.t);
-					slot_barrier<UPSP>(slot);
+					slot_barrier<TPS>(slot);
 				}
 				if (NE > 0)
 				{
-					if (is_unit) Sys::EventFunction(gsys, unit, ev, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-					slot_barrier<UPSP>(slot);
+					#pragma unroll
+					for (int u = 0; u < UPT; u++)
+						if (is_unit_of(u)) Sys::EventFunction(gsys, unit_of(u), ev[u], S.t, S.dt, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+					slot_barrier<TPS>(slot);
 				}
 				if (DENSE && !resumed)   // first point of the phase (Solver.cuh:2480-2497), stored without looking at the index
 				{
 					const int di = S.dense_index;
 					if (di < a.DenseCapacity)
 					{
-						if (is_unit)
-						{
-							#pragma unroll
-							for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
-						}
+						#pragma unroll
+						for (int u = 0; u < UPT; u++)
+							if (is_unit_of(u))
+							{
+								#pragma unroll
+								for (int i = 0; i < UD; i++) a.DenseOutputStates[ug_of(u) + i * NU + (size_t)di * NU * UD] = x[u][i];
+							}
 						if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
 					}
-					slot_barrier<UPSP>(slot);
+					slot_barrier<TPS>(slot);
 					if (unit == 0) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
-					slot_barrier<UPSP>(slot);
+					slot_barrier<TPS>(slot);
 				}
 				dt_new = resumed ? a.SliceDt[sys] : a.InitialTimeStep;
 				attempted = 0;  accepted = 0;
 				have = true;
 			}
-			else if (!dry) slot_barrier<UPSP>(slot);      // skipped: everybody has read the queue position before unit 0 asks for the next one
+			else if (!dry) slot_barrier<TPS>(slot);      // skipped: everybody has read the queue position before unit 0 asks for the next one
 		}
 		// leave when no slot has a system and none can get one any more (a slot that skipped a system takes another next trip)
 		if (MMA) { if (!__syncthreads_or((have || !dry) ? 1 : 0)) break; }
 		else if (!have) { if (dry) break; else continue; }
-		const bool live = have && is_unit;
+		const bool live = have && is_unit;      // the thread's first unit
+		auto live_of = [&](int u) { return have && is_unit_of(u); };
 
 		// right-hand side of this unit including the coupling term
-		auto rhs = [&](P* F, P* X, P T) {
-			P cpt[AtLeastOne<NC>::value], cpf[AtLeastOne<NC>::value];
+		auto rhs = [&](P (*F)[UD], P (*X)[UD], P T) {
+			P cpt[AtLeastOne<NC>::value], cpf[UPT][AtLeastOne<NC>::value];
 			if (MMA)
 			{
 				// all 8 systems of the block at once on the tensor cores; two block barriers
 				if (live)
 				{
-					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
+					Sys::OdeFunction(gsys, unit, F[0], X[0], T, upar[0], S.spar, s_gpar, s_igpar, uacc[0], iuacc[0], S.sacc, S.isacc, cpt, cpf[0]);
 					#pragma unroll
 					for (int k = 0; k < NC; k++)
 					{
@@ -489,35 +517,39 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 						P v = 0;
 						#pragma unroll
 						for (int g = 0; g < G::KG; g++) v += s_vpart[((k * G::KG + g) * G::NCOL + slot) * G::VS + unit];
-						const P add = S.strength[k] * cpf[k] * v;
+						const P add = S.strength[k] * cpf[0][k] * v;
 						const int ci = s_cidx[k];
 						#pragma unroll
-						for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
+						for (int j = 0; j < UD; j++) if (j == ci) F[0][j] += add;
 					}
 				}
 			}
 			else
 			{
 				// one slot barrier
-				if (live)
-				{
-					Sys::OdeFunction(gsys, unit, F, X, T, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc, cpt, cpf);
-					#pragma unroll
-					for (int k = 0; k < NC; k++) S.cpt[buf][k][unit] = cpt[k];
-				}
-				slot_barrier<UPSP>(slot);
-				if (live)
-				{
-					#pragma unroll
-					for (int k = 0; k < NC; k++)
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u))
 					{
-						const P v = coupling_value<P, UPS, CBW, CCI>(matrix + k * MSTRIDE, S.cpt[buf][k], unit);
-						const P add = S.strength[k] * cpf[k] * v;
-						const int ci = s_cidx[k];
+						Sys::OdeFunction(gsys, unit_of(u), F[u], X[u], T, upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc, cpt, cpf[u]);
 						#pragma unroll
-						for (int j = 0; j < UD; j++) if (j == ci) F[j] += add;
+						for (int k = 0; k < NC; k++) (BIG ? s_cptbig + (size_t)((slot * 2 + buf) * NC + k) * UPSP : S.cpt[buf][k])[unit_of(u)] = cpt[k];
 					}
-				}
+				slot_barrier<TPS>(slot);
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u))
+					{
+						#pragma unroll
+						for (int k = 0; k < NC; k++)
+						{
+							const P v = coupling_value<P, UPS, CBW, CCI>(matrix + k * MSTRIDE, BIG ? s_cptbig + (size_t)((slot * 2 + buf) * NC + k) * UPSP : S.cpt[buf][k], unit_of(u));
+							const P add = S.strength[k] * cpf[u][k] * v;
+							const int ci = s_cidx[k];
+							#pragma unroll
+							for (int j = 0; j < UD; j++) if (j == ci) F[u][j] += add;
+						}
+					}
 				buf ^= 1;
 			}
 		};
@@ -535,36 +567,44 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		attempted++;
 		bool update = true, finite = true;
 
-		P xn[UD];
+		P xn[UPT][UD];
 		if (ALG == kAlgRK4)
 		{
 			// Steppers.cuh:2015-2227 (expression shapes of the coupled stepper)
-			P X[UD], k[UD];
+			P X[UPT][UD], k[UPT][UD];
 			rhs(xn, x, t);
 			P T = t + P(0.5) * dt;
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + xn[i] * P(0.5) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + xn[u][i] * P(0.5) * dt;
 			rhs(k, X, T);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) { xn[i] += 2 * k[i]; X[i] = x[i] + k[i] * P(0.5) * dt; }
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) { xn[u][i] += 2 * k[u][i]; X[u][i] = x[u][i] + k[u][i] * P(0.5) * dt; }
 			rhs(k, X, T);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) { xn[i] += P(2.0) * k[i]; X[i] = x[i] + k[i] * dt; }
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) { xn[u][i] += P(2.0) * k[u][i]; X[u][i] = x[u][i] + k[u][i] * dt; }
 			T = t + dt;
 			rhs(k, X, T);
 			#pragma unroll
-			for (int i = 0; i < UD; i++)
-			{
-				xn[i] = x[i] + dt * (xn[i] + k[i]) * P(1.0 / 6.0);
-				finite = finite && Num<P>::finite(xn[i]);
-			}
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++)
+				{
+					xn[u][i] = x[u][i] + dt * (xn[u][i] + k[u][i]) * P(1.0 / 6.0);
+					finite = finite && (Num<P>::finite(xn[u][i]) || !live_of(u));
+				}
 			// per-system "all finite" (ErrorControllers.cuh:421-441): not finite => message, terminate, step not committed
-			int f = finite || !live;
+			int f = finite || (UPT == 1 && !live);
 			f = __all_sync(0xffffffffu, f);
 			if (WPS > 1)
 			{
 				if (lane == 0) S.red_flags[wis] = f;
-				slot_barrier<UPSP>(slot);
+				slot_barrier<TPS>(slot);
 				#pragma unroll
 				for (int w = 0; w < WPS; w++) f = f && S.red_flags[w];
 			}
@@ -578,38 +618,55 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		else
 		{
 			// Steppers.cuh:2228-2544
-			P X[UD], k1[UD], k2[UD], k3[UD], k4[UD], k5[UD], k6[UD], err[UD];
+			P X[UPT][UD], k1[UPT][UD], k2[UPT][UD], k3[UPT][UD], k4[UPT][UD], k5[UPT][UD], k6[UPT][UD];
 			rhs(k1, x, t);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A21)) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_A21)) * dt;
 			rhs(k2, X, t + ck<P>(CK_C2) * dt);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A31) + k2[i] * ck<P>(CK_A32)) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_A31) + k2[u][i] * ck<P>(CK_A32)) * dt;
 			rhs(k3, X, t + ck<P>(CK_C3) * dt);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A41) + k2[i] * ck<P>(CK_A42) + k3[i] * ck<P>(CK_A43)) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_A41) + k2[u][i] * ck<P>(CK_A42) + k3[u][i] * ck<P>(CK_A43)) * dt;
 			rhs(k4, X, t + ck<P>(CK_C4) * dt);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A51) + k2[i] * ck<P>(CK_A52) + k3[i] * ck<P>(CK_A53) + k4[i] * ck<P>(CK_A54)) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_A51) + k2[u][i] * ck<P>(CK_A52) + k3[u][i] * ck<P>(CK_A53) + k4[u][i] * ck<P>(CK_A54)) * dt;
 			rhs(k5, X, t + dt);
 			#pragma unroll
-			for (int i = 0; i < UD; i++) X[i] = x[i] + (k1[i] * ck<P>(CK_A61) + k2[i] * ck<P>(CK_A62) + k3[i] * ck<P>(CK_A63) + k4[i] * ck<P>(CK_A64) + k5[i] * ck<P>(CK_A65)) * dt;
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) X[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_A61) + k2[u][i] * ck<P>(CK_A62) + k3[u][i] * ck<P>(CK_A63) + k4[u][i] * ck<P>(CK_A64) + k5[u][i] * ck<P>(CK_A65)) * dt;
 			rhs(k6, X, t + ck<P>(CK_C6) * dt);
 
 			// per-unit error ratio q = max_i err_i/tol_i, accept flag, finite flag (ErrorControllers.cuh:483-500)
 			P q = P(0);
 			#pragma unroll
-			for (int i = 0; i < UD; i++)
+			for (int u = 0; u < UPT; u++)
 			{
-				xn[i] = x[i] + (k1[i] * ck<P>(CK_B1) + k3[i] * ck<P>(CK_B3) + k4[i] * ck<P>(CK_B4) + k6[i] * ck<P>(CK_B6)) * dt;
-				const P e = k1[i] * ck<P>(CK_E1) + k3[i] * ck<P>(CK_E3) + k4[i] * ck<P>(CK_E4) + k5[i] * ck<P>(CK_E5) + k6[i] * ck<P>(CK_E6);
-				err[i] = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
-				finite = finite && Num<P>::finite(xn[i]) && Num<P>::finite(err[i]);
-				const P tol = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[i]), fabs(x[i])), a.AbsoluteTolerance[i]);
-				update = update && (err[i] < tol);
-				q = fmax(q, err[i] / tol);
+				P qu = P(0);
+				bool update_u = true, finite_u = true;
+				#pragma unroll
+				for (int i = 0; i < UD; i++)
+				{
+					xn[u][i] = x[u][i] + (k1[u][i] * ck<P>(CK_B1) + k3[u][i] * ck<P>(CK_B3) + k4[u][i] * ck<P>(CK_B4) + k6[u][i] * ck<P>(CK_B6)) * dt;
+					const P e = k1[u][i] * ck<P>(CK_E1) + k3[u][i] * ck<P>(CK_E3) + k4[u][i] * ck<P>(CK_E4) + k5[u][i] * ck<P>(CK_E5) + k6[u][i] * ck<P>(CK_E6);
+					const P err = dt * fabs(e) + ck<P>(CK_ERRFLOOR);
+					finite_u = finite_u && Num<P>::finite(xn[u][i]) && Num<P>::finite(err);
+					const P tol = fmax(a.RelativeTolerance[i] * fmax(fabs(xn[u][i]), fabs(x[u][i])), a.AbsoluteTolerance[i]);
+					update_u = update_u && (err < tol);
+					qu = fmax(qu, err / tol);
+				}
+				if (!live_of(u)) { qu = P(0); update_u = true; finite_u = true; }
+				q = fmax(q, qu);  update = update && update_u;  finite = finite && finite_u;
 			}
-			if (!live) { q = P(0); update = true; finite = true; }
 			// slot-wide reduction: shuffles inside the warp, one word per warp across warps
 			#pragma unroll
 			for (int o = 16; o > 0; o >>= 1) q = fmax(q, __shfl_xor_sync(0xffffffffu, q, o));
@@ -617,7 +674,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			if (WPS > 1)
 			{
 				if (lane == 0) { S.red_ratio[wis] = q;  S.red_flags[wis] = flags; }
-				slot_barrier<UPSP>(slot);
+				slot_barrier<TPS>(slot);
 				#pragma unroll
 				for (int w = 0; w < WPS; w++) { q = fmax(q, S.red_ratio[w]);  flags &= S.red_flags[w]; }
 			}
@@ -662,23 +719,27 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		if (MMA && !have) { update = false;  terminated = false; }     // idle slot: no commit, no store
 
 		// ---- events: the earliest secant estimate over all units and events (EventHandling.cuh:216-268) ----
-		P evn[AtLeastOne<NE>::value];
+		P evn[UPT][AtLeastOne<NE>::value];
 		if (NE > 0)
 		{
-			if (live && !terminated)
-				Sys::EventFunction(gsys, unit, evn, t + dt, dt_new, S.td, xn, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
 			P dt_event = dt;
 			int corrected = 0;
-			if (live && update && !terminated)
+			#pragma unroll
+			for (int u = 0; u < UPT; u++)
 			{
-				#pragma unroll
-				for (int i = 0; i < NE; i++)
+				if (live_of(u) && !terminated)
+					Sys::EventFunction(gsys, unit_of(u), evn[u], t + dt, dt_new, S.td, xn[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+				if (live_of(u) && update && !terminated)
 				{
-					const P et = a.EventTolerance[i];
-					if (((ev[i] > et) && (evn[i] < -et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (evn[i] > et) && (a.EventDirection[i] >= 0)))
+					#pragma unroll
+					for (int i = 0; i < NE; i++)
 					{
-						dt_event = fmin(dt_event, -ev[i] / (evn[i] - ev[i]) * dt);
-						corrected = 1;
+						const P et = a.EventTolerance[i];
+						if (((ev[u][i] > et) && (evn[u][i] < -et) && (a.EventDirection[i] <= 0)) || ((ev[u][i] < -et) && (evn[u][i] > et) && (a.EventDirection[i] >= 0)))
+						{
+							dt_event = fmin(dt_event, -ev[u][i] / (evn[u][i] - ev[u][i]) * dt);
+							corrected = 1;
+						}
 					}
 				}
 			}
@@ -688,7 +749,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			if (WPS > 1)
 			{
 				if (lane == 0) { S.red_evdt[wis] = dt_event;  S.red_corrected[wis] = corrected; }
-				slot_barrier<UPSP>(slot);
+				slot_barrier<TPS>(slot);
 				#pragma unroll
 				for (int w = 0; w < WPS; w++) { dt_event = fmin(dt_event, S.red_evdt[w]);  corrected |= S.red_corrected[w]; }
 			}
@@ -708,25 +769,33 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			accepted++;
 			if (unit == 0) S.t = t + dt;
 			#pragma unroll
-			for (int i = 0; i < UD; i++) x[i] = xn[i];
-			slot_barrier<UPSP>(slot);
-			if (live) Sys::ActionAfterSuccessfulTimeStep(gsys, unit, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-			slot_barrier<UPSP>(slot);
+			for (int u = 0; u < UPT; u++)
+				#pragma unroll
+				for (int i = 0; i < UD; i++) x[u][i] = xn[u][i];
+			slot_barrier<TPS>(slot);
+			#pragma unroll
+			for (int u = 0; u < UPT; u++)
+				if (live_of(u)) Sys::ActionAfterSuccessfulTimeStep(gsys, unit_of(u), S.udt, S.t, S.dt, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+			slot_barrier<TPS>(slot);
 			if (NE > 0)
 			{
-				if (live)
-				{
-					#pragma unroll
-					for (int i = 0; i < NE; i++)
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u))
 					{
-						const P et = a.EventTolerance[i];
-						if (((ev[i] > et) && (fabs(evn[i]) < et) && (a.EventDirection[i] <= 0)) || ((ev[i] < -et) && (fabs(evn[i]) < et) && (a.EventDirection[i] >= 0)))
-							Sys::ActionAfterEventDetection(gsys, unit, i, S.udt, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
+						#pragma unroll
+						for (int i = 0; i < NE; i++)
+						{
+							const P et = a.EventTolerance[i];
+							if (((ev[u][i] > et) && (fabs(evn[u][i]) < et) && (a.EventDirection[i] <= 0)) || ((ev[u][i] < -et) && (fabs(evn[u][i]) < et) && (a.EventDirection[i] >= 0)))
+								Sys::ActionAfterEventDetection(gsys, unit_of(u), i, S.udt, S.t, S.dt, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+						}
 					}
-				}
-				slot_barrier<UPSP>(slot);
-				if (live) Sys::EventFunction(gsys, unit, ev, S.t, dt_new, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-				slot_barrier<UPSP>(slot);
+				slot_barrier<TPS>(slot);
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u)) Sys::EventFunction(gsys, unit_of(u), ev[u], S.t, dt_new, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
+				slot_barrier<TPS>(slot);
 			}
 		}
 		const bool user_stop = update && (S.udt == 1);
@@ -743,20 +812,22 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 			}
 			if (store)
 			{
-				if (live)
-				{
-					#pragma unroll
-					for (int i = 0; i < UD; i++) a.DenseOutputStates[ug + i * NU + (size_t)di * NU * UD] = x[i];
-				}
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u))
+					{
+						#pragma unroll
+						for (int i = 0; i < UD; i++) a.DenseOutputStates[ug_of(u) + i * NU + (size_t)di * NU * UD] = x[u][i];
+					}
 				if (unit == 0) a.DenseOutputTimeInstances[sys + (size_t)di * a.NS] = S.t;
 			}
-			slot_barrier<UPSP>(slot);
+			slot_barrier<TPS>(slot);
 			if (unit == 0)
 			{
 				if (store) { S.dense_index = di + 1;  S.dense_skipped = 0;  S.dense_next_time = fmin(S.t + a.DenseOutputMinimumTimeStep, S.td[1]); }
 				else if (update) S.dense_skipped++;
 			}
-			slot_barrier<UPSP>(slot);
+			slot_barrier<TPS>(slot);
 		}
 
 		if (update && (end_reached || user_stop)) terminated = true;
@@ -765,25 +836,35 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 		// ---- end of the phase for this system (Solver.cuh:2812-2887), or of its pilot slice ------------------------
 		if (terminated || paused)
 		{
-			slot_barrier<UPSP>(slot);
-			if (live && !paused) Sys::Finalization(gsys, unit, S.dense_index, S.t, S.dt, S.td, x, upar, S.spar, s_gpar, s_igpar, uacc, iuacc, S.sacc, S.isacc);
-			slot_barrier<UPSP>(slot);
-			if (live)
+			slot_barrier<TPS>(slot);
+			if (!paused)
 			{
 				#pragma unroll
-				for (int i = 0; i < UD; i++)   a.ActualState[ug + i * NU] = x[i];
-				#pragma unroll
-				for (int i = 0; i < NUA; i++)  a.UnitAccessories[ug + i * NU] = uacc[i];
-				#pragma unroll
-				for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[ug + i * NU] = iuacc[i];
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u)) Sys::Finalization(gsys, unit_of(u), S.dense_index, S.t, S.dt, S.td, x[u], upar[u], S.spar, s_gpar, s_igpar, uacc[u], iuacc[u], S.sacc, S.isacc);
 			}
+			slot_barrier<TPS>(slot);
+			#pragma unroll
+			for (int u = 0; u < UPT; u++)
+				if (live_of(u))
+				{
+					const size_t g = ug_of(u);
+					#pragma unroll
+					for (int i = 0; i < UD; i++)   a.ActualState[g + i * NU] = x[u][i];
+					#pragma unroll
+					for (int i = 0; i < NUA; i++)  a.UnitAccessories[g + i * NU] = uacc[u][i];
+					#pragma unroll
+					for (int i = 0; i < NiUA; i++) a.IntegerUnitAccessories[g + i * NU] = iuacc[u][i];
+				}
 			if (paused)
 			{
-				if (live)
-				{
-					#pragma unroll
-					for (int i = 0; i < NUP; i++) a.SliceUnitParameters[ug + i * NU] = upar[i];
-				}
+				#pragma unroll
+				for (int u = 0; u < UPT; u++)
+					if (live_of(u))
+					{
+						#pragma unroll
+						for (int i = 0; i < NUP; i++) a.SliceUnitParameters[ug_of(u) + i * NU] = upar[u][i];
+					}
 				if (unit < NSP) a.SliceSystemParameters[sys + unit * a.NS] = S.spar[unit];
 				if (unit < NC)  a.SliceCouplingStrength[sys + unit * a.NS] = S.strength[unit];
 			}
@@ -800,7 +881,7 @@ perblock_kernel(const __grid_constant__ PerBlockArgs<P, UD, NE> a)
 				if (a.SliceMode == 1) a.SlicePaused[sys] = paused ? 1 : 0;
 				if (paused) { a.SliceDt[sys] = dt_new;  a.SliceLastDt[sys] = S.dt;  a.SliceDenseNext[sys] = S.dense_next_time;  a.SliceSkipped[sys] = S.dense_skipped; }
 			}
-			slot_barrier<UPSP>(slot);
+			slot_barrier<TPS>(slot);
 			have = false;
 		}
 	}
@@ -813,9 +894,12 @@ template <class Sys, class P, int UPS, int UD, int NC, int CBW, int CCI, int NUP
 struct PerBlockLauncher
 {
 	static constexpr int UPSP = ((UPS + 31) / 32) * 32;
+	// systems of more than 1024 units: every thread integrates UPT units (the reference's multiple block launches), one system per block
+	static constexpr int UPT = (UPSP + 1023) / 1024;
+	static constexpr int TPS = slot_threads(UPS, UPT);      // threads of a slot
 	// slots per block: fill 512 threads (one block per SM at <= 128 registers), at most 15 named barriers
-	static constexpr int SPBK = (MPGOS_B200_COUPLED_THREADS / UPSP) < 1 ? 1 : ((MPGOS_B200_COUPLED_THREADS / UPSP) > 15 ? 15 : (MPGOS_B200_COUPLED_THREADS / UPSP));
-	static_assert(UPSP <= 1024, "UnitsPerSystem above 1024 would need several threads' worth of units per thread (not built)");
+	static constexpr int SPBK = (MPGOS_B200_COUPLED_THREADS / TPS) < 1 ? 1 : ((MPGOS_B200_COUPLED_THREADS / TPS) > 15 ? 15 : (MPGOS_B200_COUPLED_THREADS / TPS));
+	static_assert(UPT <= 4, "UnitsPerSystem above 4096: not built");
 	static_assert(NSP <= 32 && NSA <= 32 && NiSA <= 32 && NC <= 32, "system-scope arrays are staged by the first warp");
 
 	// tensor-core coupling: dense FP64 matrices shared by all systems, whole-warp systems, 8 systems x UPS threads <= 512
@@ -835,10 +919,12 @@ struct PerBlockLauncher
 	template <int SLOTS, bool MMA>
 	static int enqueue(const mpgos_coupled_launch* L, const PerBlockArgs<P, UD, NE>& a, cudaStream_t stream)
 	{
-		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA>;
+		auto kernel = perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, DENSE, ALG, SLOTS, MMA, MMA ? 1 : UPT>;
 		using G = typename MmaGeometryFor<P, MMA ? UPS : 32, MMA ? SLOTS : 8>::type;
 		const size_t extra = MMA ? (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
-		size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * (MMA ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
+		constexpr bool BIG = !MMA && UPT > 1;
+		const size_t big = BIG ? sizeof(P) * (size_t)SLOTS * 2 * NC * UPSP + 16 : 0;      // coupling terms of a system of more than 1024 units
+		size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * (MMA ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16 + big;
 		PerBlockArgs<P, UD, NE> args = a;
 		args.MatrixInGlobal = 0;
 		if (smem > kDynamicSharedLimit)
@@ -852,7 +938,7 @@ struct PerBlockLauncher
 		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return (int)e;
 		int per_sm = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SLOTS * UPSP, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SLOTS * (MMA ? UPSP : TPS), smem);
 		if (e != cudaSuccess) return (int)e;
 		if (per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
 		int grid = (a.Active + SLOTS - 1) / SLOTS;
@@ -894,14 +980,14 @@ struct PerBlockLauncher
 			args.SliceUnitParameters = pbase;  args.SliceSystemParameters = pbase + (size_t)NUP * L->desc.NS * UPS;
 			args.SliceCouplingStrength = args.SliceSystemParameters + (size_t)NSP * L->desc.NS;
 			args.SliceMode = 1;  args.SliceFraction = P(0.1);
-			kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
+			kernel<<<grid, SLOTS * (MMA ? UPSP : TPS), smem, stream>>>(args);
 			e = cudaGetLastError();
 			if (e == cudaSuccess) e = order_by_cost();
 			if (e == cudaSuccess) e = cudaMemsetAsync(L->d_WorkQueue, 0, sizeof(unsigned int), stream);
 			if (e != cudaSuccess) return (int)e;
 			args.SliceMode = 2;  args.DispatchOrder = L->d_DispatchOrder;
 		}
-		kernel<<<grid, SLOTS * UPSP, smem, stream>>>(args);
+		kernel<<<grid, SLOTS * (MMA ? UPSP : TPS), smem, stream>>>(args);
 		return (int)cudaGetLastError();
 	}
 

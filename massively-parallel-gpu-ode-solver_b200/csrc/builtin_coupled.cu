@@ -30,6 +30,8 @@ static const CoupledBuiltinEntry kEntries[] = {
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 14, 0, 0, kAlgRKCK45, true),
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 32, 0, 0, kAlgRKCK45, true),      // full matrices, 2 couplings, events: the tensor-core path with everything on
 	COUPLED_ENTRY("duffing_ring", DuffingRing, 192, 0, 0, kAlgRKCK45, true),     // two full 192 x 192 matrices (576 KB): more than shared memory holds -> read from global memory
+	COUPLED_ENTRY("duffing_ring", DuffingRing, 1500, 1, 1, kAlgRKCK45, true),     // more than 1024 units: two units per thread (768 threads), coupling terms in dynamic shared memory
+	COUPLED_ENTRY("duffing_ring", DuffingRing, 2500, 2, 0, kAlgRK4, false),        // three units per thread (864 threads), banded matrices
 	COUPLED_ENTRY("parameter_drift", ParameterDrift, 16, 0, 0, kAlgRKCK45, false),      // test system: callbacks write the parameter arrays
 	// FP32 instantiations (dense coupling on the tensor cores as 3xTF32 for UPS 32 / 64)
 	COUPLED_ENTRY_P("bubble_ensemble", BubbleEnsemble, float, 16, 0, 0, kAlgRKCK45, false),

@@ -140,6 +140,10 @@ int route(const char* system, int ups, int cbw, int cci, int algorithm, int ndo,
 	}
 	if (!std::strcmp(system, "duffing_ring") && ups == 32 && cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 32, 0, 0>, P>(algorithm, ndo, b, o, shape);
 	if (!std::strcmp(system, "duffing_ring") && ups == 192 && cbw == 0 && cci == 0) return dispatch<DuffingRing<P, 192, 0, 0>, P>(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 50 && cbw == 1 && cci == 1) return dispatch<DuffingRing<P, 50, 1, 1>, P>(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 70 && cbw == 2 && cci == 0) return dispatch<DuffingRing<P, 70, 2, 0>, P>(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 1500 && cbw == 1 && cci == 1) return dispatch<DuffingRing<P, 1500, 1, 1>, P>(algorithm, ndo, b, o, shape);
+	if (!std::strcmp(system, "duffing_ring") && ups == 2500 && cbw == 2 && cci == 0) return dispatch<DuffingRing<P, 2500, 2, 0>, P>(algorithm, ndo, b, o, shape);
 	if (!std::strcmp(system, "duffing_ring") && ups == 14)
 	{
 		if (cbw == 1 && cci == 1) return dispatch<DuffingRing<P, 14, 1, 1>, P>(algorithm, ndo, b, o, shape);

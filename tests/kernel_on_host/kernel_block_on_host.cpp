@@ -43,6 +43,9 @@ enum { UPS = KOH_UPS, CBW = KOH_CBW, CCI = KOH_CCI, UD = Sys::UD, NC = Sys::NC, 
 #ifndef KOH_BLOCKS
 #define KOH_BLOCKS 2
 #endif
+#ifndef KOH_UPT
+#define KOH_UPT 1      // units per thread (the kernel's UPT: systems of more than 1024 units on the device; here any UPS)
+#endif
 
 extern "C" void ref_coupled_shape(oracle_coupled_shape* s)
 {
@@ -54,7 +57,7 @@ extern "C" int ref_coupled_capacity() { return 1 << 20; }
 static void launch(const mpgos_b200::PerBlockArgs<P, UD, NE>& args)
 {
 	using namespace mpgos_b200;
-	const int threads = KOH_SLOTS * UPSP;
+	const int threads = KOH_SLOTS * slot_threads(UPS, KOH_UPT);
 	*args.WorkQueue = 0;
 	for (int block = 0; block < KOH_BLOCKS; block++)
 	{
@@ -62,7 +65,7 @@ static void launch(const mpgos_b200::PerBlockArgs<P, UD, NE>& args)
 		for (int t = 0; t < threads; t++)
 			pool.emplace_back([=]() {
 				host_threadIdx.x = (unsigned)t;  host_blockIdx.x = (unsigned)block;  host_blockDim.x = (unsigned)threads;  host_gridDim.x = KOH_BLOCKS;
-				perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, (KOH_NDO > 0), KOH_ALG, KOH_SLOTS, (KOH_MMA != 0)>(args);
+				perblock_kernel<Sys, P, UPS, UD, NC, CBW, CCI, NUP, NSP, NGP, NiGP, NUA, NiUA, NSA, NiSA, NE, (KOH_NDO > 0), KOH_ALG, KOH_SLOTS, (KOH_MMA != 0), KOH_UPT>(args);
 			});
 		for (auto& th : pool) th.join();
 	}
@@ -115,7 +118,8 @@ extern "C" int ref_coupled_run(const oracle_coupled_buffers* b, const oracle_cou
 		// dynamic shared memory the launcher would ask for (PerBlockLauncher::enqueue); the shim's buffer must hold it
 		using G = typename MmaGeometryFor<P, (KOH_MMA != 0) ? UPS : 32, (KOH_MMA != 0) ? KOH_SLOTS : 8>::type;
 		const size_t extra = (KOH_MMA != 0) ? (size_t)NC * G::NCOL * G::CS * G::CCOPIES + (size_t)NC * G::KG * G::NCOL * G::VS : 0;
-		const size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * ((KOH_MMA != 0) ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16;
+		const size_t smem = sizeof(P) * ((size_t)packed_matrix_elements(UPS, NC, CBW, CCI) * ((KOH_MMA != 0) ? G::MCOPIES : 1) + extra + NGP) + sizeof(int) * NiGP + 16
+		                  + ((KOH_UPT > 1) ? sizeof(P) * (size_t)KOH_SLOTS * 2 * NC * UPSP + 16 : 0);
 		if (smem > sizeof(g_dynamic_shared)) return 2;
 	}
 

@@ -306,6 +306,31 @@ def test_coupling_matrices_larger_than_shared_memory_are_read_from_global_memory
     assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
 
 
+@pytest.mark.parametrize("ups,cbw,cci,rk4", [(1500, 1, 1, False), (2500, 2, 0, True)])
+def test_systems_of_more_than_1024_units(ups, cbw, cci, rk4, pkg, oracle):
+    """More units than a block has threads: every thread integrates two (1500 units on 768 threads) or three (2500 units on 864
+    threads) units of its system -- the reference's "multiple block launches" (Solver.cuh:1508, 2215).  Rings of Duffing oscillators
+    with events, unit and system accessories, dense output (RKCK45 case), banded-circulant and banded matrices; against the checker:
+    RK4 to rounding (FMA contraction), RKCK45 with the same step counts."""
+    WC = importlib.import_module(pkg.__name__ + ".workloads_coupled")
+    wl = WC.duffing_ring(NS=4, CBW=cbw, CCI=cci, UPS=ups, ndo=0 if rk4 else 40, algorithm=WC.RK4 if rk4 else WC.RKCK45, TPB=1024, SPB=1)
+    wl.buffers.TimeDomain[1, :] = 6.0
+    rng = np.random.default_rng(ups)
+    wl.buffers.ActualState[...] = rng.uniform(-3.0, 3.0, wl.buffers.ActualState.shape)
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=2, host_threads=8)
+    out, att, acc = pkg.run_coupled_workload(wl, phases=2)
+    print(f"[parity ring {ups} units] state {rel_err(out.ActualState, ref.ActualState).max():.2e}  steps {att.tolist()} vs {ratt.tolist()}")
+    assert np.abs(att - ratt).max() <= (0 if rk4 else 2) and int(ratt.min()) > 20
+    assert np.array_equal(out.IntegerUnitAccessories, ref.IntegerUnitAccessories)
+    assert np.array_equal(out.IntegerSystemAccessories, ref.IntegerSystemAccessories)
+    assert rel_err(out.ActualTime, ref.ActualTime).max() < 1e-9
+    assert rel_err(out.ActualState, ref.ActualState).max() < 1e-8
+    assert rel_err(out.UnitAccessories, ref.UnitAccessories).max() < 1e-8
+    assert rel_err(out.SystemAccessories, ref.SystemAccessories).max() < 1e-6
+    if not rk4 and np.array_equal(att, ratt):
+        assert np.array_equal(out.DenseIndex, ref.DenseIndex)
+
+
 def test_pilot_slice_keeps_parameter_writes_of_the_callbacks(pkg):
     """Callbacks may write unit parameters, system parameters and coupling strengths; in the reference those live in registers /
     shared memory until the phase ends.  The pilot slice pauses systems in mid-phase: with the mechanism forced (DispatchOrder = 2)

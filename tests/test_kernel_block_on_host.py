@@ -109,6 +109,19 @@ def test_block_kernel_source_wide_systems_and_tensor_core_variant(build, ups, ns
     assert rel_err(out.ActualState, ref.ActualState) < 1e-12
 
 
+@pytest.mark.parametrize("build,ups,cbw,cci,alg", [("ring_u50_upt2", 50, 1, 1, "rkck45"), ("ring_u70_upt3", 70, 2, 0, "rk4")])
+def test_several_units_per_thread(build, ups, cbw, cci, alg, koh, WC, oracle):
+    """The kernel's UPT > 1 form -- thread t of a slot integrates units t, t + TPS, ... (on the device: systems of more than 1024
+    units, the reference's "multiple block launches") -- with 50 units on 32 threads and 70 units on 32 threads: events, unit and
+    system accessories, dense output, banded and banded-circulant matrices; against the checker, RK4 bit for bit."""
+    wl = WC.duffing_ring(NS=5, CBW=cbw, CCI=cci, UPS=ups, ndo=60, algorithm=WC.RK4 if alg == "rk4" else WC.RKCK45)
+    wl.buffers.TimeDomain[1, :] = 8.0
+    ref, ratt, racc = oracle.run_coupled_oracle(wl, phases=2)
+    out, att, acc = run_block_kernel_on_host(koh, oracle, build, wl, 2)
+    check_against_checker(build + "_" + alg, out, att, acc, ref, ratt, racc)
+    assert int(ratt.min()) > 20
+
+
 @pytest.mark.parametrize("name", ["ring_b1c1_rkck45", "ring_b0c1_rk4", "bubble_u16_rkck45"])
 def test_pilot_slice_and_cost_ordered_continuation_change_nothing(name, koh, WC, oracle):
     """SliceMode 1 (every system paused on its first accepted step past a tenth of the phase) followed by SliceMode 2 (the rest, in
