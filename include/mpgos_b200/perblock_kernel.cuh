@@ -17,6 +17,8 @@
 //    interleaved partial sums -- same terms as ComputeCouplingValue_* (Steppers.cuh:2551-2713), different summation order,
 //    results track the reference to rounding; 1 accumulator reproduces the reference's ascending single chain bit for bit;
 //  * slot refill: a slot that finishes its system takes the next system id from a device-side queue (persistent grid);
+//  * systems of more than 1024 units (the reference's ..._MultipleBlockLaunches kernels): UPT units per thread, thread t of the slot owns
+//    units t, t + TPS, t + 2 TPS, ... in [UPT][...] register arrays; their coupling terms live in dynamic shared memory (up to 4096 units);
 //  * TENSOR-CORE COUPLING (MMA variant; dense matrices shared by all systems, FP64, UPS = 32, 64 or 128): the column sums of the
 //    8 systems of a block (4 for UPS = 128) are ONE matrix product  V[UPS x 8] = M[UPS x UPS] . CPT[UPS x 8]  per stage, issued as
 //    mma.sync.m8n8k4.f64 (DMMA) by all warps of the block; the matrix sits in shared memory in fragment order.  The scalar
