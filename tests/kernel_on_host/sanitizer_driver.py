@@ -35,6 +35,10 @@ else:
     if case.startswith("bubble:"):
         ups, ns = map(int, case.split(":")[1:])
         wl = WC.bubble_ensemble(NS=ns, UPS=ups, amplitude=(0.2, 0.8))
+    elif case.startswith("ring:"):      # ring:UPS:CBW:CCI -- several units per thread (tests/test_kernel_block_on_host.py)
+        ups, cbw, cci = map(int, case.split(":")[1:])
+        wl = WC.duffing_ring(NS=5, CBW=cbw, CCI=cci, UPS=ups, ndo=60)
+        wl.buffers.TimeDomain[1, :] = 4.0
     else:
         tag, wl0, phases = make_coupled_cases(WC)[case]
         wl = copy.copy(wl0)

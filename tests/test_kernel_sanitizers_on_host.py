@@ -46,7 +46,8 @@ def run_under_tsan(runtime, build, case, halt=False, pilot_slice=False):
 
 
 @pytest.mark.parametrize("build,case", [("tsan_ring", "ring_b1c1_rkck45"), ("tsan_bubble_u64", "bubble:64:3"),
-                                        ("tsan_bubble_u32_mma", "bubble:32:5"), ("tsan_impact_refill", "perthread:impact_rkck45_f64")])
+                                        ("tsan_bubble_u32_mma", "bubble:32:5"), ("tsan_impact_refill", "perthread:impact_rkck45_f64"),
+                                        ("tsan_ring_u50_upt2", "ring:50:1:1")])      # two units per thread, coupling terms in dynamic shared memory
 def test_no_data_race_in_the_kernel_protocols(build, case, tsan):
     code, text = run_under_tsan(tsan, build, case)
     assert "identical to the checker's: True" in text, text[-3000:]
